@@ -1,0 +1,68 @@
+"""Pin the CPU oracle to the reference: replay the golden trajectories recorded from the UNMODIFIED reference
+(oracle/gen_golden.py) through oracle/quadswarm_oracle.py with the reference's own random streams.
+
+Tolerance: 1e-9 absolute/relative on float64 quantities (both sides are float64; differences come only from
+summation order inside numpy/LAPACK helpers); masks, dones and counters exact."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import replay
+from oracle.gen_golden import INFO_KEYS
+from quad_swarm_rl_b200.scenarios import create_scenario
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+FILES = sorted(glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
+TOL = dict(rtol=1e-9, atol=1e-9)
+
+
+def _make_scenario(mode, cfg, rng):
+    sc = create_scenario(mode, cfg.num_agents, room_dims=cfg.room_dims, rng=np.random.RandomState(0),
+                         ep_time=cfg.ep_time, use_obstacles=cfg.use_obstacles)
+    sc.rng = rng      # constructor draws (dynamic_formations) happen before the reference is seeded
+    return sc
+
+
+@pytest.mark.parametrize('path', FILES, ids=[os.path.basename(f)[4:-4] for f in FILES])
+def test_oracle_replays_reference(path):
+    g = np.load(path, allow_pickle=False)
+    out, env = replay.replay_golden(g, _make_scenario)
+    np.testing.assert_allclose(out['obs0'], g['obs0'], **TOL)
+    assert np.array_equal(out['dones'], g['dones'])
+    np.testing.assert_allclose(out['goals'], g['goals'], **TOL)
+    np.testing.assert_allclose(out['rewards'], g['rewards'], **TOL)
+    ref_infos = g['infos']
+    assert np.array_equal(np.isnan(out['infos']), np.isnan(ref_infos))
+    m = ~np.isnan(ref_infos)
+    # rew_action comes out as float32 in the reference when actions are float32; ours are float64 inputs
+    np.testing.assert_allclose(out['infos'][m], ref_infos[m], **TOL)
+    np.testing.assert_allclose(out['obs'], g['obs'], **TOL)
+    for k in ('pos', 'vel', 'rot', 'omega', 'thrust_rot_damp', 'thrust_cmds_damp', 'ou'):
+        np.testing.assert_allclose(out['state_' + k], g['state_' + k], err_msg=k, **TOL)
+    assert np.array_equal(out['state_on_floor'], g['state_on_floor'])
+    ref_stats = json.loads(str(g['ep_stats_json']))
+    assert len(ref_stats) == len(out['ep_stats'])
+    for (t0, s0), (t1, s1) in zip(ref_stats, out['ep_stats']):
+        assert t0 == t1
+        assert set(s0) == set(s1), set(s0) ^ set(s1)
+        for k in s0:
+            np.testing.assert_allclose(s1[k], s0[k], err_msg=k, **TOL)
+
+
+def test_golden_cases_exercise_the_rare_paths():
+    """The fixtures must actually contain collisions, obstacle hits, resets... otherwise the pin is hollow."""
+    seen = dict(quadcol=False, proximity=False, obst=False, crash=False, done=False)
+    for path in FILES:
+        g = np.load(path)
+        inf = g['infos']
+        k = {name: i for i, name in enumerate(INFO_KEYS)}
+        seen['quadcol'] |= bool(np.nanmin(inf[..., k['rewraw_quadcol']]) < 0)
+        seen['proximity'] |= bool(np.nanmin(inf[..., k['rew_proximity']]) < 0)
+        if not np.all(np.isnan(inf[..., k['rewraw_quadcol_obstacle']])):
+            seen['obst'] |= bool(np.nanmin(inf[..., k['rewraw_quadcol_obstacle']]) < 0)
+        seen['crash'] |= bool(np.nanmin(inf[..., k['rewraw_crash']]) < 0)
+        seen['done'] |= bool(g['dones'].any())
+    assert all(seen.values()), seen
