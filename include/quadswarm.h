@@ -1,0 +1,190 @@
+/*
+ * quadswarm.h — C ABI of the B200-native QuadSwarm vectorised environment step.
+ *
+ * The reference (Zhehui-Huang/quad-swarm-rl) has NO FFI: its hot path is a Python object protocol
+ * (SURVEY.md §8b).  This header is the boundary a binding would target; every entry point names the
+ * reference interface it replaces (paths under gym_art/quadrotor_multi/ unless stated otherwise).
+ * `quad_swarm_rl_b200/env.py` binds it with ctypes and re-exposes the reference's
+ * QuadrotorEnvMulti.reset()/step() surface on top; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - Plain C types only.  All *_dev pointers are caller-owned DEVICE memory on the handle's GPU,
+ *     *_host pointers are host memory.  Nothing is allocated per step.
+ *   - E = envs on this GPU, N = drones per env (<= 32), A = E*N agents, D = qs_obs_dim(),
+ *     M = qs_num_obstacles().  Agent index a = env*N + i everywhere.
+ *   - Work is enqueued on the cudaStream_t passed as `stream` (a void*; NULL = default stream);
+ *     only the *_host entry points synchronise.
+ *   - Return value: 0 = QS_OK, negative = error; qs_last_error() gives the message (thread-local).
+ *   - One handle per GPU; a handle is not thread-safe.
+ */
+#ifndef QUADSWARM_H_
+#define QUADSWARM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_OK 0
+#define QS_ERR_INVALID_ARG (-1)
+#define QS_ERR_UNSUPPORTED (-2)
+#define QS_ERR_CUDA (-3)
+
+#define QS_MAX_AGENTS 32
+
+/* obs_repr: quad_utils.py:30-34 (QUADS_OBS_REPR) */
+#define QS_OBS_XYZ_VXYZ_R_OMEGA 0       /* 18 floats */
+#define QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR 1 /* 19 floats */
+#define QS_OBS_XYZ_VXYZ_R_OMEGA_WALL 2  /* 24 floats */
+
+/* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a
+ * non-zero default or a CLI override (swarm_rl/env_wrappers/reward_shaping.py:7-16). */
+enum {
+    QS_REW_POS = 0, QS_REW_EFFORT, QS_REW_CRASH, QS_REW_ORIENT, QS_REW_SPIN,
+    QS_REW_QUADCOL_BIN, QS_REW_QUADCOL_BIN_SMOOTH_MAX, QS_REW_QUADCOL_BIN_OBST,
+    QS_NUM_REW_COEFF
+};
+
+/* per-agent raw reward terms written by qs_step when rew_terms_dev != NULL; these are the `rewraw_*`
+ * entries of infos[i]['rewards'] (quadrotor_single.py:68-85, quadrotor_multi.py:533-540), from which the
+ * host rebuilds every `rew_*` key by multiplying with the coefficient in force for that step. */
+enum {
+    QS_TERM_RAW_POS = 0,     /* rewraw_pos  = -dt*|goal-pos|  (== rewraw_main) */
+    QS_TERM_RAW_ACTION,      /* rewraw_action = -dt*|a| */
+    QS_TERM_RAW_CRASH,       /* rewraw_crash  = -dt*on_floor */
+    QS_TERM_RAW_ORIENT,      /* rewraw_orient */
+    QS_TERM_RAW_SPIN,        /* rewraw_spin */
+    QS_TERM_RAW_QUADCOL,     /* rewraw_quadcol (0 / -1) */
+    QS_TERM_PROXIMITY,       /* rew_proximity (already weighted: depends on quadcol_bin_smooth_max) */
+    QS_TERM_RAW_QUADCOL_OBST,/* rewraw_quadcol_obstacle (0 / -1) */
+    QS_NUM_TERMS
+};
+
+/* per-env episode statistics latched when an episode ends (quadrotor_multi.py:626-718) */
+enum {
+    QS_STAT_NUM_COLLISIONS = 0, QS_STAT_NUM_COLLISIONS_AFTER_SETTLE, QS_STAT_NUM_COLLISIONS_FINAL_5S,
+    QS_STAT_NUM_COLLISIONS_ROOM, QS_STAT_NUM_COLLISIONS_FLOOR, QS_STAT_NUM_COLLISIONS_WALL,
+    QS_STAT_NUM_COLLISIONS_CEILING, QS_STAT_NUM_COLLISIONS_OBST, QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE,
+    QS_STAT_NUM_COLLISIONS_OBST_3_5, QS_STAT_NUM_COLLISIONS_OBST_5, QS_STAT_EPISODES_DONE,
+    QS_NUM_ENV_STATS
+};
+/* per-agent episode statistics latched with them */
+enum {
+    QS_ASTAT_DIST_1S = 0, QS_ASTAT_DIST_3S, QS_ASTAT_DIST_5S,
+    QS_ASTAT_FLAGS,          /* bit0 agent_col_agent (1 = never collided after settle), bit1 agent_col_obst, bit2 reached_goal */
+    QS_NUM_AGENT_STATS
+};
+
+/* Construction arguments = the keyword set of QuadrotorEnvMulti.__init__ that the hot path reads
+ * (quadrotor_multi.py:24-41), with the fixed choices of the env factory
+ * (swarm_rl/env_wrappers/quad_utils.py:22-31: Crazyflie, raw control, default sensor noise,
+ * thrust_noise_ratio 0.05, use_numba=True) baked in. */
+typedef struct QsConfig {
+    int32_t num_envs;                /* E on this GPU */
+    int32_t num_agents;              /* N, 1..32 */
+    int32_t obs_repr;                /* QS_OBS_* */
+    int32_t neighbor_visible_num;    /* -1 = all others, 0 = none, else K (quadrotor_multi.py:47-50) */
+    int32_t use_obstacles;
+    int32_t num_obstacles;           /* M = int(density * area) (quadrotor_multi.py:128) */
+    int32_t use_downwash;
+    int32_t sense_noise;             /* 1 = 'default' (sensor_noise.py:70-76), 0 = bypass */
+    float obst_size;                 /* pillar diameter */
+    float room_dims[3];
+    float ep_time;                   /* seconds; ep_len = int(ep_time / 0.01) (quadrotor_single.py:158) */
+    float collision_hitbox_radius;   /* in arm lengths (quadrotor_multi.py:154) */
+    float collision_falloff_radius;  /* in arm lengths (quadrotor_multi.py:155) */
+    float approch_goal_metric;       /* scenario.approch_goal_metric (scenarios/base.py:31) */
+    int32_t env_id_offset;           /* global id of env 0 (multi-GPU shards: rank * E); keys the RNG */
+    uint64_t seed;
+} QsConfig;
+
+typedef struct QsHandle QsHandle;
+
+/* replaces QuadrotorEnvMulti.__init__ (quadrotor_multi.py:24-207) */
+int qs_create(const QsConfig* cfg, int device, QsHandle** out);
+int qs_destroy(QsHandle* h);
+const char* qs_last_error(void);
+
+int qs_obs_dim(const QsHandle* h);        /* D = S + 6K (+9), quadrotor_single.py:311-316 */
+int qs_num_envs(const QsHandle* h);
+int qs_num_agents(const QsHandle* h);
+int qs_num_obstacles(const QsHandle* h);
+int qs_ep_len(const QsHandle* h);
+
+/* replaces writes to env.unwrapped.rew_coeff (swarm_rl/env_wrappers/reward_shaping.py:55-61,110-118).
+ * coeffs_host[QS_NUM_REW_COEFF]; takes effect at the next qs_step. */
+int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host);
+
+/* Episode tables consumed by the next (auto-)reset of each env — what scenario.reset() and
+ * obst_generation_given_density() hand to QuadrotorEnvMulti.reset (quadrotor_multi.py:347-367).
+ * goals_dev [E,N,3]; spawn_dev [E,N,3] or NULL (spawn at the goal, :363-364); obst_xy_dev [E,M,2] or NULL.
+ * env_mask_dev [E] bytes or NULL (= all).  Tables persist until overwritten. */
+int qs_set_next_episode(QsHandle* h, const uint8_t* env_mask_dev, const float* goals_dev, const float* spawn_dev,
+                        const float* obst_xy_dev, void* stream);
+
+/* replaces `env.goal = ...` assignments made by scenario.step() (e.g. scenarios/swarm_vs_swarm.py:84-85). */
+int qs_set_goals(QsHandle* h, const uint8_t* env_mask_dev, const float* goals_dev, void* stream);
+
+/* replaces QuadrotorEnvMulti.reset (quadrotor_multi.py:339-411) for the masked envs; obs_dev [E,N,D]
+ * (rows of unmasked envs are left untouched). */
+int qs_reset(QsHandle* h, const uint8_t* env_mask_dev, float* obs_dev, void* stream);
+
+/* replaces QuadrotorEnvMulti.step (quadrotor_multi.py:413-724): one control step of every env, auto-reset
+ * included.  actions_dev [E,N,4] raw policy outputs; obs_dev [E,N,D]; rewards_dev [E,N]; dones_dev [E,N]
+ * bytes; rew_terms_dev [E,N,QS_NUM_TERMS] or NULL.  One kernel launch. */
+int qs_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev,
+            float* rew_terms_dev, void* stream);
+
+/* same step with HOST buffers: H2D of actions, the step kernel, D2H of obs/rewards/dones(/terms), then a
+ * stream synchronise — the call a non-batched rollout worker makes. */
+int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                 float* rew_terms_host);
+int qs_reset_host(QsHandle* h, const uint8_t* env_mask_host, float* obs_host);
+
+/* T consecutive control steps in ONE launch (persistent CTAs keep the env block in registers):
+ * actions_dev [T,E,N,4], obs_dev [T,E,N,D] or, when last_obs_only != 0, [E,N,D]; rewards_dev [T,E,N];
+ * dones_dev [T,E,N].  Same results as T calls of qs_step. */
+int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, float* obs_dev, float* rewards_dev,
+               uint8_t* dones_dev, int last_obs_only, void* stream);
+
+/* State snapshot / restore — what deepcopy(env) gives the replay wrapper (quad_experience_replay.py:99-104)
+ * and what parity tests use for teacher forcing.  agent_f32_dev [E,N,QS_STATE_F32]: pos3 vel3 rot9(row-major)
+ * omega3 thrust_rot_damp4 thrust_cmds_damp4 ou4 goal3 dist_ring4 dist_sums3 stale_vel3;
+ * agent_u32_dev [E,N,QS_STATE_U32]: flags, prev_collision_row, 0, 0;
+ * env_i32_dev [E,QS_STATE_ENV_I32]: tick, step_count, svd_count, episode_idx, then the QS_STAT_* counters. */
+#define QS_STATE_F32 43
+#define QS_STATE_U32 4
+#define QS_STATE_ENV_I32 16
+int qs_get_state(QsHandle* h, float* agent_f32_dev, uint32_t* agent_u32_dev, int32_t* env_i32_dev,
+                 float* obst_xy_dev, void* stream);
+int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f32_dev, const uint32_t* agent_u32_dev,
+                 const int32_t* env_i32_dev, const float* obst_xy_dev, void* stream);
+
+/* flag bits in agent_u32[.,0] */
+#define QS_FLAG_ON_FLOOR (1u << 0)
+#define QS_FLAG_CRASHED_FLOOR (1u << 1)
+#define QS_FLAG_CRASHED_WALL (1u << 2)
+#define QS_FLAG_CRASHED_CEILING (1u << 3)
+#define QS_FLAG_PREV_WALL (1u << 4)
+#define QS_FLAG_PREV_CEILING (1u << 5)
+#define QS_FLAG_PREV_ROOM (1u << 6)
+#define QS_FLAG_PREV_OBST (1u << 7)
+#define QS_FLAG_NO_COL_AGENT (1u << 8)
+#define QS_FLAG_NO_COL_OBST (1u << 9)
+#define QS_FLAG_REACHED_GOAL (1u << 10)
+#define QS_FLAG_KICKED (1u << 11)          /* a contact response / downwash changed this env's state this step */
+#define QS_FLAG_NEW_QUADCOL (1u << 12)     /* agent is in last_step_unique_collisions this step */
+#define QS_FLAG_NEW_OBSTCOL (1u << 13)     /* agent is in curr_quad_col this step */
+
+/* episode statistics of the most recently finished episode of each env:
+ * env_stats_dev [E,QS_NUM_ENV_STATS] (int32), agent_stats_dev [E,N,QS_NUM_AGENT_STATS] (float) */
+int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stats_dev, void* stream);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t qs_launch_count(const QsHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSWARM_H_ */

@@ -1,0 +1,94 @@
+// Keyed Philox4x32-10 draws for the QuadSwarm step kernels (sm_100a).
+//
+// Device twin of oracle/philox.py: both define the same function
+//   (seed, env, step_count, site, i, j, value_index) -> random value
+// so the CPU oracle and these kernels consume identical random numbers.  The reference
+// (gym_art/quadrotor_multi) draws from two order-dependent Mersenne-Twister streams
+// (SURVEY.md Appendix C), which a data-parallel kernel cannot replay; the site table below
+// names every draw site of the reference instead and gives it a fixed counter.
+//
+//   counter = (env_id, step_count, site | i << 8 | j << 16, block)   key = (seed_lo, seed_hi)
+//   uniform01(x) = (x >> 8) * 2^-24                       (exact in fp32)
+//   normal pair (xa, xb): u1 = ((xa >> 9) + 0.5) * 2^-23, u2 = (xb >> 8) * 2^-24,
+//                         r = sqrt(-2 ln u1), n0 = r cos(2 pi u2), n1 = r sin(2 pi u2)
+//   value index v lives in block v / 4, word v % 4; words (0,1) and (2,3) form the normal pairs.
+#pragma once
+#include <cstdint>
+
+namespace qs {
+
+enum Site : uint32_t {
+    SITE_OU = 0,            // (i)   normals v0..3                               numba_utils.py:103
+    SITE_FLOOR_YAW = 1,     // (i)   uniforms v0 / v1 = sub-step 0 / 1           quadrotor_dynamics.py:617
+    SITE_SENSOR0 = 2,       // (i)   normals v0..2 pos, v3..5 vel, v6..8 gyro    sensor_noise.py:241-251
+    SITE_SENSOR1 = 3,       // (i)   re-draw after a contact response            quadrotor_multi.py:598-599
+    SITE_SENSOR_RESET = 4,  // (i)   observation returned by an (auto-)reset
+    SITE_DW_I = 5,          // (i)   uniforms v0 acc noise, v1 omega noise       downwash.py:30,35
+    SITE_DW_IJ = 6,         // (i,j) uniforms v0..2 z-axis noise, v3..5 omega dir downwash.py:56,62
+    SITE_PAIR_N = 7,        // (i<j) normals, try t: v[12t..12t+8]               collisions/quadrotors.py:36-38
+    SITE_PAIR_U = 8,        // (i<j) uniforms v0,v1 decay, v2..4 omega dir, v5 omega mag  collisions/utils.py
+    SITE_OBST_N = 9,        // (i)   normals, try t: v[8t..8t+5]                 collisions/obstacles.py:33-34
+    SITE_OBST_U = 10,       // (i)   uniforms v0 decay, v1..3 omega dir, v4 omega mag
+    SITE_WALL_U = 11,       // (i)   uniforms v0 speed, v1..3 dir, v4 x, v5 y, v6 z, v7..9 omega dir, v10 mag  collisions/room.py:10-40
+    SITE_CEIL_U = 12,       // (i)   uniforms v0 speed, v1..3 dir, v4 z, v5..7 omega dir, v8 mag               collisions/room.py:94-110
+    SITE_SPAWN_U = 13,      // (i)   uniforms v0..2                              quadrotor_single.py:394
+    SITE_RESET_YAW_U = 14,  // (i)   uniforms v[k], k = rejection try            quadrotor_single.py:432-434
+    SITE_SCENARIO_U = 15,   // (slot) env-level scenario generators
+};
+
+constexpr int RESET_YAW_MAX_TRIES = 64;
+
+struct RngKey {
+    uint32_t k0, k1;      // seed
+    uint32_t env;         // global env id
+    uint32_t step;        // per-env step counter
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 rng_block(const RngKey& k, uint32_t site, uint32_t i, uint32_t j, uint32_t block) {
+    return philox4x32_10(k.env, k.step, site | (i << 8) | (j << 16), block, k.k0, k.k1);
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }  // 2^-24
+
+__device__ __forceinline__ void normal_pair(uint32_t xa, uint32_t xb, float& n0, float& n1) {
+    const float u1 = ((float)(xa >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23, exact
+    const float u2 = (float)(xb >> 8) * 5.9604644775390625e-08f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// 4 uniforms / 4 normals of one block
+__device__ __forceinline__ float4 rng_uniform4(const RngKey& k, uint32_t site, uint32_t i, uint32_t j, uint32_t block) {
+    const uint4 b = rng_block(k, site, i, j, block);
+    return make_float4(u01(b.x), u01(b.y), u01(b.z), u01(b.w));
+}
+
+__device__ __forceinline__ float4 rng_normal4(const RngKey& k, uint32_t site, uint32_t i, uint32_t j, uint32_t block) {
+    const uint4 b = rng_block(k, site, i, j, block);
+    float4 n;
+    normal_pair(b.x, b.y, n.x, n.y);
+    normal_pair(b.z, b.w, n.z, n.w);
+    return n;
+}
+
+}  // namespace qs

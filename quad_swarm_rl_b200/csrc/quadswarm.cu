@@ -1,0 +1,489 @@
+// C ABI of the B200-native QuadSwarm env step (see include/quadswarm.h for the contract and the
+// reference interfaces each entry point replaces).  Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "qs_step.cuh"
+
+using namespace qs;
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct QsHandle {
+    QsConfig cfg;
+    int device;
+    int NP;               // lanes per env (next pow2 >= N)
+    int K, S, D, M, ep_len;
+    long long A, a_pad;
+    DevState st;
+    float rew[QS_NUM_REW_COEFF];
+    int64_t launches;
+    // staging for the *_host entry points (pinned host + device mirrors)
+    float *d_actions, *d_obs, *d_rewards, *d_terms;
+    uint8_t *d_dones, *d_mask;
+    float *h_actions, *h_obs, *h_rewards, *h_terms;
+    uint8_t *h_dones, *h_mask;
+    cudaStream_t own_stream;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define QS_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(QS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+extern "C" const char* qs_last_error(void) { return g_err.c_str(); }
+
+static int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+static void fill_params(const QsHandle* h, StepParams& p) {
+    memset(&p, 0, sizeof(p));
+    const QsConfig& c = h->cfg;
+    p.st = h->st;
+    p.E = c.num_envs; p.N = c.num_agents; p.K = h->K; p.D = h->D; p.S = h->S; p.M = h->M;
+    p.obs_repr = c.obs_repr; p.use_obst = c.use_obstacles ? 1 : 0; p.use_downwash = c.use_downwash ? 1 : 0;
+    p.sense_noise = c.sense_noise ? 1 : 0;
+    p.ep_len = h->ep_len; p.T = 1; p.last_obs_only = 0;
+    // room_box, quadrotor_single.py:146-147
+    p.room_lo[0] = -c.room_dims[0] / 2.f; p.room_lo[1] = -c.room_dims[1] / 2.f; p.room_lo[2] = 0.f;
+    p.room_hi[0] = c.room_dims[0] / 2.f; p.room_hi[1] = c.room_dims[1] / 2.f; p.room_hi[2] = c.room_dims[2];
+    const double arm = 0.04596194077712559;
+    p.col_thr = (float)(c.collision_hitbox_radius * arm);        // quadrotor_multi.py:154
+    p.falloff_thr = (float)(c.collision_falloff_radius * arm);   // quadrotor_multi.py:155
+    p.obst_radius = (float)(c.obst_size / 2.0);
+    p.obst_col_thr = (float)(arm + c.obst_size / 2.0);           // obstacles/utils.py:33
+    p.obst_half_size = (float)(c.obst_size / 2.0);
+    p.grace_steps = 150.f;                                       // 1.5 * control_freq, quadrotor_multi.py:146
+    p.final_steps = 500.f;                                       // 5.0 * control_freq, quadrotor_multi.py:150
+    p.approach_metric = c.approch_goal_metric;
+    for (int k = 0; k < QS_NUM_REW_COEFF; ++k) p.rew[k] = h->rew[k];
+    p.seed_lo = (uint32_t)(c.seed & 0xffffffffull);
+    p.seed_hi = (uint32_t)(c.seed >> 32);
+    p.env_id_offset = c.env_id_offset;
+}
+
+// ------------------------------------------------------------------------------------------
+// small kernels: tables, goals, state import / export
+// ------------------------------------------------------------------------------------------
+__global__ void k_set_next_episode(DevState st, int E, int N, int M, const uint8_t* mask, const float* goals,
+                                   const float* spawn, const float* obst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long A = (long long)E * N;
+    if (t < A) {
+        const int env = (int)(t / N);
+        if (mask == nullptr || mask[env]) {
+            st.next_goal[t] = make_float4(goals[3 * t], goals[3 * t + 1], goals[3 * t + 2], 0.f);
+            st.next_spawn[t] = spawn ? make_float4(spawn[3 * t], spawn[3 * t + 1], spawn[3 * t + 2], 1.f)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (obst != nullptr && t < (long long)E * M) {
+        const int env = (int)(t / M);
+        if (mask == nullptr || mask[env]) st.next_obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
+    }
+}
+
+__global__ void k_set_goals(DevState st, int E, int N, const uint8_t* mask, const float* goals) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)E * N) return;
+    const int env = (int)(t / N);
+    if (mask == nullptr || mask[env])
+        st.slots[SL_GOAL * st.a_pad + t] = make_float4(goals[3 * t], goals[3 * t + 1], goals[3 * t + 2], 0.f);
+}
+
+__global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_t* au, int32_t* ei, float* obst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long A = (long long)E * N;
+    if (t < A) {
+        Agent s;
+        load_agent(st, t, s);
+        float* o = af + t * QS_STATE_F32;
+        int k = 0;
+        for (int c = 0; c < 3; ++c) o[k++] = s.pos[c];
+        for (int c = 0; c < 3; ++c) o[k++] = s.vel[c];
+        for (int c = 0; c < 9; ++c) o[k++] = s.R[c];
+        for (int c = 0; c < 3; ++c) o[k++] = s.om[c];
+        for (int c = 0; c < 4; ++c) o[k++] = s.rd[c];
+        for (int c = 0; c < 4; ++c) o[k++] = s.cd[c];
+        for (int c = 0; c < 4; ++c) o[k++] = s.ou[c];
+        for (int c = 0; c < 3; ++c) o[k++] = s.goal[c];
+        for (int c = 0; c < 4; ++c) o[k++] = s.ring[c];
+        const float4 sums = st.slots[SL_DIST_SUMS * st.a_pad + t], sv = st.slots[SL_STALE_VEL * st.a_pad + t];
+        o[k++] = sums.x; o[k++] = sums.y; o[k++] = sums.z;
+        o[k++] = sv.x; o[k++] = sv.y; o[k++] = sv.z;
+        uint32_t* u = au + t * QS_STATE_U32;
+        u[0] = s.flags; u[1] = s.prev_col; u[2] = 0u; u[3] = 0u;
+    }
+    if (t < E) {
+        const int4 c = st.env_ctr[t];
+        int32_t* e = ei + t * QS_STATE_ENV_I32;
+        e[0] = c.x; e[1] = c.y; e[2] = c.z; e[3] = c.w;
+        for (int k = 0; k < QS_NUM_ENV_STATS; ++k) e[4 + k] = st.env_cnt[t * QS_NUM_ENV_STATS + k];
+    }
+    if (obst != nullptr && t < (long long)E * M) {
+        const float2 ob = st.obst[t];
+        obst[2 * t] = ob.x; obst[2 * t + 1] = ob.y;
+    }
+}
+
+__global__ void k_set_state(DevState st, int E, int N, int M, const uint8_t* mask, const float* af, const uint32_t* au,
+                            const int32_t* ei, const float* obst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long A = (long long)E * N;
+    if (t < A && (mask == nullptr || mask[t / N])) {
+        Agent s;
+        const float* o = af + t * QS_STATE_F32;
+        int k = 0;
+        for (int c = 0; c < 3; ++c) s.pos[c] = o[k++];
+        for (int c = 0; c < 3; ++c) s.vel[c] = o[k++];
+        for (int c = 0; c < 9; ++c) s.R[c] = o[k++];
+        for (int c = 0; c < 3; ++c) s.om[c] = o[k++];
+        for (int c = 0; c < 4; ++c) s.rd[c] = o[k++];
+        for (int c = 0; c < 4; ++c) s.cd[c] = o[k++];
+        for (int c = 0; c < 4; ++c) s.ou[c] = o[k++];
+        for (int c = 0; c < 3; ++c) s.goal[c] = o[k++];
+        for (int c = 0; c < 4; ++c) s.ring[c] = o[k++];
+        st.slots[SL_DIST_SUMS * st.a_pad + t] = make_float4(o[k], o[k + 1], o[k + 2], 0.f);
+        k += 3;
+        st.slots[SL_STALE_VEL * st.a_pad + t] = make_float4(o[k], o[k + 1], o[k + 2], 0.f);
+        const uint32_t* u = au + t * QS_STATE_U32;
+        s.flags = u[0]; s.prev_col = u[1];
+        store_agent(st, t, s, true);
+    }
+    if (t < E && (mask == nullptr || mask[t])) {
+        const int32_t* e = ei + t * QS_STATE_ENV_I32;
+        st.env_ctr[t] = make_int4(e[0], e[1], e[2], e[3]);
+        for (int k = 0; k < QS_NUM_ENV_STATS; ++k) st.env_cnt[t * QS_NUM_ENV_STATS + k] = e[4 + k];
+    }
+    if (obst != nullptr && t < (long long)E * M && (mask == nullptr || mask[t / M]))
+        st.obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
+}
+
+__global__ void k_read_stats(DevState st, int E, int N, int32_t* env_stats, float* agent_stats) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)E * N && agent_stats) {
+        const float4 v = st.stats_agent[t];
+        agent_stats[4 * t] = v.x; agent_stats[4 * t + 1] = v.y; agent_stats[4 * t + 2] = v.z;
+        agent_stats[4 * t + 3] = (float)__float_as_uint(v.w);
+    }
+    if (t < (long long)E * QS_NUM_ENV_STATS && env_stats) env_stats[t] = st.stats_env[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static const int kBlock = 128;
+
+template <typename F>
+static int dispatch_np(int NP, F&& f) {
+    switch (NP) {
+        case 1: return f(std::integral_constant<int, 1>());
+        case 2: return f(std::integral_constant<int, 2>());
+        case 4: return f(std::integral_constant<int, 4>());
+        case 8: return f(std::integral_constant<int, 8>());
+        case 16: return f(std::integral_constant<int, 16>());
+        case 32: return f(std::integral_constant<int, 32>());
+    }
+    return fail(QS_ERR_UNSUPPORTED, "num_agents > 32 is not supported by this build");
+}
+
+static int launch_step(QsHandle* h, const StepParams& p, cudaStream_t s) {
+    const int envs_per_block = kBlock / h->NP;
+    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
+    int rc = dispatch_np(h->NP, [&](auto np) {
+        qs_step_kernel<decltype(np)::value><<<grid, kBlock, smem, s>>>(p);
+        return QS_OK;
+    });
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+static int launch_reset(QsHandle* h, const StepParams& p, cudaStream_t s) {
+    const int envs_per_block = kBlock / h->NP;
+    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
+    int rc = dispatch_np(h->NP, [&](auto np) {
+        qs_reset_kernel<decltype(np)::value><<<grid, kBlock, smem, s>>>(p);
+        return QS_OK;
+    });
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// API
+// ------------------------------------------------------------------------------------------
+extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
+    if (!cfg || !out) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (cfg->num_envs < 1) return fail(QS_ERR_INVALID_ARG, "num_envs must be >= 1");
+    if (cfg->num_agents < 1) return fail(QS_ERR_INVALID_ARG, "num_agents must be >= 1");
+    if (cfg->num_agents > QS_MAX_AGENTS) return fail(QS_ERR_UNSUPPORTED, "num_agents > 32 is not supported by this build");
+    if (cfg->obs_repr < 0 || cfg->obs_repr > 2) return fail(QS_ERR_INVALID_ARG, "unknown obs_repr");
+    int K = cfg->neighbor_visible_num == -1 ? cfg->num_agents - 1 : cfg->neighbor_visible_num;
+    // quadrotor_multi.py:253-274: K must be 0, N-1, or in [1, N-2]
+    if (K < 0 || K > cfg->num_agents - 1) return fail(QS_ERR_INVALID_ARG, "Incorrect number of neigbors");
+    if (cfg->use_obstacles && cfg->num_obstacles < 1) return fail(QS_ERR_INVALID_ARG, "use_obstacles needs num_obstacles >= 1");
+    if (cfg->ep_time <= 0.f) return fail(QS_ERR_INVALID_ARG, "ep_time must be positive");
+    QS_CUDA(cudaSetDevice(device));
+    QsHandle* h = new (std::nothrow) QsHandle();
+    if (!h) return fail(QS_ERR_INVALID_ARG, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->device = device;
+    h->NP = next_pow2(cfg->num_agents);
+    h->K = K;
+    h->S = cfg->obs_repr == 0 ? 18 : (cfg->obs_repr == 1 ? 19 : 24);
+    h->M = cfg->use_obstacles ? cfg->num_obstacles : 0;
+    h->D = h->S + 6 * K + (cfg->use_obstacles ? 9 : 0);
+    h->ep_len = (int)((double)cfg->ep_time / (0.005 * 2));      // quadrotor_single.py:158
+    h->A = (long long)cfg->num_envs * cfg->num_agents;
+    h->a_pad = (h->A + 31) / 32 * 32;
+    // QuadrotorEnvMulti defaults, quadrotor_multi.py:91-94
+    const float def[QS_NUM_REW_COEFF] = {1.f, 0.05f, 1.f, 1.f, 0.1f, 5.f, 4.f, 5.f};
+    memcpy(h->rew, def, sizeof(def));
+    DevState& st = h->st;
+    st.a_pad = h->a_pad;
+    const long long E = cfg->num_envs, A = h->A, M = h->M > 0 ? h->M : 1;
+#define QS_ALLOC0(ptr, bytes)                                     \
+    do {                                                          \
+        QS_CUDA(cudaMalloc((void**)&(ptr), (size_t)(bytes)));     \
+        QS_CUDA(cudaMemset((ptr), 0, (size_t)(bytes)));           \
+    } while (0)
+    QS_ALLOC0(st.slots, sizeof(float4) * NUM_SLOTS * h->a_pad);
+    QS_ALLOC0(st.env_ctr, sizeof(int4) * E);
+    QS_ALLOC0(st.env_cnt, sizeof(int32_t) * E * QS_NUM_ENV_STATS);
+    QS_ALLOC0(st.obst, sizeof(float2) * E * M);
+    QS_ALLOC0(st.next_goal, sizeof(float4) * A);
+    QS_ALLOC0(st.next_spawn, sizeof(float4) * A);
+    QS_ALLOC0(st.next_obst, sizeof(float2) * E * M);
+    QS_ALLOC0(st.stats_env, sizeof(int32_t) * E * QS_NUM_ENV_STATS);
+    QS_ALLOC0(st.stats_agent, sizeof(float4) * A);
+    // rotation = identity so that a never-reset env still holds a valid state
+    {
+        std::string tmp;
+        float4* init = (float4*)malloc(sizeof(float4) * h->a_pad);
+        for (long long a = 0; a < h->a_pad; ++a) init[a] = make_float4(0.f, 1.f, 0.f, 0.f);   // omega.z, R00, R01, R02
+        QS_CUDA(cudaMemcpy(st.slots + SL_OM_R0 * h->a_pad, init, sizeof(float4) * h->a_pad, cudaMemcpyHostToDevice));
+        for (long long a = 0; a < h->a_pad; ++a) init[a] = make_float4(0.f, 1.f, 0.f, 0.f);   // R10, R11, R12, R20
+        QS_CUDA(cudaMemcpy(st.slots + SL_R1_R20 * h->a_pad, init, sizeof(float4) * h->a_pad, cudaMemcpyHostToDevice));
+        for (long long a = 0; a < h->a_pad; ++a) init[a] = make_float4(0.f, 1.f, 0.f, 0.f);   // R21, R22, flags, prev
+        QS_CUDA(cudaMemcpy(st.slots + SL_R2_FLAGS * h->a_pad, init, sizeof(float4) * h->a_pad, cudaMemcpyHostToDevice));
+        free(init);
+    }
+    // default episode table: every goal at (0, 0, 2), spawn at the goal (scenarios/base.py:137-139, static_same_goal)
+    {
+        float4* g = (float4*)malloc(sizeof(float4) * A);
+        for (long long a = 0; a < A; ++a) g[a] = make_float4(0.f, 0.f, 2.f, 0.f);
+        QS_CUDA(cudaMemcpy(st.next_goal, g, sizeof(float4) * A, cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMemcpy(st.slots + SL_GOAL * h->a_pad, g, sizeof(float4) * A, cudaMemcpyHostToDevice));
+        free(g);
+    }
+    // staging buffers for the host entry points
+    QS_CUDA(cudaMalloc((void**)&h->d_actions, sizeof(float) * 4 * A));
+    QS_CUDA(cudaMalloc((void**)&h->d_obs, sizeof(float) * h->D * A));
+    QS_CUDA(cudaMalloc((void**)&h->d_rewards, sizeof(float) * A));
+    QS_CUDA(cudaMalloc((void**)&h->d_terms, sizeof(float) * QS_NUM_TERMS * A));
+    QS_CUDA(cudaMalloc((void**)&h->d_dones, A));
+    QS_CUDA(cudaMalloc((void**)&h->d_mask, E));
+    QS_CUDA(cudaMallocHost((void**)&h->h_actions, sizeof(float) * 4 * A));
+    QS_CUDA(cudaMallocHost((void**)&h->h_obs, sizeof(float) * h->D * A));
+    QS_CUDA(cudaMallocHost((void**)&h->h_rewards, sizeof(float) * A));
+    QS_CUDA(cudaMallocHost((void**)&h->h_terms, sizeof(float) * QS_NUM_TERMS * A));
+    QS_CUDA(cudaMallocHost((void**)&h->h_dones, A));
+    QS_CUDA(cudaMallocHost((void**)&h->h_mask, E));
+    QS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    *out = h;
+    return QS_OK;
+}
+
+extern "C" int qs_destroy(QsHandle* h) {
+    if (!h) return QS_OK;
+    cudaSetDevice(h->device);
+    DevState& st = h->st;
+    cudaFree(st.slots); cudaFree(st.env_ctr); cudaFree(st.env_cnt); cudaFree(st.obst); cudaFree(st.next_goal);
+    cudaFree(st.next_spawn); cudaFree(st.next_obst); cudaFree(st.stats_env); cudaFree(st.stats_agent);
+    cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_rewards); cudaFree(h->d_terms); cudaFree(h->d_dones);
+    cudaFree(h->d_mask);
+    cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);
+    cudaFreeHost(h->h_dones); cudaFreeHost(h->h_mask);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return QS_OK;
+}
+
+extern "C" int qs_obs_dim(const QsHandle* h) { return h ? h->D : 0; }
+extern "C" int qs_num_envs(const QsHandle* h) { return h ? h->cfg.num_envs : 0; }
+extern "C" int qs_num_agents(const QsHandle* h) { return h ? h->cfg.num_agents : 0; }
+extern "C" int qs_num_obstacles(const QsHandle* h) { return h ? h->M : 0; }
+extern "C" int qs_ep_len(const QsHandle* h) { return h ? h->ep_len : 0; }
+extern "C" int64_t qs_launch_count(const QsHandle* h) { return h ? h->launches : 0; }
+
+extern "C" int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host) {
+    if (!h || !coeffs_host) return fail(QS_ERR_INVALID_ARG, "null argument");
+    for (int k = 0; k < QS_NUM_REW_COEFF; ++k) {
+        if (!(coeffs_host[k] == coeffs_host[k])) return fail(QS_ERR_INVALID_ARG, "reward coefficient is NaN");
+        h->rew[k] = coeffs_host[k];
+    }
+    return QS_OK;
+}
+
+static inline int blocks_for(long long n) { return (int)((n + 255) / 256); }
+
+extern "C" int qs_set_next_episode(QsHandle* h, const uint8_t* env_mask_dev, const float* goals_dev, const float* spawn_dev,
+                                   const float* obst_xy_dev, void* stream) {
+    if (!h || !goals_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (obst_xy_dev && !h->cfg.use_obstacles) return fail(QS_ERR_INVALID_ARG, "obstacle table given but use_obstacles = 0");
+    QS_CUDA(cudaSetDevice(h->device));
+    const long long n = h->A > (long long)h->cfg.num_envs * h->M ? h->A : (long long)h->cfg.num_envs * h->M;
+    k_set_next_episode<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(h->st, h->cfg.num_envs, h->cfg.num_agents, h->M,
+                                                                         env_mask_dev, goals_dev, spawn_dev, obst_xy_dev);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+extern "C" int qs_set_goals(QsHandle* h, const uint8_t* env_mask_dev, const float* goals_dev, void* stream) {
+    if (!h || !goals_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    k_set_goals<<<blocks_for(h->A), 256, 0, (cudaStream_t)stream>>>(h->st, h->cfg.num_envs, h->cfg.num_agents, env_mask_dev,
+                                                                     goals_dev);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+extern "C" int qs_reset(QsHandle* h, const uint8_t* env_mask_dev, float* obs_dev, void* stream) {
+    if (!h || !obs_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    p.obs = obs_dev;
+    p.env_mask = env_mask_dev;
+    return launch_reset(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int qs_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev,
+                       float* rew_terms_dev, void* stream) {
+    if (!h || !actions_dev || !obs_dev || !rewards_dev || !dones_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (((uintptr_t)actions_dev & 15u) != 0) return fail(QS_ERR_INVALID_ARG, "actions must be 16-byte aligned");
+    QS_CUDA(cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    p.actions = (const float4*)actions_dev;
+    p.obs = obs_dev; p.rewards = rewards_dev; p.dones = dones_dev; p.rew_terms = rew_terms_dev;
+    return launch_step(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, float* obs_dev, float* rewards_dev,
+                          uint8_t* dones_dev, int last_obs_only, void* stream) {
+    if (!h || !actions_dev || !obs_dev || !rewards_dev || !dones_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (num_steps < 1) return fail(QS_ERR_INVALID_ARG, "num_steps must be >= 1");
+    if (((uintptr_t)actions_dev & 15u) != 0) return fail(QS_ERR_INVALID_ARG, "actions must be 16-byte aligned");
+    QS_CUDA(cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    p.actions = (const float4*)actions_dev;
+    p.obs = obs_dev; p.rewards = rewards_dev; p.dones = dones_dev; p.rew_terms = nullptr;
+    p.T = num_steps; p.last_obs_only = last_obs_only ? 1 : 0;
+    return launch_step(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                            float* rew_terms_host) {
+    if (!h || !actions_host || !obs_host || !rewards_host || !dones_host) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->own_stream;
+    const long long A = h->A;
+    memcpy(h->h_actions, actions_host, sizeof(float) * 4 * A);
+    QS_CUDA(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * 4 * A, cudaMemcpyHostToDevice, s));
+    int rc = qs_step(h, h->d_actions, h->d_obs, h->d_rewards, h->d_dones, rew_terms_host ? h->d_terms : nullptr, s);
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * h->D * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(h->h_rewards, h->d_rewards, sizeof(float) * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(h->h_dones, h->d_dones, A, cudaMemcpyDeviceToHost, s));
+    if (rew_terms_host)
+        QS_CUDA(cudaMemcpyAsync(h->h_terms, h->d_terms, sizeof(float) * QS_NUM_TERMS * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaStreamSynchronize(s));
+    memcpy(obs_host, h->h_obs, sizeof(float) * h->D * A);
+    memcpy(rewards_host, h->h_rewards, sizeof(float) * A);
+    memcpy(dones_host, h->h_dones, A);
+    if (rew_terms_host) memcpy(rew_terms_host, h->h_terms, sizeof(float) * QS_NUM_TERMS * A);
+    return QS_OK;
+}
+
+extern "C" int qs_reset_host(QsHandle* h, const uint8_t* env_mask_host, float* obs_host) {
+    if (!h || !obs_host) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->own_stream;
+    const long long A = h->A;
+    if (env_mask_host) {
+        memcpy(h->h_mask, env_mask_host, h->cfg.num_envs);
+        QS_CUDA(cudaMemcpyAsync(h->d_mask, h->h_mask, h->cfg.num_envs, cudaMemcpyHostToDevice, s));
+        // rows of unmasked envs keep the caller's values
+        memcpy(h->h_obs, obs_host, sizeof(float) * h->D * A);
+        QS_CUDA(cudaMemcpyAsync(h->d_obs, h->h_obs, sizeof(float) * h->D * A, cudaMemcpyHostToDevice, s));
+    }
+    int rc = qs_reset(h, env_mask_host ? h->d_mask : nullptr, h->d_obs, s);
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * h->D * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaStreamSynchronize(s));
+    memcpy(obs_host, h->h_obs, sizeof(float) * h->D * A);
+    return QS_OK;
+}
+
+extern "C" int qs_get_state(QsHandle* h, float* agent_f32_dev, uint32_t* agent_u32_dev, int32_t* env_i32_dev,
+                            float* obst_xy_dev, void* stream) {
+    if (!h || !agent_f32_dev || !agent_u32_dev || !env_i32_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    const long long n = h->A > (long long)h->cfg.num_envs * h->M ? h->A : (long long)h->cfg.num_envs * h->M;
+    k_get_state<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(h->st, h->cfg.num_envs, h->cfg.num_agents, h->M, agent_f32_dev,
+                                                                  agent_u32_dev, env_i32_dev, h->M > 0 ? obst_xy_dev : nullptr);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+extern "C" int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f32_dev, const uint32_t* agent_u32_dev,
+                            const int32_t* env_i32_dev, const float* obst_xy_dev, void* stream) {
+    if (!h || !agent_f32_dev || !agent_u32_dev || !env_i32_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    const long long n = h->A > (long long)h->cfg.num_envs * h->M ? h->A : (long long)h->cfg.num_envs * h->M;
+    k_set_state<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(h->st, h->cfg.num_envs, h->cfg.num_agents, h->M, env_mask_dev,
+                                                                  agent_f32_dev, agent_u32_dev, env_i32_dev,
+                                                                  h->M > 0 ? obst_xy_dev : nullptr);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}
+
+extern "C" int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stats_dev, void* stream) {
+    if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    const long long n1 = h->A, n2 = (long long)h->cfg.num_envs * QS_NUM_ENV_STATS;
+    k_read_stats<<<blocks_for(n1 > n2 ? n1 : n2), 256, 0, (cudaStream_t)stream>>>(h->st, h->cfg.num_envs, h->cfg.num_agents,
+                                                                                   env_stats_dev, agent_stats_dev);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return QS_OK;
+}

@@ -131,6 +131,34 @@ def z_above_ground(rng, num_agents, per_layer, box, formation, size):
     return max(lower, z)
 
 
+def grid_cell_centers(area_length, area_width, grid_size=1.0):
+    """Centres of the pillar grid cells, column-major from the top-left (obstacles/utils.py:47-58)."""
+    L_, W_ = int(area_length / grid_size), int(area_width / grid_size)
+    xs = np.arange(0, area_length, grid_size) + grid_size / 2 - area_length // 2
+    ys = np.arange(area_width - grid_size, -grid_size, -grid_size) + grid_size / 2 - area_width // 2
+    out = np.zeros((L_ * W_, 2))
+    out[:, 0] = np.repeat(xs, len(ys))
+    out[:, 1] = np.tile(ys, len(xs))
+    return out
+
+
+def obstacle_map_given_density(rng, obst_spawn_area, obst_density, room_height=10.0, grid_size=1.0):
+    """Random pillar placement on the grid without replacement (quadrotor_multi.py:304-325).
+    Returns (obst_map[L,W] of 0/1, pillar positions [M,3] with z = room_height / 2, cell centres)."""
+    L_, W_ = int(obst_spawn_area[0]), int(obst_spawn_area[1])
+    n_cells = L_ * W_
+    cells = grid_cell_centers(L_, W_, grid_size)
+    picks = rng.choice(a=list(range(n_cells)), size=int(n_cells * obst_density), replace=False)
+    obst_map = np.zeros([L_, W_])
+    pos = []
+    for k in picks:
+        rid, cid = k // W_, k - (k // W_) * W_
+        obst_map[rid, cid] = 1
+        c = cells[rid + int(L_ / grid_size) * cid]
+        pos.append([c[0], c[1], room_height / 2.])
+    return obst_map, pos, cells
+
+
 # ------------------------------------------------------------------------------------------
 # scenario objects
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,160 @@
+"""GPU parity: the CUDA env step (through the C ABI) against the CPU oracle on identical seeds, actions and tables.
+
+Tolerances (fp32 kernel vs fp64 oracle, teacher-forced every `resync` steps):
+  observations / rewards / state: |err| <= 1e-4 + 1e-4 * |ref|   (BASELINE.json north_star: 1e-4 relative)
+  done / collision / obstacle-collision / on-floor / kicked masks: bit-exact on every env-step whose decisions are
+  further than 2e-5 from their thresholds in float64 (parity_util.MARGIN_EPS); the skipped fraction is bounded."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+C2 = dict(num_agents=8, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega', ep_time=1.0)
+C3 = dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True,
+          use_downwash=True, ep_time=1.0)
+C4 = dict(num_agents=32, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega', ep_time=0.6)
+C1 = dict(num_agents=1, neighbor_visible_num=0, neighbor_obs_type='none', obs_repr='xyz_vxyz_R_omega', ep_time=0.8)
+ALLN = dict(num_agents=5, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega_wall', ep_time=0.5, use_downwash=True)
+
+
+def _run(kw, E, T, seed, **extra):
+    from tests.parity_util import Pair, run_parity
+    pair = Pair(E, kw, seed=seed, table_seed=seed + 1, rew_coeff=extra.pop('rew_coeff', None))
+    rep = run_parity(pair, T, np.random.RandomState(seed + 2), **extra)
+    frac = rep['skipped_env_steps'] / max(1, rep['skipped_env_steps'] + rep['compared_env_steps'])
+    print(rep)
+    assert frac < 0.02, rep
+    pair.engine.close()
+    return rep
+
+
+def test_c1_single_drone():
+    rep = _run(C1, E=24, T=200, seed=100)
+    assert rep['dones'] >= 24 * 2
+
+
+def test_c2_eight_drones_same_goal():
+    rep = _run(C2, E=16, T=230, seed=200, rew_coeff=dict(quadcol_bin=5.0, quadcol_bin_smooth_max=10.0))
+    assert rep['dones'] >= 16 * 2 and rep['floor'] > 0
+
+
+def test_c3_obstacles_downwash_knn():
+    rep = _run(C3, E=12, T=230, seed=300)
+    assert rep['dones'] >= 12 * 2
+
+
+def test_c4_thirtytwo_drones():
+    _run(C4, E=3, T=70, seed=400)
+
+
+def test_all_neighbors_wall_obs_non_pow2():
+    _run(ALLN, E=9, T=120, seed=500, action_scale=1.3)
+
+
+def _cluster_hook(center, spread, speed, every):
+    """Every `every` steps plant the drones of each env in a tight cluster flying at each other (collisions,
+    proximity penalties, downwash), by editing the ORACLE state and teacher-forcing the device from it."""
+    def hook(pair, t):
+        if t % every != 0:
+            return
+        rs = np.random.RandomState(1000 + t)
+        for o in pair.oracles:
+            c = np.array(center) + rs.uniform(-1, 1, 3) * [2, 2, 0.5]
+            for d in o.drones:
+                off = rs.uniform(-spread, spread, 3)
+                off[2] = rs.uniform(-0.45, 0.45)
+                d.pos = c + off
+                d.vel = -speed * off / (np.linalg.norm(off) + 1e-9) + rs.uniform(-0.1, 0.1, 3)
+                d.omega = rs.uniform(-1, 1, 3)
+        pair.sync_device_from_oracle()
+    return hook
+
+
+def test_collisions_proximity_downwash_cluster():
+    rep = _run(dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega', use_downwash=True, ep_time=2.0),
+               E=10, T=150, seed=600, hook=_cluster_hook((0.0, 0.0, 3.0), 0.12, 0.6, 25),
+               rew_coeff=dict(quadcol_bin=5.0, quadcol_bin_smooth_max=10.0))
+    assert rep['quadcol'] > 10 and rep['kicked'] > 10, rep
+
+
+def _room_hook(every):
+    def hook(pair, t):
+        if t % every != 0:
+            return
+        rs = np.random.RandomState(2000 + t)
+        for o in pair.oracles:
+            for i, d in enumerate(o.drones):
+                kind = (i + t // every) % 5
+                if kind == 0:
+                    d.pos = np.array([4.99, rs.uniform(-3, 3), 3.0]); d.vel = np.array([3.0, 0.2, 0.1])
+                elif kind == 1:
+                    d.pos = np.array([rs.uniform(-3, 3), -4.99, 2.0]); d.vel = np.array([0.3, -3.0, 0.0])
+                elif kind == 2:
+                    d.pos = np.array([rs.uniform(-3, 3), rs.uniform(-3, 3), 9.99]); d.vel = np.array([0.1, 0.0, 4.0])
+                elif kind == 3:
+                    d.pos = np.array([rs.uniform(-3, 3), rs.uniform(-3, 3), 0.07]); d.vel = np.array([0.5, 0.3, -2.0])
+                else:
+                    d.pos = np.array([rs.uniform(-3, 3), rs.uniform(-3, 3), 0.07]); d.vel = np.array([-0.2, 0.4, -2.0])
+                    c, s = np.cos(np.pi - 0.2), np.sin(np.pi - 0.2)
+                    d.rot = d.rot @ np.array([[1., 0, 0], [0, c, -s], [0, s, c]])      # upside down -> random yaw branch
+                d.on_floor = False
+        pair.sync_device_from_oracle()
+    return hook
+
+
+def test_room_contacts_walls_ceiling_floor():
+    rep = _run(dict(num_agents=5, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega', ep_time=2.0),
+               E=8, T=120, seed=700, hook=_room_hook(30))
+    assert rep['kicked'] > 5 and rep['floor'] > 0, rep
+
+
+def _obst_hook(every):
+    def hook(pair, t):
+        if t % every != 0 or t == 0:
+            return
+        rs = np.random.RandomState(3000 + t)
+        for o in pair.oracles:
+            for k, d in enumerate(o.drones[:4]):
+                ob = o.obst_xy[k]
+                ang = rs.uniform(-np.pi, np.pi)
+                r = 0.3 + 0.046 + 0.02 if k else 0.15
+                d.pos = np.array([ob[0] + r * np.cos(ang), ob[1] + r * np.sin(ang), rs.uniform(1.0, 3.0) if k else 5.0])
+                d.vel = np.array([-1.5 * np.cos(ang), -1.5 * np.sin(ang), 0.1])
+        pair.sync_device_from_oracle()
+    return hook
+
+
+def test_obstacle_collisions_and_sdf():
+    rep = _run(dict(C3, ep_time=2.0), E=8, T=130, seed=800, hook=_obst_hook(20))
+    assert rep['obstcol'] > 5, rep
+
+
+def test_episode_stats_latch_matches_oracle():
+    """The statistics latched at episode end equal the oracle's episode_extra_stats (quadrotor_multi.py:626-718)."""
+    from tests.parity_util import Pair
+    from quad_swarm_rl_b200 import _lib as L
+    import torch
+    kw = dict(C3, ep_time=0.4)
+    pair = Pair(6, kw, seed=900, table_seed=901)
+    pair.reset()
+    rs = np.random.RandomState(902)
+    stats = None
+    for t in range(41):
+        d, o = pair.step(rs.uniform(-1, 1, (6, 8, 4)).astype(np.float32))
+        if (t + 1) % 10 == 0 and not o['dones'].any():
+            pair.sync_device_from_oracle()
+        if o['dones'].any():
+            stats = o['infos']
+    assert stats is not None
+    es, ags = pair.engine.episode_stats()
+    es, ags = es.cpu().numpy(), ags.cpu().numpy()
+    for e in range(6):
+        s0 = stats[e][0]['episode_extra_stats']
+        for k, key in enumerate(L.ENV_STAT_KEYS[:11]):
+            assert es[e, k] == s0[key], (e, key, es[e, k], s0[key])
+        for i in range(8):
+            si = stats[e][i]['episode_extra_stats']
+            np.testing.assert_allclose(ags[e, i, 0], si['distance_to_goal_1s'], rtol=1e-4)
+            np.testing.assert_allclose(ags[e, i, 1], si['distance_to_goal_3s'], rtol=1e-4)
+            np.testing.assert_allclose(ags[e, i, 2], si['distance_to_goal_5s'], rtol=1e-4)
+    pair.engine.close()
