@@ -454,7 +454,9 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         {
             if (wall_c) wall_response(key, i, s, p);
             if (ceil_c) ceiling_response(key, i, s);
-            kicked = kicked || (group_ballot<NP>(wall_c || ceil_c) != 0u);
+            // NB: the ballot must not sit behind a short-circuit `||` — `kicked` differs between the envs of a warp
+            const bool room_any = group_ballot<NP>(wall_c || ceil_c) != 0u;
+            kicked = kicked || room_any;
         }
         if (kicked) s.flags |= QS_FLAG_KICKED;
 

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# tiny 3x3 numpy/LAPACK calls dominate the oracle; BLAS thread pools on many-core hosts make them pathologically slow
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ.setdefault(_v, '1')
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

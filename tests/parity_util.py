@@ -13,7 +13,7 @@ from quad_swarm_rl_b200 import _lib as L
 from quad_swarm_rl_b200.engine import QuadSwarmEngine, STATE_F32_FIELDS
 
 MARGIN_EPS = 2e-5        # float32 resolution of positions in a 10 m room (ulp(10) ~ 1e-6) with head-room
-NEIGHBOR_GAP_EPS = 1e-4
+NEIGHBOR_GAP_EPS = 3e-5
 
 
 def make_tables(rs, E, N, M, use_obst, episodes=3, spread=1.5):
