@@ -99,8 +99,14 @@ struct Agent {
 };
 
 // ---- small helpers ----
+struct V3 { float x, y, z; };
+struct KickVO { V3 vel; V3 dom; };         // new velocity, delta omega
+struct PairOut { V3 v1, v2, dom; };        // new velocities of both drones, +/- delta omega
+struct ResetPose { V3 pos; float cs, sn; };
+struct Noise9 { float p[3], v[3], w[3]; }; // scaled sensor noise: position, velocity, gyro
+
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-__device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }
+__device__ __forceinline__ float norm3(float x, float y, float z) { return fsqrt(x * x + y * y + z * z); }
 
 template <int NP>
 __device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src, NP); }
@@ -146,25 +152,26 @@ __device__ __forceinline__ void store_agent(const DevState& st, long long a, con
     if (store_goal) p[SL_GOAL * st.a_pad] = make_float4(s.goal[0], s.goal[1], s.goal[2], 0.f);
 }
 
-// R -> pure yaw (quadrotor_dynamics.py:579-581, :614-621)
+// R -> pure yaw (quadrotor_dynamics.py:579-581, :614-621): theta = atan2(R10, R00 + eps), then (cos, sin) of it.
+// cos(atan2(y, x)) = x / hypot, so no trigonometry is needed; atan2(0, 0) = 0 gives the identity.
 __device__ __forceinline__ void yaw_only(float R[9]) {
-    const float theta = atan2f(R[3], R[0] + EPS_DYN);
-    float s, c;
-    sincosf(theta, &s, &c);
-    R[0] = c; R[1] = -s; R[2] = 0.f; R[3] = s; R[4] = c; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
-}
-
-__device__ __forceinline__ void set_yaw(float R[9], float theta) {
-    float s, c;
-    sincosf(theta, &s, &c);
+    const float x = R[0] + EPS_DYN, y = R[3];
+    const float h2 = x * x + y * y;
+    float c = 1.f, s = 0.f;
+    if (h2 > 0.f) {
+        const float inv = frsqrt(h2);
+        c = x * inv; s = y * inv;
+    }
     R[0] = c; R[1] = -s; R[2] = 0.f; R[3] = s; R[4] = c; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
 }
 
 // Nearest orthogonal matrix (polar factor) = U V^T of the SVD the reference takes every 0.5 s
 // (quadrotor_dynamics.py:547-551).  R is orthogonal to rounding on entry, so two Newton steps
 // X <- (X + X^-T) / 2 reach fp32 precision; no LAPACK-style SVD is needed on the device.
-__device__ __forceinline__ void orthonormalize(float R[9]) {
-#pragma unroll
+struct M3 { float m[9]; };
+__device__ __noinline__ M3 orthonormalize(M3 in) {
+    float* R = in.m;
+#pragma unroll 1
     for (int it = 0; it < 2; ++it) {
         const float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
         const float c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
@@ -175,6 +182,16 @@ __device__ __forceinline__ void orthonormalize(float R[9]) {
         R[3] = 0.5f * R[3] + h * c10; R[4] = 0.5f * R[4] + h * c11; R[5] = 0.5f * R[5] + h * c12;
         R[6] = 0.5f * R[6] + h * c20; R[7] = 0.5f * R[7] + h * c21; R[8] = 0.5f * R[8] + h * c22;
     }
+    return in;
+}
+
+// cold half of the floor contact: upside-down first contact draws a random yaw (quadrotor_dynamics.py:616-619)
+__device__ __noinline__ float2 floor_random_yaw(RngKey key, int i, int sub) {
+    const float4 u = rng_uniform4(key, SITE_FLOOR_YAW, i, 0, 0);
+    const float th = -PI_F + (PI_F - (-PI_F)) * (sub == 0 ? u.x : u.y);
+    float s, c;
+    sincosf(th, &s, &c);
+    return make_float2(c, s);
 }
 
 // One 5 ms physics sub-step of the njit path: step1_numba, quadrotor_dynamics.py:348-383
@@ -187,10 +204,9 @@ __device__ __forceinline__ void dynamics_substep(Agent& s, const float cmd[4], b
     float thr[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        const float c = clampf(cmd[m], 0.f, 1.f);
-        float tau = (c < s.cd[m]) ? MOTOR_TAU_DOWN : MOTOR_TAU_UP;
-        tau = fminf(tau, 1.f);
-        s.rd[m] = tau * (sqrtf(c) - s.rd[m]) + s.rd[m];
+        const float c = cmd[m];                       // already in [0,1]; the second np.clip (:504) is a no-op
+        const float tau = fminf((c < s.cd[m]) ? MOTOR_TAU_DOWN : MOTOR_TAU_UP, 1.f);
+        s.rd[m] = tau * (fsqrt(c) - s.rd[m]) + s.rd[m];
         s.cd[m] = clampf(s.rd[m] * s.rd[m] + c * s.ou[m], 0.f, 1.f);
         thr[m] = THRUST_MAX * s.cd[m];
     }
@@ -200,41 +216,44 @@ __device__ __forceinline__ void dynamics_substep(Agent& s, const float cmd[4], b
     const float tq2 = TORQUE_MAX * ((s.cd[1] + s.cd[3]) - (s.cd[0] + s.cd[2]));
     const float thrust_z = (thr[0] + thr[1]) + (thr[2] + thr[3]);
 
-    // Rodrigues rotation by the world-frame angular velocity (:537-544)
+    // Rodrigues rotation by the world-frame angular velocity w (:537-544):
+    //   R <- (I + sin(t) K + (1 - cos(t)) K^2) R,  K = [w]x / |w|,  t = |w| dt
+    // written as R + a (w x r) + b (w (w.r) - r |w|^2) per column r, with a = dt sin(t)/t and b = dt^2 (1-cos t)/t^2
+    // evaluated as polynomials in t^2 (t <= 40 sqrt(3) dt = 0.35): no sqrt, no division, exact identity at w = 0
+    // (the reference skips the update when |w| == 0).
     {
         const float wx = s.R[0] * s.om[0] + s.R[1] * s.om[1] + s.R[2] * s.om[2];
         const float wy = s.R[3] * s.om[0] + s.R[4] * s.om[1] + s.R[5] * s.om[2];
         const float wz = s.R[6] * s.om[0] + s.R[7] * s.om[1] + s.R[8] * s.om[2];
-        const float wn = norm3(wx, wy, wz);
-        if (wn != 0.f) {
-            const float inv = 1.f / wn;
-            const float kx = wx * inv, ky = wy * inv, kz = wz * inv;
-            float sn, cs, sh, ch;
-            const float ang = wn * SIM_DT;
-            sincosf(ang, &sn, &cs);
-            sincosf(0.5f * ang, &sh, &ch);
-            const float omc = 2.f * sh * sh;          // 1 - cos(ang) without cancellation
-            (void)cs; (void)ch;
+        const float w2 = wx * wx + wy * wy + wz * wz;
+        const float t2 = w2 * (SIM_DT * SIM_DT);
+        const float ca = SIM_DT * (1.f + t2 * (-1.f / 6.f + t2 * (1.f / 120.f + t2 * (-1.f / 5040.f))));
+        const float cb = (SIM_DT * SIM_DT) * (0.5f + t2 * (-1.f / 24.f + t2 * (1.f / 720.f + t2 * (-1.f / 40320.f))));
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {             // column c of R: v + sin (k x v) + (1-cos) (k (k.v) - v)
-                const float vx = s.R[c], vy = s.R[3 + c], vz = s.R[6 + c];
-                const float kd = kx * vx + ky * vy + kz * vz;
-                const float cx = ky * vz - kz * vy, cy = kz * vx - kx * vz, cz = kx * vy - ky * vx;
-                s.R[c] = vx + sn * cx + omc * (kx * kd - vx);
-                s.R[3 + c] = vy + sn * cy + omc * (ky * kd - vy);
-                s.R[6 + c] = vz + sn * cz + omc * (kz * kd - vz);
-            }
+        for (int c = 0; c < 3; ++c) {
+            const float vx = s.R[c], vy = s.R[3 + c], vz = s.R[6 + c];
+            const float wd = wx * vx + wy * vy + wz * vz;
+            s.R[c] = vx + ca * (wy * vz - wz * vy) + cb * (wx * wd - vx * w2);
+            s.R[3 + c] = vy + ca * (wz * vx - wx * vz) + cb * (wy * wd - vy * w2);
+            s.R[6 + c] = vz + ca * (wx * vy - wy * vx) + cb * (wz * wd - vz * w2);
         }
     }
-    if (do_svd) orthonormalize(s.R);
+    if (do_svd) {
+        M3 m;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) m.m[k] = s.R[k];
+        m = orthonormalize(m);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s.R[k] = m.m[k];
+    }
 
     // Euler step of the body rates with gyroscopic term (:555-560); quadratic damping is zero
     {
         const float ox = s.om[0], oy = s.om[1], oz = s.om[2];
         const float ix = IXX * ox, iy = IYY * oy, iz = IZZ * oz;
-        const float cxx = (-oy) * iz - (-oz) * iy;
-        const float cyy = (-oz) * ix - (-ox) * iz;
-        const float czz = (-ox) * iy - (-oy) * ix;
+        const float cxx = oz * iy - oy * iz;          // cross(-omega, I omega)
+        const float cyy = ox * iz - oz * ix;
+        const float czz = oy * ix - ox * iy;
         s.om[0] = clampf(ox + SIM_DT * (INV_IXX * (cxx + tq0)), -OMEGA_MAX, OMEGA_MAX);
         s.om[1] = clampf(oy + SIM_DT * (INV_IYY * (cyy + tq1)), -OMEGA_MAX, OMEGA_MAX);
         s.om[2] = clampf(oz + SIM_DT * (INV_IZZ * (czz + tq2)), -OMEGA_MAX, OMEGA_MAX);
@@ -249,26 +268,33 @@ __device__ __forceinline__ void dynamics_substep(Agent& s, const float cmd[4], b
     if (pz > s.pos[2]) fl |= QS_FLAG_CRASHED_CEILING;
 
     // floor contact / friction, threshold = arm (:569-639)
-    float acc[3];
+    float fx = s.R[2] * thrust_z, fy = s.R[5] * thrust_z;
+    const float fz = s.R[8] * thrust_z;
     if (s.pos[2] <= ARM) {
         s.pos[2] = ARM;
-        float fx = s.R[2] * thrust_z, fy = s.R[5] * thrust_z;
-        const float fz = s.R[8] * thrust_z;
         if (fl & QS_FLAG_ON_FLOOR) {
             yaw_only(s.R);
             const float fric = FLOOR_MU * (MASS * GRAV - fz);
-            if (norm3(s.vel[0], s.vel[1], s.vel[2]) < EPS_DYN) {
-                const float mag = fmaxf(sqrtf(fx * fx + fy * fy) - fric, 0.f);
-                if (mag == 0.f) {
-                    fx = 0.f; fy = 0.f;
-                } else {
-                    float sa, ca;
-                    sincosf(atan2f(fy, fx), &sa, &ca);
-                    fx = mag * ca; fy = mag * sa;
+            const float v2 = s.vel[0] * s.vel[0] + s.vel[1] * s.vel[1] + s.vel[2] * s.vel[2];
+            if (v2 < EPS_DYN * EPS_DYN) {
+                // at rest: static friction eats the horizontal force (direction kept: cos/sin of atan2(fy, fx))
+                const float f2 = fx * fx + fy * fy;
+                const float fm = fsqrt(f2);
+                const float mag = fmaxf(fm - fric, 0.f);
+                if (fm > 0.f) {
+                    const float sc = mag * frcp(fm);
+                    fx *= sc; fy *= sc;
+                } else {                                // atan2(0, 0) = 0: the residual force points along +x
+                    fx = mag; fy = 0.f;
                 }
             } else {
-                float sa, ca;
-                sincosf(atan2f(s.vel[1], s.vel[0]), &sa, &ca);
+                // sliding: friction against the horizontal velocity direction; atan2(0, 0) = 0 -> direction (1, 0)
+                const float h2 = s.vel[0] * s.vel[0] + s.vel[1] * s.vel[1];
+                float ca = 1.f, sa = 0.f;
+                if (h2 > 0.f) {
+                    const float inv = frsqrt(h2);
+                    ca = s.vel[0] * inv; sa = s.vel[1] * inv;
+                }
                 fx -= ca * fric; fy -= sa * fric;
             }
         } else {
@@ -276,25 +302,27 @@ __device__ __forceinline__ void dynamics_substep(Agent& s, const float cmd[4], b
             s.vel[0] = s.vel[1] = s.vel[2] = 0.f;
             s.om[0] = s.om[1] = s.om[2] = 0.f;
             if (s.R[8] < 0.f) {                         // upside down: random yaw (:616-619)
-                const float4 u = rng_uniform4(key, SITE_FLOOR_YAW, i, 0, 0);
-                const float uu = sub == 0 ? u.x : u.y;
-                set_yaw(s.R, -PI_F + (PI_F - (-PI_F)) * uu);
+                const float2 cs = floor_random_yaw(key, i, sub);
+                s.R[0] = cs.x; s.R[1] = -cs.y; s.R[2] = 0.f; s.R[3] = cs.y; s.R[4] = cs.x; s.R[5] = 0.f;
+                s.R[6] = 0.f; s.R[7] = 0.f; s.R[8] = 1.f;
             } else {
                 yaw_only(s.R);
             }
 #pragma unroll
             for (int m = 0; m < 4; ++m) { s.rd[m] = 0.f; s.cd[m] = 0.f; }
         }
-        acc[0] = INV_MASS * fx; acc[1] = INV_MASS * fy; acc[2] = fmaxf(0.f, -GRAV + INV_MASS * fz);
+        // the force was taken with the pre-flattening rotation (:576), as here
+        s.vel[0] += SIM_DT * (INV_MASS * fx);
+        s.vel[1] += SIM_DT * (INV_MASS * fy);
+        s.vel[2] += SIM_DT * fmaxf(0.f, -GRAV + INV_MASS * fz);
     } else {
         fl &= ~QS_FLAG_ON_FLOOR;
-        acc[0] = INV_MASS * (s.R[2] * thrust_z);
-        acc[1] = INV_MASS * (s.R[5] * thrust_z);
-        acc[2] = -GRAV + INV_MASS * (s.R[8] * thrust_z);
+        s.vel[0] += SIM_DT * (INV_MASS * fx);
+        s.vel[1] += SIM_DT * (INV_MASS * fy);
+        s.vel[2] += SIM_DT * (-GRAV + INV_MASS * fz);
     }
     s.flags = fl;
-    // velocity with the NEW acceleration (:645); vel_damp = 0.  The accelerometer reading (:648) is never observed.
-    s.vel[0] += SIM_DT * acc[0]; s.vel[1] += SIM_DT * acc[1]; s.vel[2] += SIM_DT * acc[2];
+    // velocity used the NEW acceleration (:645); vel_damp = 0.  The accelerometer reading (:648) is never observed.
 }
 
 // rot2quat -> quat2R round trip of the observed rotation (sensor_noise.py:34-63,205-210; quad_utils.py:133-138);
@@ -303,167 +331,215 @@ __device__ __forceinline__ void observed_rotation(const float R[9], float out[9]
     const float trace = R[0] + R[4] + R[8];
     float qw, qx, qy, qz;
     if (trace > 0.f) {
-        const float S = sqrtf(trace + 1.0f) * 2.f;
-        qw = 0.25f * S; qx = (R[7] - R[5]) / S; qy = (R[2] - R[6]) / S; qz = (R[3] - R[1]) / S;
+        const float S = fsqrt(trace + 1.0f) * 2.f, iS = frcp(S);
+        qw = 0.25f * S; qx = (R[7] - R[5]) * iS; qy = (R[2] - R[6]) * iS; qz = (R[3] - R[1]) * iS;
     } else if (R[0] > R[4] && R[0] > R[8]) {
-        const float S = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f;
-        qw = (R[7] - R[5]) / S; qx = 0.25f * S; qy = (R[1] + R[3]) / S; qz = (R[2] + R[6]) / S;
+        const float S = fsqrt(1.0f + R[0] - R[4] - R[8]) * 2.f, iS = frcp(S);
+        qw = (R[7] - R[5]) * iS; qx = 0.25f * S; qy = (R[1] + R[3]) * iS; qz = (R[2] + R[6]) * iS;
     } else if (R[4] > R[8]) {
-        const float S = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f;
-        qw = (R[2] - R[6]) / S; qx = (R[1] + R[3]) / S; qy = 0.25f * S; qz = (R[5] + R[7]) / S;
+        const float S = fsqrt(1.0f + R[4] - R[0] - R[8]) * 2.f, iS = frcp(S);
+        qw = (R[2] - R[6]) * iS; qx = (R[1] + R[3]) * iS; qy = 0.25f * S; qz = (R[5] + R[7]) * iS;
     } else {
-        const float S = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f;
-        qw = (R[3] - R[1]) / S; qx = (R[2] + R[6]) / S; qy = (R[5] + R[7]) / S; qz = 0.25f * S;
+        const float S = fsqrt(1.0f + R[8] - R[0] - R[4]) * 2.f, iS = frcp(S);
+        qw = (R[3] - R[1]) * iS; qx = (R[2] + R[6]) * iS; qy = (R[5] + R[7]) * iS; qz = 0.25f * S;
     }
-    out[0] = 1.0f - 2.f * qy * qy - 2.f * qz * qz; out[1] = 2.f * qx * qy - 2.f * qz * qw; out[2] = 2.f * qx * qz + 2.f * qy * qw;
-    out[3] = 2.f * qx * qy + 2.f * qz * qw; out[4] = 1.0f - 2.f * qx * qx - 2.f * qz * qz; out[5] = 2.f * qy * qz - 2.f * qx * qw;
-    out[6] = 2.f * qx * qz - 2.f * qy * qw; out[7] = 2.f * qy * qz + 2.f * qx * qw; out[8] = 1.0f - 2.f * qx * qx - 2.f * qy * qy;
+    const float xx = 2.f * qx * qx, yy = 2.f * qy * qy, zz = 2.f * qz * qz;
+    const float xy = 2.f * qx * qy, xz = 2.f * qx * qz, yz = 2.f * qy * qz;
+    const float wx = 2.f * qx * qw, wy = 2.f * qy * qw, wz = 2.f * qz * qw;
+    out[0] = 1.0f - yy - zz; out[1] = xy - wz; out[2] = xz + wy;
+    out[3] = xy + wz; out[4] = 1.0f - xx - zz; out[5] = yz - wx;
+    out[6] = xz - wy; out[7] = yz + wx; out[8] = 1.0f - xx - yy;
+}
+
+// fresh sensor-noise draw for a non-default site (after a contact response / a reset)
+__device__ __noinline__ Noise9 sensor_noise(RngKey key, uint32_t site, int i) {
+    const float4 a = rng_normal4(key, site, i, 0, 0), b = rng_normal4(key, site, i, 0, 1), c = rng_normal4(key, site, i, 0, 2);
+    Noise9 n;
+    n.p[0] = POS_NOISE_STD * a.x; n.p[1] = POS_NOISE_STD * a.y; n.p[2] = POS_NOISE_STD * a.z;
+    n.v[0] = VEL_NOISE_STD * a.w; n.v[1] = VEL_NOISE_STD * b.x; n.v[2] = VEL_NOISE_STD * b.y;
+    n.w[0] = GYRO_NOISE_STD * b.z; n.w[1] = GYRO_NOISE_STD * b.w; n.w[2] = GYRO_NOISE_STD * c.x;
+    return n;
 }
 
 // compute_new_vel, collisions/utils.py:8-18
-__device__ __forceinline__ void compute_new_vel(float u, float max_vel_magn, float vel[3], const float shift[3],
-                                                float low, float high) {
+__device__ __forceinline__ V3 compute_new_vel(float u, float max_vel_magn, V3 vel, V3 shift, float low, float high) {
     const float decay = low + (high - low) * u;
-    const float nx = vel[0] + shift[0], ny = vel[1] + shift[1], nz = vel[2] + shift[2];
-    float mag = norm3(nx, ny, nz);
+    const float nx = vel.x + shift.x, ny = vel.y + shift.y, nz = vel.z + shift.z;
+    float mag = sqrtf(nx * nx + ny * ny + nz * nz);
     const float den = (mag == 0.f) ? mag + EPS_COL : mag;
     const float dx = nx / den, dy = ny / den, dz = nz / den;
     mag = fminf(mag * decay, max_vel_magn);
-    const float vx = dx * mag, vy = dy * mag, vz = dz * mag;
-    vel[0] += vx - vel[0]; vel[1] += vy - vel[1]; vel[2] += vz - vel[2];
+    V3 out;
+    out.x = vel.x + (dx * mag - vel.x); out.y = vel.y + (dy * mag - vel.y); out.z = vel.z + (dz * mag - vel.z);
+    return out;
 }
 
-// compute_new_omega, collisions/utils.py:22-33 (u3 = direction uniforms, um = magnitude uniform)
-__device__ __forceinline__ void compute_new_omega(float u0, float u1, float u2, float um, float magn_scale, float out[3]) {
+// compute_new_omega, collisions/utils.py:22-33 (three direction uniforms, one magnitude uniform)
+__device__ __forceinline__ V3 compute_new_omega(float u0, float u1, float u2, float um, float magn_scale) {
     const float omega_max = magn_scale * PI_F;
     const float x = -1.f + 2.f * u0, y = -1.f + 2.f * u1, z = -1.f + 2.f * u2;
-    const float mag = norm3(x, y, z);
+    const float mag = sqrtf(x * x + y * y + z * z);
     const float den = (mag == 0.f) ? mag + EPS_COL : mag;
     const float lo = omega_max * 0.5f;
     const float m = lo + (omega_max - lo) * um;
-    out[0] = x / den * m; out[1] = y / den * m; out[2] = z / den * m;
+    V3 out;
+    out.x = x / den * m; out.y = y / den * m; out.z = z / den * m;
+    return out;
 }
 
 // perform_collision_between_drones, collisions/quadrotors.py:24-59.  Every lane of the env evaluates the pair
 // (a < b) from shuffled copies of both drones and keyed draws, lanes a and b keep their half of the result.
-__device__ __forceinline__ void pair_response(const RngKey& key, int a, int b, const float p1[3], float v1[3],
-                                              const float p2[3], float v2[3], float domega[3]) {
-    float nx = p1[0] - p2[0], ny = p1[1] - p2[1], nz = p1[2] - p2[2];
-    const float nm = norm3(nx, ny, nz);
+__device__ __noinline__ PairOut pair_response(RngKey key, int a, int b, V3 p1, V3 v1, V3 p2, V3 v2) {
+    float nx = p1.x - p2.x, ny = p1.y - p2.y, nz = p1.z - p2.z;
+    const float nm = sqrtf(nx * nx + ny * ny + nz * nz);
     const float den = (nm == 0.f) ? nm + EPS_COL : nm;
     nx /= den; ny /= den; nz /= den;
-    const float v1n = v1[0] * nx + v1[1] * ny + v1[2] * nz;
-    const float v2n = v2[0] * nx + v2[1] * ny + v2[2] * nz;
+    const float v1n = v1.x * nx + v1.y * ny + v1.z * nz;
+    const float v2n = v2.x * nx + v2.y * ny + v2.z * nz;
     const float ch[3] = {(v2n - v1n) * nx, (v2n - v1n) * ny, (v2n - v1n) * nz};
-    float s1[3] = {ch[0], ch[1], ch[2]}, s2[3] = {-ch[0], -ch[1], -ch[2]};
+    V3 s1 = {ch[0], ch[1], ch[2]}, s2 = {-ch[0], -ch[1], -ch[2]};
+#pragma unroll 1
     for (int t = 0; t < 3; ++t) {
         const float4 n0 = rng_normal4(key, SITE_PAIR_N, a, b, 3 * t), n1 = rng_normal4(key, SITE_PAIR_N, a, b, 3 * t + 1),
                      n2 = rng_normal4(key, SITE_PAIR_N, a, b, 3 * t + 2);
-        const float cons[3] = {0.8f * n0.x, 0.8f * n0.y, 0.8f * n0.z};
-        const float e1[3] = {n0.w, n1.x, n1.y}, e2[3] = {n1.z, n1.w, n2.x};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            s1[k] = ch[k] + (cons[k] + 0.15f * e1[k]);
-            s2[k] = -ch[k] + (-cons[k] + 0.15f * e2[k]);
-        }
-        const float d1 = (v1[0] + s1[0]) * nx + (v1[1] + s1[1]) * ny + (v1[2] + s1[2]) * nz;
-        const float d2 = (v2[0] + s2[0]) * nx + (v2[1] + s2[1]) * ny + (v2[2] + s2[2]) * nz;
+        s1.x = ch[0] + (0.8f * n0.x + 0.15f * n0.w); s1.y = ch[1] + (0.8f * n0.y + 0.15f * n1.x); s1.z = ch[2] + (0.8f * n0.z + 0.15f * n1.y);
+        s2.x = -ch[0] + (-0.8f * n0.x + 0.15f * n1.z); s2.y = -ch[1] + (-0.8f * n0.y + 0.15f * n1.w); s2.z = -ch[2] + (-0.8f * n0.z + 0.15f * n2.x);
+        const float d1 = (v1.x + s1.x) * nx + (v1.y + s1.y) * ny + (v1.z + s1.z) * nz;
+        const float d2 = (v2.x + s2.x) * nx + (v2.y + s2.y) * ny + (v2.z + s2.z) * nz;
         if (d1 > 0.f && 0.f > d2) break;
     }
-    const float maxv = fmaxf(norm3(v1[0], v1[1], v1[2]), norm3(v2[0], v2[1], v2[2]));
+    const float maxv = fmaxf(sqrtf(v1.x * v1.x + v1.y * v1.y + v1.z * v1.z), sqrtf(v2.x * v2.x + v2.y * v2.y + v2.z * v2.z));
     const float4 u0 = rng_uniform4(key, SITE_PAIR_U, a, b, 0), u1 = rng_uniform4(key, SITE_PAIR_U, a, b, 1);
-    compute_new_vel(u0.x, maxv, v1, s1, 0.2f, 0.8f);
-    compute_new_vel(u0.y, maxv, v2, s2, 0.2f, 0.8f);
-    compute_new_omega(u0.z, u0.w, u1.x, u1.y, 20.0f, domega);
+    PairOut o;
+    o.v1 = compute_new_vel(u0.x, maxv, v1, s1, 0.2f, 0.8f);
+    o.v2 = compute_new_vel(u0.y, maxv, v2, s2, 0.2f, 0.8f);
+    o.dom = compute_new_omega(u0.z, u0.w, u1.x, u1.y, 20.0f);
+    return o;
 }
 
 // perform_collision_with_obstacle, collisions/obstacles.py:23-50 (obstacle z = room_height / 2, quadrotor_multi.py:322)
-__device__ __forceinline__ void obstacle_response(const RngKey& key, int i, Agent& s, float ox, float oy, float oz,
-                                                  float obst_half_size) {
-    float nx = s.pos[0] - ox, ny = s.pos[1] - oy;
+__device__ __noinline__ KickVO obstacle_response(RngKey key, int i, V3 pos, V3 vel, float ox, float oy, float oz,
+                                                 float obst_half_size) {
+    float nx = pos.x - ox, ny = pos.y - oy;
     const float nm = sqrtf(nx * nx + ny * ny);
     const float den = (nm == 0.f) ? nm + EPS_COL : nm;
     nx /= den; ny /= den;
-    const float vmag = norm3(s.vel[0], s.vel[1], s.vel[2]);
-    const float nv[3] = {vmag * nx, vmag * ny, 0.f};
+    const float vmag = sqrtf(vel.x * vel.x + vel.y * vel.y + vel.z * vel.z);
+    const float nvx = vmag * nx, nvy = vmag * ny;
     float noise[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
     for (int t = 0; t < 3; ++t) {
         const float4 n0 = rng_normal4(key, SITE_OBST_N, i, 0, 2 * t), n1 = rng_normal4(key, SITE_OBST_N, i, 0, 2 * t + 1);
-        const float tmp[3] = {0.1f * n0.x + 0.05f * n0.w, 0.1f * n0.y + 0.05f * n1.x, 0.1f * n0.z + 0.05f * n1.y};
-        if ((nv[0] + tmp[0]) * nx + (nv[1] + tmp[1]) * ny > 0.f) {
-            noise[0] = tmp[0]; noise[1] = tmp[1]; noise[2] = tmp[2];
+        const float tx = 0.1f * n0.x + 0.05f * n0.w, ty = 0.1f * n0.y + 0.05f * n1.x, tz = 0.1f * n0.z + 0.05f * n1.y;
+        if ((nvx + tx) * nx + (nvy + ty) * ny > 0.f) {
+            noise[0] = tx; noise[1] = ty; noise[2] = tz;
             break;
         }
     }
     const float4 u0 = rng_uniform4(key, SITE_OBST_U, i, 0, 0), u1 = rng_uniform4(key, SITE_OBST_U, i, 0, 1);
-    const float shift[3] = {nv[0] - s.vel[0] + noise[0], nv[1] - s.vel[1] + noise[1], nv[2] - s.vel[2] + noise[2]};
-    const bool inside = norm3(s.pos[0] - ox, s.pos[1] - oy, s.pos[2] - oz) < obst_half_size;
-    compute_new_vel(u0.x, vmag, s.vel, shift, inside ? 1.0f : 0.2f, inside ? 1.0f : 0.8f);
-    float dw[3];
-    compute_new_omega(u0.y, u0.z, u0.w, u1.x, 1.0f, dw);
-    s.om[0] += dw[0]; s.om[1] += dw[1]; s.om[2] += dw[2];
+    const V3 shift = {nvx - vel.x + noise[0], nvy - vel.y + noise[1], 0.f - vel.z + noise[2]};
+    const float dx = pos.x - ox, dy = pos.y - oy, dz = pos.z - oz;
+    const bool inside = sqrtf(dx * dx + dy * dy + dz * dz) < obst_half_size;
+    KickVO o;
+    o.vel = compute_new_vel(u0.x, vmag, vel, shift, inside ? 1.0f : 0.2f, inside ? 1.0f : 0.8f);
+    o.dom = compute_new_omega(u0.y, u0.z, u0.w, u1.x, 1.0f);
+    return o;
 }
 
-__device__ __forceinline__ void room_omega_kick(float u0, float u1, float u2, float um, Agent& s) {
+__device__ __forceinline__ V3 room_omega_kick(float u0, float u1, float u2, float um) {
     const float omega_max = 20.f * PI_F;
-    float x = -1.f + 2.f * u0, y = -1.f + 2.f * u1, z = -1.f + 2.f * u2;
-    const float inv = 1.f / (norm3(x, y, z) + 1e-5f);
+    const float x = -1.f + 2.f * u0, y = -1.f + 2.f * u1, z = -1.f + 2.f * u2;
+    const float inv = 1.f / (sqrtf(x * x + y * y + z * z) + 1e-5f);
     const float lo = omega_max * 0.5f;
     const float m = lo + (omega_max - lo) * um;
-    s.om[0] += x * inv * m; s.om[1] += y * inv * m; s.om[2] += z * inv * m;
+    V3 o = {x * inv * m, y * inv * m, z * inv * m};
+    return o;
 }
 
-// perform_collision_with_wall, collisions/room.py:6-44
-__device__ __forceinline__ void wall_response(const RngKey& key, int i, Agent& s, const StepParams& p) {
+// perform_collision_with_wall, collisions/room.py:6-44.  touch_* say which wall the clipped position sits on.
+__device__ __noinline__ KickVO wall_response(RngKey key, int i, V3 vel, int touch_x, int touch_y) {
     const float4 u0 = rng_uniform4(key, SITE_WALL_U, i, 0, 0), u1 = rng_uniform4(key, SITE_WALL_U, i, 0, 1),
                  u2 = rng_uniform4(key, SITE_WALL_U, i, 0, 2);
-    const float speed = norm3(s.vel[0], s.vel[1], s.vel[2]);
+    const float speed = sqrtf(vel.x * vel.x + vel.y * vel.y + vel.z * vel.z);
     const float lo = 0.2f * speed, hi = 0.8f * speed;
     const float real_speed = clampf(lo + (hi - lo) * u0.x, 0.1f, 6.0f);
     float dx = -1.f + 2.f * u0.y, dy = -1.f + 2.f * u0.z;
-    if (s.pos[0] == p.room_lo[0]) dx = 0.1f + (1.0f - 0.1f) * u1.x;
-    else if (s.pos[0] == p.room_hi[0]) dx = -1.0f + (-0.1f - -1.0f) * u1.x;
-    if (s.pos[1] == p.room_lo[1]) dy = 0.1f + (1.0f - 0.1f) * u1.y;
-    else if (s.pos[1] == p.room_hi[1]) dy = -1.0f + (-0.1f - -1.0f) * u1.y;
+    if (touch_x < 0) dx = 0.1f + (1.0f - 0.1f) * u1.x;
+    else if (touch_x > 0) dx = -1.0f + (-0.1f - -1.0f) * u1.x;
+    if (touch_y < 0) dy = 0.1f + (1.0f - 0.1f) * u1.y;
+    else if (touch_y > 0) dy = -1.0f + (-0.1f - -1.0f) * u1.y;
     const float dz = -1.0f + (-0.5f - -1.0f) * u1.z;
-    const float inv = 1.f / (norm3(dx, dy, dz) + 1e-5f);
-    s.vel[0] = real_speed * (dx * inv); s.vel[1] = real_speed * (dy * inv); s.vel[2] = real_speed * (dz * inv);
-    room_omega_kick(u1.w, u2.x, u2.y, u2.z, s);
+    const float inv = 1.f / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-5f);
+    KickVO o;
+    o.vel.x = real_speed * (dx * inv); o.vel.y = real_speed * (dy * inv); o.vel.z = real_speed * (dz * inv);
+    o.dom = room_omega_kick(u1.w, u2.x, u2.y, u2.z);
+    return o;
 }
 
 // perform_collision_with_ceiling, collisions/room.py:91-113
-__device__ __forceinline__ void ceiling_response(const RngKey& key, int i, Agent& s) {
+__device__ __noinline__ KickVO ceiling_response(RngKey key, int i, V3 vel) {
     const float4 u0 = rng_uniform4(key, SITE_CEIL_U, i, 0, 0), u1 = rng_uniform4(key, SITE_CEIL_U, i, 0, 1),
                  u2 = rng_uniform4(key, SITE_CEIL_U, i, 0, 2);
-    const float speed = norm3(s.vel[0], s.vel[1], s.vel[2]);
+    const float speed = sqrtf(vel.x * vel.x + vel.y * vel.y + vel.z * vel.z);
     const float lo = 0.2f * speed, hi = 0.8f * speed;
     const float real_speed = clampf(lo + (hi - lo) * u0.x, 0.1f, 6.0f);
     const float dx = -1.f + 2.f * u0.y, dy = -1.f + 2.f * u0.z;
     const float dz = -1.0f + (-0.5f - -1.0f) * u1.x;
-    const float inv = 1.f / (norm3(dx, dy, dz) + 1e-5f);
-    s.vel[0] = real_speed * (dx * inv); s.vel[1] = real_speed * (dy * inv); s.vel[2] = real_speed * (dz * inv);
-    room_omega_kick(u1.y, u1.z, u1.w, u2.x, s);
+    const float inv = 1.f / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-5f);
+    KickVO o;
+    o.vel.x = real_speed * (dx * inv); o.vel.y = real_speed * (dy * inv); o.vel.z = real_speed * (dz * inv);
+    o.dom = room_omega_kick(u1.y, u1.z, u1.w, u2.x);
+    return o;
 }
 
-// QuadrotorSingle._reset, quadrotor_single.py:387-447: spawn jitter, z >= 0.75, random yaw facing the origin,
-// zero rates and motor state, cleared contact flags.  OU state and the SVD counter are NOT reset (Appendix D-9).
-__device__ __forceinline__ void reset_agent(Agent& s, const RngKey& key, int i, const float spawn[3], float box) {
+// downwash push on drone `me` sitting in the cylinder below drone `other` (aerodynamics/downwash.py:27-66);
+// d = |p_me - p_other|, (zx, zy, zz) = body z-axis of `other`.  Returns delta velocity / delta omega.
+__device__ __noinline__ KickVO downwash_kick(RngKey key, int other, int me, float d, float zx, float zy, float zz) {
+    const float4 ui = rng_uniform4(key, SITE_DW_I, other, 0, 0);
+    const float4 u0 = rng_uniform4(key, SITE_DW_IJ, other, me, 0), u1 = rng_uniform4(key, SITE_DW_IJ, other, me, 1);
+    const float acc = fmaxf(1e-6f, (6.f / 17.f) * (-10.f * d + 7.f) + (-0.1f + 0.2f * ui.x));
+    const float omd = fmaxf(1e-6f, 0.3f * (d - 1.f) * (d - 1.f) + (-0.01f + 0.02f * ui.y));
+    float ax = zx + (-0.1f + 0.2f * u0.x), ay = zy + (-0.1f + 0.2f * u0.y), az = zz + (-0.1f + 0.2f * u0.z);
+    float mag = sqrtf(ax * ax + ay * ay + az * az);
+    float den = (mag == 0.f) ? mag + 1e-6f : mag;
+    ax = -(ax / den); ay = -(ay / den); az = -(az / den);
+    const float bx = -1.f + 2.f * u0.w, by = -1.f + 2.f * u1.x, bz = -1.f + 2.f * u1.y;
+    mag = sqrtf(bx * bx + by * by + bz * bz);
+    den = (mag == 0.f) ? mag + 1e-6f : mag;
+    KickVO o;
+    o.vel.x = acc * ax * CONTROL_DT; o.vel.y = acc * ay * CONTROL_DT; o.vel.z = acc * az * CONTROL_DT;
+    o.dom.x = omd * (bx / den) * CONTROL_DT; o.dom.y = omd * (by / den) * CONTROL_DT; o.dom.z = omd * (bz / den) * CONTROL_DT;
+    return o;
+}
+
+// QuadrotorSingle._reset, quadrotor_single.py:387-447: spawn jitter, z >= 0.75, random yaw facing the origin.
+__device__ __noinline__ ResetPose reset_pose(RngKey key, int i, V3 spawn, float box) {
     const float4 u = rng_uniform4(key, SITE_SPAWN_U, i, 0, 0);
-    s.pos[0] = (-box + (box - (-box)) * u.x) + spawn[0];
-    s.pos[1] = (-box + (box - (-box)) * u.y) + spawn[1];
-    s.pos[2] = fmaxf((-box + (box - (-box)) * u.z) + spawn[2], 0.75f);
+    ResetPose r;
+    r.pos.x = (-box + (box - (-box)) * u.x) + spawn.x;
+    r.pos.y = (-box + (box - (-box)) * u.y) + spawn.y;
+    r.pos.z = fmaxf((-box + (box - (-box)) * u.z) + spawn.z, 0.75f);
     // to_xyhat(-pos), quad_utils.py:75-82,112-116
-    float hx = -s.pos[0], hy = -s.pos[1];
+    float hx = -r.pos.x, hy = -r.pos.y;
     const float n = sqrtf(hx * hx + hy * hy);
     if (!(n < 0.00001f)) { hx /= n; hy /= n; }
     float sn = 0.f, cs = 1.f;
+#pragma unroll 1
     for (int k = 0; k < RESET_YAW_MAX_TRIES; ++k) {
         const float4 uy = rng_uniform4(key, SITE_RESET_YAW_U, i, 0, k >> 2);
         const float uu = (k & 3) == 0 ? uy.x : (k & 3) == 1 ? uy.y : (k & 3) == 2 ? uy.z : uy.w;
         sincosf(-PI_F + (PI_F - (-PI_F)) * uu, &sn, &cs);
         if (cs * hx + sn * hy >= 0.5f) break;          // rotation[:, 0] = (cos, sin, 0)
     }
-    s.R[0] = cs; s.R[1] = -sn; s.R[2] = 0.f; s.R[3] = sn; s.R[4] = cs; s.R[5] = 0.f; s.R[6] = 0.f; s.R[7] = 0.f; s.R[8] = 1.f;
+    r.cs = cs; r.sn = sn;
+    return r;
+}
+
+// apply a reset pose: zero rates and motor state, cleared contact flags.  OU state and the SVD counter are NOT
+// reset (Appendix D-9).
+__device__ __forceinline__ void apply_reset(Agent& s, const ResetPose& r) {
+    s.pos[0] = r.pos.x; s.pos[1] = r.pos.y; s.pos[2] = r.pos.z;
+    s.R[0] = r.cs; s.R[1] = -r.sn; s.R[2] = 0.f; s.R[3] = r.sn; s.R[4] = r.cs; s.R[5] = 0.f; s.R[6] = 0.f; s.R[7] = 0.f; s.R[8] = 1.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { s.vel[k] = 0.f; s.om[k] = 0.f; }
 #pragma unroll

@@ -5,6 +5,12 @@
 // Thread mapping: NP = next power of two >= N lanes per env, 32/NP envs per warp; lane i of a group owns
 // drone i.  All cross-drone traffic is __shfl_sync within the group; the env's pillar table is staged in
 // shared memory.  Follows QuadrotorEnvMulti.step, quadrotor_multi.py:413-724 (see DESIGN.md for the map).
+//
+// Shape of the code (measured, profiles/r01_*): at the benchmark sizes a B200 holds < 2 warps per SM
+// sub-partition, so the kernel is bound by instruction fetch and dependent-issue latency, not by HBM or
+// issue slots.  Hence: rolled loops (small instruction footprint), SFU approximations instead of the
+// branchy IEEE sqrt/div sequences, trigonometry-free contact code, and every rare path (contact
+// responses, random yaw, reset, re-drawn sensor noise) out of line.
 #pragma once
 #include "qs_device.cuh"
 
@@ -16,45 +22,35 @@ struct EnvCtr {
 
 // Observation row of one drone: get_state.py:6-72 (self part), quadrotor_multi.py:233-274 (neighbours),
 // obstacles/utils.py:5-27 (3x3 SDF).  `nvel` is the velocity the neighbour block sees (stale after a reset,
-// SURVEY Appendix D-6); `site` picks the sensor-noise draw.
+// SURVEY Appendix D-6); `nz` is the scaled sensor noise of this observation.
 template <int NP>
-__device__ __forceinline__ void write_observation(const StepParams& p, const RngKey& key, const Agent& s, const float nvel[3],
-                                                  int i, bool valid, uint32_t site, const float2* s_obst_env,
-                                                  float* __restrict__ row) {
+__device__ __forceinline__ void write_observation(const StepParams& p, const Agent& s, const float nvel[3], const Noise9& nz,
+                                                  int i, bool valid, const float2* s_obst_env, float* __restrict__ row) {
     // ---- self observation
-    float o[24];
     {
-        float np_[3] = {0.f, 0.f, 0.f}, nv[3] = {0.f, 0.f, 0.f}, nw[3] = {0.f, 0.f, 0.f};
+        const float px = s.pos[0] + nz.p[0], py = s.pos[1] + nz.p[1], pz = s.pos[2] + nz.p[2];
+        float rot[9];
         if (p.sense_noise) {
-            const float4 a = rng_normal4(key, site, i, 0, 0), b = rng_normal4(key, site, i, 0, 1),
-                         c = rng_normal4(key, site, i, 0, 2);
-            np_[0] = POS_NOISE_STD * a.x; np_[1] = POS_NOISE_STD * a.y; np_[2] = POS_NOISE_STD * a.z;
-            nv[0] = VEL_NOISE_STD * a.w; nv[1] = VEL_NOISE_STD * b.x; nv[2] = VEL_NOISE_STD * b.y;
-            nw[0] = GYRO_NOISE_STD * b.z; nw[1] = GYRO_NOISE_STD * b.w; nw[2] = GYRO_NOISE_STD * c.x;
-        }
-        const float px = s.pos[0] + np_[0], py = s.pos[1] + np_[1], pz = s.pos[2] + np_[2];
-        o[0] = px - s.goal[0]; o[1] = py - s.goal[1]; o[2] = pz - s.goal[2];
-        o[3] = s.vel[0] + nv[0]; o[4] = s.vel[1] + nv[1]; o[5] = s.vel[2] + nv[2];
-        if (p.sense_noise) {
-            observed_rotation(s.R, o + 6);
+            observed_rotation(s.R, rot);
         } else {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) o[6 + k] = s.R[k];
+            for (int k = 0; k < 9; ++k) rot[k] = s.R[k];
         }
-        o[15] = s.om[0] + nw[0]; o[16] = s.om[1] + nw[1]; o[17] = s.om[2] + nw[2];
-        if (p.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR) {
-            o[18] = pz;
-        } else if (p.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL) {
-            o[18] = clampf(px - p.room_lo[0], 0.f, 5.f); o[19] = clampf(py - p.room_lo[1], 0.f, 5.f);
-            o[20] = clampf(pz - p.room_lo[2], 0.f, 5.f);
-            o[21] = clampf(p.room_hi[0] - px, 0.f, 5.f); o[22] = clampf(p.room_hi[1] - py, 0.f, 5.f);
-            o[23] = clampf(p.room_hi[2] - pz, 0.f, 5.f);
-        }
-    }
-    if (valid) {
+        if (valid) {
+            row[0] = px - s.goal[0]; row[1] = py - s.goal[1]; row[2] = pz - s.goal[2];
+            row[3] = s.vel[0] + nz.v[0]; row[4] = s.vel[1] + nz.v[1]; row[5] = s.vel[2] + nz.v[2];
 #pragma unroll
-        for (int k = 0; k < 24; ++k)
-            if (k < p.S) row[k] = o[k];
+            for (int k = 0; k < 9; ++k) row[6 + k] = rot[k];
+            row[15] = s.om[0] + nz.w[0]; row[16] = s.om[1] + nz.w[1]; row[17] = s.om[2] + nz.w[2];
+            if (p.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR) {
+                row[18] = pz;
+            } else if (p.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL) {
+                row[18] = clampf(px - p.room_lo[0], 0.f, 5.f); row[19] = clampf(py - p.room_lo[1], 0.f, 5.f);
+                row[20] = clampf(pz - p.room_lo[2], 0.f, 5.f);
+                row[21] = clampf(p.room_hi[0] - px, 0.f, 5.f); row[22] = clampf(p.room_hi[1] - py, 0.f, 5.f);
+                row[23] = clampf(p.room_hi[2] - pz, 0.f, 5.f);
+            }
+        }
     }
 
     // ---- neighbour block: K nearest by distance + closing speed, or all others in index order
@@ -64,11 +60,11 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Rng
         float* nrow = row + p.S;
         if (p.K == p.N - 1) {
             int slot = 0;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) {
+#pragma unroll 1
+            for (int j = 0; j < p.N; ++j) {
                 const float qx = shfl<NP>(s.pos[0], j), qy = shfl<NP>(s.pos[1], j), qz = shfl<NP>(s.pos[2], j);
                 const float wx = shfl<NP>(nvel[0], j), wy = shfl<NP>(nvel[1], j), wz = shfl<NP>(nvel[2], j);
-                if (j < p.N && j != i && valid) {
+                if (j != i && valid) {
                     float* d = nrow + 6 * slot;
                     d[0] = clampf(qx - s.pos[0], -rx, rx); d[1] = clampf(qy - s.pos[1], -ry, ry);
                     d[2] = clampf(qz - s.pos[2], -rz, rz);
@@ -78,6 +74,7 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Rng
                 }
             }
         } else {
+            // score_j = max(|dp|, 0.01) + dp_hat . dv (quadrotor_multi.py:259-266); kept in registers
             float score[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
@@ -86,18 +83,21 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Rng
                 const float ux = shfl<NP>(nvel[0], j) - nvel[0], uy = shfl<NP>(nvel[1], j) - nvel[1],
                             uz = shfl<NP>(nvel[2], j) - nvel[2];
                 const float dist = fmaxf(norm3(dx, dy, dz), 0.01f);
-                const float sc = dist + ((dx / dist) * ux + (dy / dist) * uy + (dz / dist) * uz);
+                const float sc = dist + (dx * ux + dy * uy + dz * uz) * frcp(dist);
                 score[j] = (j < p.N && j != i) ? sc : __int_as_float(0x7f800000);   // +inf: never selected
             }
             uint32_t taken = 0u;
+#pragma unroll 1
             for (int k = 0; k < p.K; ++k) {
                 float best = __int_as_float(0x7f800000);
                 int bj = -1;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const bool ok = !((taken >> j) & 1u) && j < p.N && j != i;
                     // stable argsort: strictly smaller score wins, ties keep the lower index (Appendix D-11)
-                    if (ok && (bj < 0 || score[j] < best)) { best = score[j]; bj = j; }
+                    const bool cand = !((taken >> j) & 1u) && j < p.N && j != i;
+                    const bool better = cand && (bj < 0 || score[j] < best);
+                    best = better ? score[j] : best;
+                    bj = better ? j : bj;
                 }
                 const int src = bj < 0 ? i : bj;
                 taken |= 1u << src;
@@ -114,42 +114,39 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Rng
         }
     }
 
-    // ---- 3x3 signed-distance patch around the drone (resolution 0.1 m)
+    // ---- 3x3 signed-distance patch around the drone (resolution 0.1 m): min over pillars of the squared distance,
+    //      one square root per cell (sqrt is monotone, so min-then-sqrt equals the reference's sqrt-then-min)
     if (p.use_obst) {
         const float res = 0.1f;
-        const float gx[3] = {s.pos[0] - res, s.pos[0], s.pos[0] + res};
-        const float gy[3] = {s.pos[1] - res, s.pos[1], s.pos[1] + res};
-        float best[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) best[c] = 100.0f * 100.0f;
+        const float gx0 = s.pos[0] - res, gx1 = s.pos[0], gx2 = s.pos[0] + res;
+        const float gy0 = s.pos[1] - res, gy1 = s.pos[1], gy2 = s.pos[1] + res;
+        float b0 = 1e4f, b1 = 1e4f, b2 = 1e4f, b3 = 1e4f, b4 = 1e4f, b5 = 1e4f, b6 = 1e4f, b7 = 1e4f, b8 = 1e4f;
+#pragma unroll 2
         for (int m = 0; m < p.M; ++m) {
             const float2 ob = s_obst_env[m];
-            float ex[3], ey[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float dx = gx[c] - ob.x, dy = gy[c] - ob.y;
-                ex[c] = dx * dx; ey[c] = dy * dy;
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) best[3 * a + b] = fminf(best[3 * a + b], ex[a] + ey[b]);
+            const float ex0 = (gx0 - ob.x) * (gx0 - ob.x), ex1 = (gx1 - ob.x) * (gx1 - ob.x), ex2 = (gx2 - ob.x) * (gx2 - ob.x);
+            const float ey0 = (gy0 - ob.y) * (gy0 - ob.y), ey1 = (gy1 - ob.y) * (gy1 - ob.y), ey2 = (gy2 - ob.y) * (gy2 - ob.y);
+            b0 = fminf(b0, ex0 + ey0); b1 = fminf(b1, ex0 + ey1); b2 = fminf(b2, ex0 + ey2);
+            b3 = fminf(b3, ex1 + ey0); b4 = fminf(b4, ex1 + ey1); b5 = fminf(b5, ex1 + ey2);
+            b6 = fminf(b6, ex2 + ey0); b7 = fminf(b7, ex2 + ey1); b8 = fminf(b8, ex2 + ey2);
         }
         if (valid) {
             float* srow = row + p.S + 6 * p.K;
-#pragma unroll
-            for (int c = 0; c < 9; ++c) srow[c] = sqrtf(best[c]) - p.obst_radius;
+            const float r = p.obst_radius;
+            srow[0] = fsqrt(b0) - r; srow[1] = fsqrt(b1) - r; srow[2] = fsqrt(b2) - r;
+            srow[3] = fsqrt(b3) - r; srow[4] = fsqrt(b4) - r; srow[5] = fsqrt(b5) - r;
+            srow[6] = fsqrt(b6) - r; srow[7] = fsqrt(b7) - r; srow[8] = fsqrt(b8) - r;
         }
     }
 }
 
 // Copy the next-episode tables into the live episode of one env and respawn its drones
-// (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).  Returns the velocity the neighbour block must see.
+// (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).  Called by ALL lanes of a warp (the branch around it is
+// warp-uniform); `do_reset` is per env.  Sets nvel to the velocity the neighbour block must see.
 template <int NP>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
                                           float nvel[3]) {
-    // Called by ALL lanes of a warp (the branch around it is warp-uniform); `do_reset` is per env.
     const DevState& st = p.st;
     if (do_reset && valid) {
         // stale velocity (Appendix D-6): the multi-env's self.vel is only refreshed by step()
@@ -162,8 +159,10 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
         st.slots[SL_STALE_VEL * st.a_pad + a] = make_float4(nvel[0], nvel[1], nvel[2], 0.f);
         const float4 g = st.next_goal[a], sp = st.next_spawn[a];
         s.goal[0] = g.x; s.goal[1] = g.y; s.goal[2] = g.z;
-        const float spawn[3] = {sp.w != 0.f ? sp.x : g.x, sp.w != 0.f ? sp.y : g.y, sp.w != 0.f ? sp.z : g.z};
-        reset_agent(s, key, i, spawn, p.use_obst ? 0.1f : 2.0f);      // box: quadrotor_single.py:215-218
+        V3 spawn;
+        spawn.x = sp.w != 0.f ? sp.x : g.x; spawn.y = sp.w != 0.f ? sp.y : g.y; spawn.z = sp.w != 0.f ? sp.z : g.z;
+        const ResetPose rp = reset_pose(key, i, spawn, p.use_obst ? 0.1f : 2.0f);      // box: quadrotor_single.py:215-218
+        apply_reset(s, rp);
         st.slots[SL_DIST_SUMS * st.a_pad + a] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (p.use_obst) {
@@ -219,12 +218,33 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
     }
     bool goal_dirty = false;
+    const float col_thr2 = p.col_thr * p.col_thr, falloff2 = p.falloff_thr * p.falloff_thr;
+    const float obst_thr2 = p.obst_col_thr * p.obst_col_thr;
 
+#pragma unroll 1
     for (int t = 0; t < p.T; ++t) {
         RngKey key;
         key.k0 = p.seed_lo; key.k1 = p.seed_hi;
         key.env = (uint32_t)(p.env_id_offset + env);
         key.step = (uint32_t)ctr.step_count;
+
+        // the draws every drone needs every step: OU thrust noise + first sensor-noise draw (4 Philox blocks, 4-way ILP)
+        Noise9 nz;
+        float4 ou_z;
+        {
+            const uint32_t c2[4] = {rng_c2(SITE_OU, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0)};
+            const uint32_t c3[4] = {0u, 0u, 1u, 2u};
+            uint4 blk[4];
+            philox4x32_10_x4(key.env, key.step, c2, c3, key.k0, key.k1, blk);
+            ou_z = normal4_of(blk[0]);
+            const float4 na = normal4_of(blk[1]), nb = normal4_of(blk[2]);
+            float nc0, nc1;
+            normal_pair(blk[3].x, blk[3].y, nc0, nc1);
+            const float on = p.sense_noise ? 1.f : 0.f;
+            nz.p[0] = on * POS_NOISE_STD * na.x; nz.p[1] = on * POS_NOISE_STD * na.y; nz.p[2] = on * POS_NOISE_STD * na.z;
+            nz.v[0] = on * VEL_NOISE_STD * na.w; nz.v[1] = on * VEL_NOISE_STD * nb.x; nz.v[2] = on * VEL_NOISE_STD * nb.y;
+            nz.w[0] = on * GYRO_NOISE_STD * nb.z; nz.w[1] = on * GYRO_NOISE_STD * nb.w; nz.w[2] = on * GYRO_NOISE_STD * nc0;
+        }
 
         // ================= per-drone part: QuadrotorSingle._step, quadrotor_single.py:341-357 =================
         float act[4] = {0.f, 0.f, 0.f, 0.f};
@@ -235,14 +255,12 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         float cmd[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) cmd[m] = 0.5f * (clampf(act[m], -1.f, 1.f) + 1.f);    // RawControl.step, quadrotor_control.py:53-57
-        {   // OU thrust noise, once per control step (numba_utils.py:101-105, quadrotor_dynamics.py:209)
-            const float4 z = rng_normal4(key, SITE_OU, i, 0, 0);
-            s.ou[0] += OU_THETA * (0.f - s.ou[0]) + OU_SIGMA * z.x;
-            s.ou[1] += OU_THETA * (0.f - s.ou[1]) + OU_SIGMA * z.y;
-            s.ou[2] += OU_THETA * (0.f - s.ou[2]) + OU_SIGMA * z.z;
-            s.ou[3] += OU_THETA * (0.f - s.ou[3]) + OU_SIGMA * z.w;
-        }
-#pragma unroll
+        // OU thrust noise, once per control step (numba_utils.py:101-105, quadrotor_dynamics.py:209)
+        s.ou[0] += OU_THETA * (0.f - s.ou[0]) + OU_SIGMA * ou_z.x;
+        s.ou[1] += OU_THETA * (0.f - s.ou[1]) + OU_SIGMA * ou_z.y;
+        s.ou[2] += OU_THETA * (0.f - s.ou[2]) + OU_SIGMA * ou_z.z;
+        s.ou[3] += OU_THETA * (0.f - s.ou[3]) + OU_SIGMA * ou_z.w;
+#pragma unroll 1
         for (int sub = 0; sub < SIM_STEPS; ++sub) {
             ctr.svd_count += 1;
             const bool do_svd = ctr.svd_count >= SVD_PERIOD;
@@ -252,9 +270,9 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         // compute_reward_weighted, quadrotor_single.py:34-92 (dt = SIM dt, raw unclipped action)
         const bool on_floor = (s.flags & QS_FLAG_ON_FLOOR) != 0u;
         const float dist = norm3(s.goal[0] - s.pos[0], s.goal[1] - s.pos[1], s.goal[2] - s.pos[2]);
-        const float raw_effort = sqrtf(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
+        const float raw_effort = fsqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
         const float raw_orient = on_floor ? 1.0f : -s.R[8];
-        const float raw_spin = sqrtf(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+        const float raw_spin = norm3(s.om[0], s.om[1], s.om[2]);
         const float raw_crash = on_floor ? 1.0f : 0.0f;
         float reward = -SIM_DT * (p.rew[QS_REW_POS] * dist + p.rew[QS_REW_EFFORT] * raw_effort + p.rew[QS_REW_CRASH] * raw_crash +
                                   p.rew[QS_REW_ORIENT] * raw_orient + p.rew[QS_REW_SPIN] * raw_spin);
@@ -265,45 +283,37 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
 
         // ================= env part: all-pairs pass (positions only) =================
         // calculate_collision_matrix (collisions/quadrotors.py:63-91), proximity penalties (:95-103), downwash
-        // detection (aerodynamics/downwash.py:4-51) — drone i scans every other drone j of its env.
+        // detection (aerodynamics/downwash.py:4-51) — drone i scans every other drone j of its env.  Thresholds are
+        // compared on squared distances (same predicate, no square root on the common path).
         uint32_t cur_col = 0u;
         float prox = 0.f;
         bool dw_applied = false;
         float dw_dv[3] = {0.f, 0.f, 0.f}, dw_dw[3] = {0.f, 0.f, 0.f};
         if (NP > 1) {
-            const float pen_ratio = -p.rew[QS_REW_QUADCOL_BIN_SMOOTH_MAX] / p.falloff_thr;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                const float qx = shfl<NP>(s.pos[0], j), qy = shfl<NP>(s.pos[1], j), qz = shfl<NP>(s.pos[2], j);
+            const float max_pen = p.rew[QS_REW_QUADCOL_BIN_SMOOTH_MAX];
+            const float pen_ratio = -max_pen / p.falloff_thr;
+#pragma unroll 1
+            for (int j = 0; j < p.N; ++j) {
+                const float dx = s.pos[0] - shfl<NP>(s.pos[0], j), dy = s.pos[1] - shfl<NP>(s.pos[1], j),
+                            dz = s.pos[2] - shfl<NP>(s.pos[2], j);
                 float zx = 0.f, zy = 0.f, zz = 0.f;
                 if (p.use_downwash) { zx = shfl<NP>(s.R[2], j); zy = shfl<NP>(s.R[5], j); zz = shfl<NP>(s.R[8], j); }
-                if (j < p.N && j != i && valid) {
-                    // same expression order as the reference for i<j: (p_lo - p_hi)^2 is symmetric
-                    const float dx = s.pos[0] - qx, dy = s.pos[1] - qy, dz = s.pos[2] - qz;
-                    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-                    if (d <= p.col_thr) cur_col |= 1u << j;
-                    if (d <= p.falloff_thr) prox += pen_ratio * d + p.rew[QS_REW_QUADCOL_BIN_SMOOTH_MAX];
-                    if (p.use_downwash) {
-                        // is drone i (me) inside the downwash cylinder below drone j?
-                        const float rel_z = dx * zx + dy * zy + dz * zz;
-                        const float rel_xy = sqrtf(d * d - rel_z * rel_z);         // NaN -> comparison false, as in numpy
-                        if (-0.7f < rel_z && rel_z < 0.f && rel_xy < 0.1f) {
-                            const float4 ui = rng_uniform4(key, SITE_DW_I, j, 0, 0);
-                            const float4 u0 = rng_uniform4(key, SITE_DW_IJ, j, i, 0), u1 = rng_uniform4(key, SITE_DW_IJ, j, i, 1);
-                            const float acc = fmaxf(1e-6f, (6.f / 17.f) * (-10.f * d + 7.f) + (-0.1f + 0.2f * ui.x));
-                            const float omd = fmaxf(1e-6f, 0.3f * (d - 1.f) * (d - 1.f) + (-0.01f + 0.02f * ui.y));
-                            float ax = zx + (-0.1f + 0.2f * u0.x), ay = zy + (-0.1f + 0.2f * u0.y), az = zz + (-0.1f + 0.2f * u0.z);
-                            float mag = norm3(ax, ay, az);
-                            float den = (mag == 0.f) ? mag + 1e-6f : mag;
-                            ax = -(ax / den); ay = -(ay / den); az = -(az / den);
-                            float bx = -1.f + 2.f * u0.w, by = -1.f + 2.f * u1.x, bz = -1.f + 2.f * u1.y;
-                            mag = norm3(bx, by, bz);
-                            den = (mag == 0.f) ? mag + 1e-6f : mag;
-                            dw_dv[0] += acc * ax * CONTROL_DT; dw_dv[1] += acc * ay * CONTROL_DT; dw_dv[2] += acc * az * CONTROL_DT;
-                            dw_dw[0] += omd * (bx / den) * CONTROL_DT; dw_dw[1] += omd * (by / den) * CONTROL_DT;
-                            dw_dw[2] += omd * (bz / den) * CONTROL_DT;
-                            dw_applied = true;
-                        }
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                const bool other = (j != i) && valid;
+                if (other && d2 <= falloff2) {
+                    const float d = fsqrt(d2);
+                    if (d2 <= col_thr2) cur_col |= 1u << j;
+                    prox += pen_ratio * d + max_pen;
+                }
+                if (p.use_downwash && other) {
+                    // is drone i (me) inside the downwash cylinder below drone j?  -0.7 < rel_z < 0 and rel_xy < 0.1
+                    const float rel_z = dx * zx + dy * zy + dz * zz;
+                    const float rxy2 = d2 - rel_z * rel_z;                 // negative -> sqrt is NaN in numpy -> false
+                    if (-0.7f < rel_z && rel_z < 0.f && rxy2 >= 0.f && rxy2 < 0.1f * 0.1f) {
+                        const KickVO k = downwash_kick(key, j, i, fsqrt(d2), zx, zy, zz);
+                        dw_dv[0] += k.vel.x; dw_dv[1] += k.vel.y; dw_dv[2] += k.vel.z;
+                        dw_dw[0] += k.dom.x; dw_dw[1] += k.dom.y; dw_dw[2] += k.dom.z;
+                        dw_applied = true;
                     }
                 }
             }
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         const int col_curr_tick = __popc(u_mask) / 2;
         const bool u_any = (u_mask & ~1u) != 0u;                                      // ids.any(): id 0 alone is falsy
         const float raw_quadcol = (u_any && in_u) ? -1.0f : 0.0f;
-        uint32_t new_pairs = cur_col & ~s.prev_col;                                   // pair-level novelty (:437-438)
+        const uint32_t new_pairs = cur_col & ~s.prev_col;                             // pair-level novelty (:437-438)
         const bool settled = (float)ctr.tick >= p.grace_steps;
         if (col_curr_tick > 0 && settled && in_u) s.flags &= ~QS_FLAG_NO_COL_AGENT;
         s.prev_col = cur_col;
@@ -322,26 +332,22 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         // obstacles: first pillar in index order within arm + radius (obstacles/utils.py:31-43), :462-488
         int hit = -1;
         if (p.use_obst) {
+#pragma unroll 4
             for (int m = p.M - 1; m >= 0; --m) {
                 const float2 ob = s_obst_env[m];
                 const float dx = s.pos[0] - ob.x, dy = s.pos[1] - ob.y;
-                if (sqrtf(dx * dx + dy * dy) <= p.obst_col_thr) hit = m;
+                hit = (dx * dx + dy * dy <= obst_thr2) ? m : hit;
             }
         }
         const bool new_obst = (hit >= 0) && !(s.flags & QS_FLAG_PREV_OBST) && valid;
         const uint32_t obst_mask = p.use_obst ? group_ballot<NP>(new_obst) : 0u;
         const float raw_obst = new_obst ? -1.0f : 0.0f;
         s.flags = (hit >= 0) ? (s.flags | QS_FLAG_PREV_OBST) : (s.flags & ~QS_FLAG_PREV_OBST);
-        int far35 = 0, far5 = 0;
+        bool far35 = false, far5 = false;
         if (new_obst && settled) {
             s.flags &= ~QS_FLAG_NO_COL_OBST;
             // distance to goal of the FIRST-draw noisy position (quadrotor_multi.py:474)
-            float nx = 0.f, ny = 0.f, nz = 0.f;
-            if (p.sense_noise) {
-                const float4 n = rng_normal4(key, SITE_SENSOR0, i, 0, 0);
-                nx = POS_NOISE_STD * n.x; ny = POS_NOISE_STD * n.y; nz = POS_NOISE_STD * n.z;
-            }
-            const float q = norm3((s.pos[0] + nx) - s.goal[0], (s.pos[1] + ny) - s.goal[1], (s.pos[2] + nz) - s.goal[2]);
+            const float q = norm3((s.pos[0] + nz.p[0]) - s.goal[0], (s.pos[1] + nz.p[1]) - s.goal[1], (s.pos[2] + nz.p[2]) - s.goal[2]);
             far35 = q > 3.5f; far5 = q > 5.0f;
         }
 
@@ -379,86 +385,101 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
             }
         }
 
+        // ballots of this step's discrete events.  NB: none of them may sit behind a short-circuit `||` / `&&` whose
+        // left side differs between the envs of a warp.
+        const uint32_t floor_m = group_ballot<NP>(floor_c), wall_m = group_ballot<NP>(wall_c),
+                       ceil_m = group_ballot<NP>(ceil_c), room_m = group_ballot<NP>(room_c);
+        const uint32_t dw_m = p.use_downwash ? group_ballot<NP>(dw_applied) : 0u;
+        const uint32_t new_pair_m = group_ballot<NP>(new_pairs != 0u && valid);
+        const bool kicked = (dw_m | new_pair_m | obst_mask | wall_m | ceil_m) != 0u;     // self_state_update_flag, :549-587
+
         // episode counters (lane 0 of the env), quadrotor_multi.py:448-456,468-478,522-526
         {
-            const uint32_t floor_m = group_ballot<NP>(floor_c), wall_m = group_ballot<NP>(wall_c),
-                           ceil_m = group_ballot<NP>(ceil_c), room_m = group_ballot<NP>(room_c);
-            const uint32_t f35 = group_ballot<NP>(far35 != 0), f5 = group_ballot<NP>(far5 != 0);
             const int n_obst = __popc(obst_mask);
             const bool any_event = col_curr_tick > 0 || n_obst > 0 || ((floor_m | wall_m | ceil_m | room_m) != 0u && settled);
-            if (any_event && i == 0 && env_ok) {
-                int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
-                c[QS_STAT_NUM_COLLISIONS] += col_curr_tick;
-                if (col_curr_tick > 0 && settled) c[QS_STAT_NUM_COLLISIONS_AFTER_SETTLE] += col_curr_tick;
-                if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) c[QS_STAT_NUM_COLLISIONS_FINAL_5S] += col_curr_tick;
-                c[QS_STAT_NUM_COLLISIONS_OBST] += n_obst;
-                if (settled) {
-                    c[QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE] += n_obst;
-                    c[QS_STAT_NUM_COLLISIONS_OBST_3_5] += __popc(f35);
-                    c[QS_STAT_NUM_COLLISIONS_OBST_5] += __popc(f5);
-                    c[QS_STAT_NUM_COLLISIONS_ROOM] += __popc(room_m);
-                    c[QS_STAT_NUM_COLLISIONS_FLOOR] += __popc(floor_m);
-                    c[QS_STAT_NUM_COLLISIONS_WALL] += __popc(wall_m);
-                    c[QS_STAT_NUM_COLLISIONS_CEILING] += __popc(ceil_m);
+            if (__any_sync(0xffffffffu, any_event)) {
+                const uint32_t f35 = group_ballot<NP>(far35), f5 = group_ballot<NP>(far5);
+                if (any_event && i == 0 && env_ok) {
+                    int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
+                    c[QS_STAT_NUM_COLLISIONS] += col_curr_tick;
+                    if (col_curr_tick > 0 && settled) c[QS_STAT_NUM_COLLISIONS_AFTER_SETTLE] += col_curr_tick;
+                    if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) c[QS_STAT_NUM_COLLISIONS_FINAL_5S] += col_curr_tick;
+                    c[QS_STAT_NUM_COLLISIONS_OBST] += n_obst;
+                    if (settled) {
+                        c[QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE] += n_obst;
+                        c[QS_STAT_NUM_COLLISIONS_OBST_3_5] += __popc(f35);
+                        c[QS_STAT_NUM_COLLISIONS_OBST_5] += __popc(f5);
+                        c[QS_STAT_NUM_COLLISIONS_ROOM] += __popc(room_m);
+                        c[QS_STAT_NUM_COLLISIONS_FLOOR] += __popc(floor_m);
+                        c[QS_STAT_NUM_COLLISIONS_WALL] += __popc(wall_m);
+                        c[QS_STAT_NUM_COLLISIONS_CEILING] += __popc(ceil_m);
+                    }
                 }
             }
         }
 
-        // ================= contact responses, quadrotor_multi.py:548-587 =================
-        bool kicked = false;
-        if (p.use_downwash) {
+        // ================= contact responses, quadrotor_multi.py:548-587 (rare: one warp-uniform branch) =================
+        if (__any_sync(0xffffffffu, kicked)) {
             if (dw_applied) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { s.vel[k] += dw_dv[k]; s.om[k] += dw_dw[k]; }
             }
-            kicked = group_ballot<NP>(dw_applied) != 0u;
-        }
-        if (NP > 1) {
-            // new colliding pairs, lexicographic order, one at a time (the second response of a drone sees the first)
-            uint32_t pending = new_pairs & ~((2u << i) - 1u);      // partners j > i: lane i owns pair (i, j)
-            if (!valid) pending = 0u;
-            while (__any_sync(0xffffffffu, pending != 0u)) {
-                // every lane of the warp runs the same shuffles; groups without a pending pair just idle
-                const uint32_t owners = group_ballot<NP>(pending != 0u);
-                const bool act = owners != 0u;
-                const int pa = act ? __ffs(owners) - 1 : 0;
-                const uint32_t pend_a = shfl_u<NP>(pending, pa);
-                const int pb = act ? __ffs(pend_a) - 1 : 0;
-                float p1[3], v1[3], p2[3], v2[3], dwv[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    p1[k] = shfl<NP>(s.pos[k], pa); v1[k] = shfl<NP>(s.vel[k], pa);
-                    p2[k] = shfl<NP>(s.pos[k], pb); v2[k] = shfl<NP>(s.vel[k], pb);
-                }
-                if (act) {
-                    pair_response(key, pa, pb, p1, v1, p2, v2, dwv);
-                    if (i == pa) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { s.vel[k] = v1[k]; s.om[k] += dwv[k]; }
-                        pending &= ~(1u << pb);
-                    } else if (i == pb) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { s.vel[k] = v2[k]; s.om[k] -= dwv[k]; }
+            if (NP > 1) {
+                // new colliding pairs, lexicographic order, one at a time (the second response of a drone sees the first)
+                uint32_t pending = new_pairs & ~((2u << i) - 1u);      // partners j > i: lane i owns pair (i, j)
+                if (!valid) pending = 0u;
+                while (__any_sync(0xffffffffu, pending != 0u)) {
+                    // every lane of the warp runs the same shuffles; groups without a pending pair just idle
+                    const uint32_t owners = group_ballot<NP>(pending != 0u);
+                    const bool act_pair = owners != 0u;
+                    const int pa = act_pair ? __ffs(owners) - 1 : 0;
+                    const uint32_t pend_a = shfl_u<NP>(pending, pa);
+                    const int pb = act_pair ? __ffs(pend_a) - 1 : 0;
+                    V3 p1, v1, p2, v2;
+                    p1.x = shfl<NP>(s.pos[0], pa); p1.y = shfl<NP>(s.pos[1], pa); p1.z = shfl<NP>(s.pos[2], pa);
+                    v1.x = shfl<NP>(s.vel[0], pa); v1.y = shfl<NP>(s.vel[1], pa); v1.z = shfl<NP>(s.vel[2], pa);
+                    p2.x = shfl<NP>(s.pos[0], pb); p2.y = shfl<NP>(s.pos[1], pb); p2.z = shfl<NP>(s.pos[2], pb);
+                    v2.x = shfl<NP>(s.vel[0], pb); v2.y = shfl<NP>(s.vel[1], pb); v2.z = shfl<NP>(s.vel[2], pb);
+                    if (act_pair && (i == pa || i == pb)) {
+                        const PairOut o = pair_response(key, pa, pb, p1, v1, p2, v2);
+                        if (i == pa) {
+                            s.vel[0] = o.v1.x; s.vel[1] = o.v1.y; s.vel[2] = o.v1.z;
+                            s.om[0] += o.dom.x; s.om[1] += o.dom.y; s.om[2] += o.dom.z;
+                            pending &= ~(1u << pb);
+                        } else {
+                            s.vel[0] = o.v2.x; s.vel[1] = o.v2.y; s.vel[2] = o.v2.z;
+                            s.om[0] -= o.dom.x; s.om[1] -= o.dom.y; s.om[2] -= o.dom.z;
+                        }
                     }
-                    kicked = true;
                 }
             }
-        }
-        if (p.use_obst) {
             if (new_obst) {
                 const float2 ob = s_obst_env[hit];
-                obstacle_response(key, i, s, ob.x, ob.y, 0.5f * (p.room_hi[2] - p.room_lo[2]) + p.room_lo[2], p.obst_half_size);
+                V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
+                const KickVO o = obstacle_response(key, i, pos, vel, ob.x, ob.y, 0.5f * (p.room_hi[2] - p.room_lo[2]) + p.room_lo[2],
+                                                   p.obst_half_size);
+                s.vel[0] = o.vel.x; s.vel[1] = o.vel.y; s.vel[2] = o.vel.z;
+                s.om[0] += o.dom.x; s.om[1] += o.dom.y; s.om[2] += o.dom.z;
             }
-            kicked = kicked || obst_mask != 0u;
+            if (wall_c) {
+                V3 vel = {s.vel[0], s.vel[1], s.vel[2]};
+                const int tx = s.pos[0] == p.room_lo[0] ? -1 : (s.pos[0] == p.room_hi[0] ? 1 : 0);
+                const int ty = s.pos[1] == p.room_lo[1] ? -1 : (s.pos[1] == p.room_hi[1] ? 1 : 0);
+                const KickVO o = wall_response(key, i, vel, tx, ty);
+                s.vel[0] = o.vel.x; s.vel[1] = o.vel.y; s.vel[2] = o.vel.z;
+                s.om[0] += o.dom.x; s.om[1] += o.dom.y; s.om[2] += o.dom.z;
+            }
+            if (ceil_c) {
+                V3 vel = {s.vel[0], s.vel[1], s.vel[2]};
+                const KickVO o = ceiling_response(key, i, vel);
+                s.vel[0] = o.vel.x; s.vel[1] = o.vel.y; s.vel[2] = o.vel.z;
+                s.om[0] += o.dom.x; s.om[1] += o.dom.y; s.om[2] += o.dom.z;
+            }
+            if (kicked) {
+                s.flags |= QS_FLAG_KICKED;
+                if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR1, i);      // fresh noise for every drone of the env (:598-599)
+            }
         }
-        {
-            if (wall_c) wall_response(key, i, s, p);
-            if (ceil_c) ceiling_response(key, i, s);
-            // NB: the ballot must not sit behind a short-circuit `||` — `kicked` differs between the envs of a warp
-            const bool room_any = group_ballot<NP>(wall_c || ceil_c) != 0u;
-            kicked = kicked || room_any;
-        }
-        if (kicked) s.flags |= QS_FLAG_KICKED;
 
         // ================= outputs of this step =================
         const long long ta = (long long)t * A + a;
@@ -480,7 +501,6 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
 
         // ================= episode end: latch statistics, auto-reset (quadrotor_multi.py:626-722) =================
         float nvel[3] = {s.vel[0], s.vel[1], s.vel[2]};
-        uint32_t site = kicked ? SITE_SENSOR1 : SITE_SENSOR0;
         const bool do_reset = done && env_ok;
         if (__any_sync(0xffffffffu, do_reset)) {          // warp-uniform branch
             if (do_reset && valid) {
@@ -502,14 +522,14 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
                 goal_dirty = true;
-                site = SITE_SENSOR_RESET;
+                if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
             }
         }
 
         // ================= observation (of the post-response, or freshly reset, state) =================
         if (!p.last_obs_only || t == p.T - 1) {
             float* row = p.obs + ((p.last_obs_only ? 0 : (long long)t * A) + a) * p.D;
-            write_observation<NP>(p, key, s, nvel, i, valid, site, s_obst_env, row);
+            write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, row);
         }
         ctr.step_count += 1;
     }
@@ -561,7 +581,11 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) c[k] = 0;
         st.env_ctr[env] = make_int4(0, ctr.step_count + 1, ctr.svd_count, ctr.episode_idx);
     }
-    write_observation<NP>(p, key, s, nvel, i, valid, SITE_SENSOR_RESET, s_obst_env, p.obs + a * p.D);
+    Noise9 nz;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { nz.p[k] = 0.f; nz.v[k] = 0.f; nz.w[k] = 0.f; }
+    if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
+    write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, p.obs + a * p.D);
     if (valid) store_agent(st, a, s, true);
 }
 

@@ -188,7 +188,16 @@ __global__ void k_read_stats(DevState st, int E, int N, int32_t* env_stats, floa
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
-static const int kBlock = 128;
+static int block_size() {
+    // threads per CTA (multiple of 32, <= 128); QS_BLOCK overrides for tuning experiments
+    static int b = 0;
+    if (b == 0) {
+        const char* e = getenv("QS_BLOCK");
+        b = e ? atoi(e) : 64;
+        if (b < 32 || b > 128 || (b % 32) != 0) b = 64;
+    }
+    return b;
+}
 
 template <typename F>
 static int dispatch_np(int NP, F&& f) {
@@ -204,6 +213,7 @@ static int dispatch_np(int NP, F&& f) {
 }
 
 static int launch_step(QsHandle* h, const StepParams& p, cudaStream_t s) {
+    const int kBlock = block_size();
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
@@ -218,6 +228,7 @@ static int launch_step(QsHandle* h, const StepParams& p, cudaStream_t s) {
 }
 
 static int launch_reset(QsHandle* h, const StepParams& p, cudaStream_t s) {
+    const int kBlock = block_size();
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
