@@ -88,6 +88,8 @@ struct StepParams {
     float rew[QS_NUM_REW_COEFF];
     uint32_t seed_lo, seed_hi;
     int env_id_offset;
+    // observation staging (coalesced write-out): vector width V, Q = D / V, padded row stride Dp, magic = ceil(2^20 / Q)
+    int obs_stage, obs_v, obs_q, obs_dp, obs_magic, smem_tile_off;
 };
 
 struct Agent {

@@ -20,12 +20,27 @@ struct EnvCtr {
     int tick, step_count, svd_count, episode_idx;
 };
 
+// smallest squared centre distance from the drone to a pillar of its env
+__device__ __forceinline__ float min_pillar_dist2(const StepParams& p, const Agent& s, const float2* s_obst_env) {
+    float dmin2 = 1e4f;
+#pragma unroll 4
+    for (int m = 0; m < p.M; ++m) {
+        const float2 ob = s_obst_env[m];
+        const float dx = s.pos[0] - ob.x, dy = s.pos[1] - ob.y;
+        dmin2 = fminf(dmin2, dx * dx + dy * dy);
+    }
+    return dmin2;
+}
+
 // Observation row of one drone: get_state.py:6-72 (self part), quadrotor_multi.py:233-274 (neighbours),
 // obstacles/utils.py:5-27 (3x3 SDF).  `nvel` is the velocity the neighbour block sees (stale after a reset,
 // SURVEY Appendix D-6); `nz` is the scaled sensor noise of this observation.
+// `row` points either at the drone's row in global memory or at its row of the warp's shared-memory staging tile
+// (see flush_observation_tile).
 template <int NP>
 __device__ __forceinline__ void write_observation(const StepParams& p, const Agent& s, const float nvel[3], const Noise9& nz,
-                                                  int i, bool valid, const float2* s_obst_env, float* __restrict__ row) {
+                                                  int i, bool valid, const float2* s_obst_env, float dmin2,
+                                                  float* __restrict__ row) {
     // ---- self observation
     {
         const float px = s.pos[0] + nz.p[0], py = s.pos[1] + nz.p[1], pz = s.pos[2] + nz.p[2];
@@ -86,21 +101,21 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
                 const float sc = dist + (dx * ux + dy * uy + dz * uz) * frcp(dist);
                 score[j] = (j < p.N && j != i) ? sc : __int_as_float(0x7f800000);   // +inf: never selected
             }
-            uint32_t taken = 0u;
 #pragma unroll 1
             for (int k = 0; k < p.K; ++k) {
-                float best = __int_as_float(0x7f800000);
-                int bj = -1;
+                // stable argsort: strictly smaller score wins, ties keep the lower index (Appendix D-11); a taken
+                // candidate's score is overwritten with +inf; K <= N - 2 guarantees a finite score remains
+                float best = score[0];
+                int bj = 0;
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    // stable argsort: strictly smaller score wins, ties keep the lower index (Appendix D-11)
-                    const bool cand = !((taken >> j) & 1u) && j < p.N && j != i;
-                    const bool better = cand && (bj < 0 || score[j] < best);
+                for (int j = 1; j < NP; ++j) {
+                    const bool better = score[j] < best;
                     best = better ? score[j] : best;
                     bj = better ? j : bj;
                 }
-                const int src = bj < 0 ? i : bj;
-                taken |= 1u << src;
+                const int src = bj;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) score[j] = (j == src) ? __int_as_float(0x7f800000) : score[j];
                 const float qx = shfl<NP>(s.pos[0], src), qy = shfl<NP>(s.pos[1], src), qz = shfl<NP>(s.pos[2], src);
                 const float wx = shfl<NP>(nvel[0], src), wy = shfl<NP>(nvel[1], src), wz = shfl<NP>(nvel[2], src);
                 if (valid) {
@@ -114,28 +129,82 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
         }
     }
 
-    // ---- 3x3 signed-distance patch around the drone (resolution 0.1 m): min over pillars of the squared distance,
-    //      one square root per cell (sqrt is monotone, so min-then-sqrt equals the reference's sqrt-then-min)
+    // ---- 3x3 signed-distance patch around the drone (resolution 0.1 m, obstacles/utils.py:5-27):
+    //      cell value = min over pillars of |cell - pillar| - radius.  A pillar whose CENTRE distance exceeds the
+    //      smallest centre distance by more than 2 sqrt(2) * 0.1 cannot be the nearest pillar of any of the 9 cells
+    //      (triangle inequality), so only the few qualifying pillars get the 9-cell update; the min is taken on
+    //      squared distances and one square root per cell follows (sqrt is monotone).
     if (p.use_obst) {
         const float res = 0.1f;
+        const float lim = fsqrt(dmin2) + (2.0f * 1.41421356f * res + 1e-4f);
+        const float lim2 = lim * lim;
+        uint32_t cand = 0u;
+        const int Mb = min(p.M, 32);
+#pragma unroll 4
+        for (int m = 0; m < Mb; ++m) {
+            const float2 ob = s_obst_env[m];
+            const float dx = s.pos[0] - ob.x, dy = s.pos[1] - ob.y;
+            cand |= (dx * dx + dy * dy <= lim2) ? (1u << m) : 0u;
+        }
         const float gx0 = s.pos[0] - res, gx1 = s.pos[0], gx2 = s.pos[0] + res;
         const float gy0 = s.pos[1] - res, gy1 = s.pos[1], gy2 = s.pos[1] + res;
         float b0 = 1e4f, b1 = 1e4f, b2 = 1e4f, b3 = 1e4f, b4 = 1e4f, b5 = 1e4f, b6 = 1e4f, b7 = 1e4f, b8 = 1e4f;
-#pragma unroll 2
-        for (int m = 0; m < p.M; ++m) {
-            const float2 ob = s_obst_env[m];
-            const float ex0 = (gx0 - ob.x) * (gx0 - ob.x), ex1 = (gx1 - ob.x) * (gx1 - ob.x), ex2 = (gx2 - ob.x) * (gx2 - ob.x);
-            const float ey0 = (gy0 - ob.y) * (gy0 - ob.y), ey1 = (gy1 - ob.y) * (gy1 - ob.y), ey2 = (gy2 - ob.y) * (gy2 - ob.y);
-            b0 = fminf(b0, ex0 + ey0); b1 = fminf(b1, ex0 + ey1); b2 = fminf(b2, ex0 + ey2);
-            b3 = fminf(b3, ex1 + ey0); b4 = fminf(b4, ex1 + ey1); b5 = fminf(b5, ex1 + ey2);
-            b6 = fminf(b6, ex2 + ey0); b7 = fminf(b7, ex2 + ey1); b8 = fminf(b8, ex2 + ey2);
+#define QS_SDF_UPDATE(ob)                                                                                                  \
+        {                                                                                                                  \
+            const float ex0 = (gx0 - ob.x) * (gx0 - ob.x), ex1 = (gx1 - ob.x) * (gx1 - ob.x), ex2 = (gx2 - ob.x) * (gx2 - ob.x); \
+            const float ey0 = (gy0 - ob.y) * (gy0 - ob.y), ey1 = (gy1 - ob.y) * (gy1 - ob.y), ey2 = (gy2 - ob.y) * (gy2 - ob.y); \
+            b0 = fminf(b0, ex0 + ey0); b1 = fminf(b1, ex0 + ey1); b2 = fminf(b2, ex0 + ey2);                                \
+            b3 = fminf(b3, ex1 + ey0); b4 = fminf(b4, ex1 + ey1); b5 = fminf(b5, ex1 + ey2);                                \
+            b6 = fminf(b6, ex2 + ey0); b7 = fminf(b7, ex2 + ey1); b8 = fminf(b8, ex2 + ey2);                                \
         }
+        while (cand != 0u) {
+            const int m = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            const float2 ob = s_obst_env[m];
+            QS_SDF_UPDATE(ob)
+        }
+        for (int m = 32; m < p.M; ++m) {        // tables with more than 32 pillars: plain scan of the tail
+            const float2 ob = s_obst_env[m];
+            QS_SDF_UPDATE(ob)
+        }
+#undef QS_SDF_UPDATE
         if (valid) {
             float* srow = row + p.S + 6 * p.K;
             const float r = p.obst_radius;
             srow[0] = fsqrt(b0) - r; srow[1] = fsqrt(b1) - r; srow[2] = fsqrt(b2) - r;
             srow[3] = fsqrt(b3) - r; srow[4] = fsqrt(b4) - r; srow[5] = fsqrt(b5) - r;
             srow[6] = fsqrt(b6) - r; srow[7] = fsqrt(b7) - r; srow[8] = fsqrt(b8) - r;
+        }
+    }
+}
+
+// Coalesced write-out of a warp's observation tile.  The rows of the drones a warp owns are contiguous in global
+// memory ([A][D] row-major, consecutive agents), so the tile staged in shared memory (row stride Dp) is copied out
+// with full-width vector stores: chunk c of V floats -> row c / Q, column (c % Q) * V, Q = D / V.
+__device__ __forceinline__ void flush_observation_tile(const StepParams& p, const float* tile, float* __restrict__ gdst, int n_rows,
+                                                       int lane) {
+    const int Q = p.obs_q, V = p.obs_v, Dp = p.obs_dp;
+    const int total = n_rows * Q;
+    if (V == 4) {
+#pragma unroll 2
+        for (int c = lane; c < total; c += 32) {
+            const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
+            const int q = c - r * Q;
+            *reinterpret_cast<float4*>(gdst + 4 * c) = *reinterpret_cast<const float4*>(tile + r * Dp + 4 * q);
+        }
+    } else if (V == 2) {
+#pragma unroll 2
+        for (int c = lane; c < total; c += 32) {
+            const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
+            const int q = c - r * Q;
+            *reinterpret_cast<float2*>(gdst + 2 * c) = *reinterpret_cast<const float2*>(tile + r * Dp + 2 * q);
+        }
+    } else {
+#pragma unroll 2
+        for (int c = lane; c < total; c += 32) {
+            const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
+            const int q = c - r * Q;
+            gdst[c] = tile[r * Dp + q];
         }
     }
 }
@@ -191,6 +260,19 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
     const long long a = (long long)env * p.N + i;
     const long long A = (long long)p.E * p.N;
 
+    // Programmatic dependent launch: let the NEXT step's grid start launching while this one runs, and wait here for
+    // the PREVIOUS step's grid to complete (and flush) before touching any state.  Without the launch attribute
+    // both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
+    float2* s_obst_env = s_obst + env_local * p.M;
+    float* s_tile = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + (threadIdx.x >> 5) * (32 * p.obs_dp);
+
+    Agent s;
+    EnvCtr ctr = {0, 0, 0, 0};
+    if (valid) load_agent(st, a, s);          // state loads are issued before the pillar staging barrier
     // stage this block's pillar tables (contiguous [envs_per_block][M] float2) in shared memory
     if (p.use_obst) {
         const long long base = (long long)blockIdx.x * envs_per_block * p.M;
@@ -199,12 +281,7 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
             if (base + k < total) s_obst[k] = st.obst[base + k];
         __syncthreads();
     }
-    float2* s_obst_env = s_obst + env_local * p.M;
-
-    Agent s;
-    EnvCtr ctr = {0, 0, 0, 0};
-    if (valid) load_agent(st, a, s);
-    else {
+    if (!valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) { s.pos[k] = 1e9f + 1e6f * i; s.vel[k] = 0.f; s.om[k] = 0.f; s.goal[k] = 0.f; }
 #pragma unroll
@@ -292,12 +369,10 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         if (NP > 1) {
             const float max_pen = p.rew[QS_REW_QUADCOL_BIN_SMOOTH_MAX];
             const float pen_ratio = -max_pen / p.falloff_thr;
-#pragma unroll 1
+#pragma unroll 2
             for (int j = 0; j < p.N; ++j) {
                 const float dx = s.pos[0] - shfl<NP>(s.pos[0], j), dy = s.pos[1] - shfl<NP>(s.pos[1], j),
                             dz = s.pos[2] - shfl<NP>(s.pos[2], j);
-                float zx = 0.f, zy = 0.f, zz = 0.f;
-                if (p.use_downwash) { zx = shfl<NP>(s.R[2], j); zy = shfl<NP>(s.R[5], j); zz = shfl<NP>(s.R[8], j); }
                 const float d2 = dx * dx + dy * dy + dz * dz;
                 const bool other = (j != i) && valid;
                 if (other && d2 <= falloff2) {
@@ -305,11 +380,14 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
                     if (d2 <= col_thr2) cur_col |= 1u << j;
                     prox += pen_ratio * d + max_pen;
                 }
-                if (p.use_downwash && other) {
+                // the downwash cylinder (|rel_z| < 0.7, rel_xy < 0.1) lies inside the ball d^2 < 0.5: the z-axis
+                // exchange and the cylinder test run only when some drone of the warp is that close to drone j
+                if (p.use_downwash && __any_sync(0xffffffffu, other && d2 < 0.5f)) {
+                    const float zx = shfl<NP>(s.R[2], j), zy = shfl<NP>(s.R[5], j), zz = shfl<NP>(s.R[8], j);
                     // is drone i (me) inside the downwash cylinder below drone j?  -0.7 < rel_z < 0 and rel_xy < 0.1
                     const float rel_z = dx * zx + dy * zy + dz * zz;
                     const float rxy2 = d2 - rel_z * rel_z;                 // negative -> sqrt is NaN in numpy -> false
-                    if (-0.7f < rel_z && rel_z < 0.f && rxy2 >= 0.f && rxy2 < 0.1f * 0.1f) {
+                    if (other && -0.7f < rel_z && rel_z < 0.f && rxy2 >= 0.f && rxy2 < 0.1f * 0.1f) {
                         const KickVO k = downwash_kick(key, j, i, fsqrt(d2), zx, zy, zz);
                         dw_dv[0] += k.vel.x; dw_dv[1] += k.vel.y; dw_dv[2] += k.vel.z;
                         dw_dw[0] += k.dom.x; dw_dw[1] += k.dom.y; dw_dw[2] += k.dom.z;
@@ -331,12 +409,15 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
 
         // obstacles: first pillar in index order within arm + radius (obstacles/utils.py:31-43), :462-488
         int hit = -1;
+        float dmin2 = 1e4f;                          // smallest squared centre distance to a pillar (prunes the SDF pass)
         if (p.use_obst) {
 #pragma unroll 4
             for (int m = p.M - 1; m >= 0; --m) {
                 const float2 ob = s_obst_env[m];
                 const float dx = s.pos[0] - ob.x, dy = s.pos[1] - ob.y;
-                hit = (dx * dx + dy * dy <= obst_thr2) ? m : hit;
+                const float d2 = dx * dx + dy * dy;
+                hit = (d2 <= obst_thr2) ? m : hit;
+                dmin2 = fminf(dmin2, d2);
             }
         }
         const bool new_obst = (hit >= 0) && !(s.flags & QS_FLAG_PREV_OBST) && valid;
@@ -523,13 +604,26 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
                 ctr.episode_idx += 1;
                 goal_dirty = true;
                 if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
+                dmin2 = min_pillar_dist2(p, s, s_obst_env);          // new pose, new pillar table
             }
         }
 
         // ================= observation (of the post-response, or freshly reset, state) =================
         if (!p.last_obs_only || t == p.T - 1) {
-            float* row = p.obs + ((p.last_obs_only ? 0 : (long long)t * A) + a) * p.D;
-            write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, row);
+            float* gbase = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
+            if (p.obs_stage) {
+                // rows go to the warp's shared-memory tile, then out with coalesced vector stores
+                const int slot = (lane / NP) * p.N + i;               // row of this drone inside the warp's tile
+                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp);
+                __syncwarp();
+                const int env_first = blockIdx.x * envs_per_block + (threadIdx.x >> 5) * (32 / NP);
+                const int envs_here = min(32 / NP, p.E - env_first);
+                if (envs_here > 0)
+                    flush_observation_tile(p, s_tile, gbase + (long long)env_first * p.N * p.D, envs_here * p.N, lane);
+                __syncwarp();
+            } else {
+                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, gbase + a * p.D);
+            }
         }
         ctr.step_count += 1;
     }
@@ -585,7 +679,8 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
 #pragma unroll
     for (int k = 0; k < 3; ++k) { nz.p[k] = 0.f; nz.v[k] = 0.f; nz.w[k] = 0.f; }
     if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
-    write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, p.obs + a * p.D);
+    write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, p.use_obst ? min_pillar_dist2(p, s, s_obst_env) : 1e4f,
+                          p.obs + a * p.D);
     if (valid) store_agent(st, a, s, true);
 }
 

@@ -76,6 +76,14 @@ static void fill_params(const QsHandle* h, StepParams& p) {
     p.seed_lo = (uint32_t)(c.seed & 0xffffffffull);
     p.seed_hi = (uint32_t)(c.seed >> 32);
     p.env_id_offset = c.env_id_offset;
+    // observation staging tile: only when a warp's tile fits comfortably in shared memory
+    const int D = h->D;
+    const int V = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+    const int Q = D / V;
+    p.obs_v = V; p.obs_q = Q;
+    p.obs_dp = (Q % 2 == 0) ? D + V : D;                 // odd number of V-wide words per row: fewer bank conflicts
+    p.obs_magic = ((1 << 20) + Q - 1) / Q;
+    p.obs_stage = (D <= 72) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -212,15 +220,30 @@ static int dispatch_np(int NP, F&& f) {
     return fail(QS_ERR_UNSUPPORTED, "num_agents > 32 is not supported by this build");
 }
 
-static int launch_step(QsHandle* h, const StepParams& p, cudaStream_t s) {
+static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     const int kBlock = block_size();
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
-    const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
+    size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
+    smem = (smem + 15) / 16 * 16;
+    StepParams p = p_in;
+    p.smem_tile_off = (int)(smem / sizeof(float));
+    if (p.obs_stage) smem += (size_t)(kBlock / 32) * 32 * p.obs_dp * sizeof(float);
+    // Programmatic dependent launch (opt-in, QS_PDL=1): measured SLOWER than plain graph edges on this kernel
+    // (11.96 vs 9.97 us/step on c3, profiles/r01_notes.md), so it stays off by default.
+    static const bool use_pdl = [] { const char* e = getenv("QS_PDL"); return e ? atoi(e) != 0 : false; }();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t lerr = cudaSuccess;
     int rc = dispatch_np(h->NP, [&](auto np) {
-        qs_step_kernel<decltype(np)::value><<<grid, kBlock, smem, s>>>(p);
+        lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<decltype(np)::value>, p);
         return QS_OK;
     });
+    if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
     if (rc != QS_OK) return rc;
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
