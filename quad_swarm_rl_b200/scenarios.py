@@ -165,6 +165,7 @@ def obstacle_map_given_density(rng, obst_spawn_area, obst_density, room_height=1
 class Scenario:
     """Common state + the formation bookkeeping of base.py:8-150."""
     mode = None
+    dynamic = False          # True when step() can move goals (the env then calls it every tick)
 
     def __init__(self, num_agents, room_dims=(10., 10., 10.), rng=None, control_freq=100.0, ep_time=15.0, box=2.0,
                  use_obstacles=False):
@@ -237,6 +238,7 @@ class StaticDiffGoal(Scenario):
 class DynamicSameGoal(Scenario):
     """dynamic_same_goal.py: the common goal teleports every 4-6 s."""
     mode = 'dynamic_same_goal'
+    dynamic = True
 
     def reset(self, obst_map=None, cell_centers=None):
         self._draw_period()
@@ -253,6 +255,7 @@ class DynamicSameGoal(Scenario):
 class DynamicDiffGoal(Scenario):
     """dynamic_diff_goal.py: a new formation at a new centre every 4-6 s."""
     mode = 'dynamic_diff_goal'
+    dynamic = True
 
     def reset(self, obst_map=None, cell_centers=None):
         self._draw_period()
@@ -272,6 +275,7 @@ class DynamicDiffGoal(Scenario):
 class SwapGoals(Scenario):
     """swap_goals.py: goals are permuted among the drones every 4-6 s."""
     mode = 'swap_goals'
+    dynamic = True
 
     def reset(self, obst_map=None, cell_centers=None):
         self._draw_period()
@@ -285,6 +289,7 @@ class SwapGoals(Scenario):
 class DynamicFormations(Scenario):
     """dynamic_formations.py: the formation breathes, goals move every tick."""
     mode = 'dynamic_formations'
+    dynamic = True
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
@@ -310,6 +315,7 @@ class DynamicFormations(Scenario):
 class Lissajous3D(Scenario):
     """ep_lissajous3D.py: all drones chase one goal that random-walks along Lissajous increments."""
     mode = 'ep_lissajous3D'
+    dynamic = True
 
     def reset(self, obst_map=None, cell_centers=None):
         self.pick_formation()
@@ -325,6 +331,7 @@ class Lissajous3D(Scenario):
 class SwarmVsSwarm(Scenario):
     """swarm_vs_swarm.py: two half-swarms whose formation centres swap every 4-6 s."""
     mode = 'swarm_vs_swarm'
+    dynamic = True
 
     def _centers(self):
         box = self.box
@@ -457,6 +464,7 @@ class Mix(Scenario):
     """mix.py:37-93: a fresh scenario drawn uniformly per episode.  The two bezier modes need the third-party
     `bezier` package, which this image does not have; they are re-drawn (documented deviation)."""
     mode = 'mix'
+    dynamic = True
 
     def __init__(self, num_agents, **kw):
         super().__init__(num_agents, **kw)

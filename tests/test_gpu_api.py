@@ -1,0 +1,206 @@
+"""GPU tests of the C-ABI surface and the reference-facing env objects: API equivalences that hold bit-exactly
+(one launch vs many, host vs device buffers, shard invariance, snapshot / restore) and size-independent properties at
+BASELINE.json's full sizes (rotation orthonormality, episode length, bounds, determinism)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+C3 = dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, use_downwash=True)
+C2 = dict(num_agents=8, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega')
+
+
+def _engine(E, kw, seed=3, ep_time=0.5, **extra):
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    from tests.parity_util import make_tables
+    eng = QuadSwarmEngine(num_envs=E, seed=seed, ep_time=ep_time, **kw, **extra)
+    t = make_tables(np.random.RandomState(11), E, kw['num_agents'], eng.M, kw.get('use_obstacles', False), episodes=1)[0]
+    eng.set_next_episode(t['goals'], t['spawn'], t['obst'])
+    return eng, t
+
+
+def _actions(T, E, N, seed=5):
+    g = torch.Generator(device='cuda'); g.manual_seed(seed)
+    return (torch.rand((T, E, N, 4), device='cuda', generator=g) * 2 - 1).contiguous()
+
+
+@pytest.mark.parametrize('kw', [C3, C2], ids=['c3', 'c2'])
+def test_rollout_equals_repeated_steps(kw):
+    """qs_rollout(T) == T x qs_step, bit for bit (same kernel, state kept in registers), across an auto-reset."""
+    T, E = 70, 37
+    a = _actions(T, E, kw['num_agents'])
+    e1, _ = _engine(E, kw); e2, _ = _engine(E, kw)
+    o1 = e1.reset().clone(); o2 = e2.reset().clone()
+    assert torch.equal(o1, o2)
+    obs_s, rew_s, done_s = [], [], []
+    for t in range(T):
+        o, r, d = e1.step(a[t])
+        obs_s.append(o.clone()); rew_s.append(r.clone()); done_s.append(d.clone())
+    obs_r, rew_r, done_r = e2.rollout(a)
+    assert torch.equal(torch.stack(obs_s), obs_r) and torch.equal(torch.stack(rew_s), rew_r) and torch.equal(torch.stack(done_s), done_r)
+    assert int(done_r.sum()) == E * kw['num_agents']          # ep_len = 50 -> exactly one episode end inside 70 steps
+    s1, s2 = e1.get_state(), e2.get_state()
+    for k in ('agent_f32', 'agent_u32', 'env_i32'):
+        assert torch.equal(s1[k], s2[k]), k
+    e3, _ = _engine(E, kw); e3.reset()
+    o_last, _, _ = e3.rollout(a, last_obs_only=True)
+    assert torch.equal(o_last[0], obs_r[-1])
+    for e in (e1, e2, e3):
+        e.close()
+
+
+def test_host_buffer_step_equals_device_step():
+    E, kw = 19, C3
+    e1, _ = _engine(E, kw); e2, _ = _engine(E, kw)
+    e1.reset(); e2.reset()
+    a = _actions(12, E, 8)
+    obs_h = np.zeros((E, 8, e1.D), np.float32); rew_h = np.zeros((E, 8), np.float32); dn_h = np.zeros((E, 8), np.uint8)
+    terms_h = np.zeros((E, 8, 8), np.float32)
+    for t in range(12):
+        o, r, d = e1.step(a[t], with_terms=True)
+        e2.step_host(a[t].cpu().numpy(), obs_h, rew_h, dn_h, terms_h)
+        assert np.array_equal(o.cpu().numpy(), obs_h) and np.array_equal(r.cpu().numpy(), rew_h)
+        assert np.array_equal(d.cpu().numpy(), dn_h) and np.array_equal(e1.rew_terms.cpu().numpy(), terms_h)
+    e1.close(); e2.close()
+
+
+def test_shard_invariance():
+    """Results depend on the GLOBAL env id only: one engine of 8 envs == two engines of 4 envs with offsets 0 and 4."""
+    kw = C3
+    whole, t = _engine(8, kw)
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    parts = []
+    for r in range(2):
+        p = QuadSwarmEngine(num_envs=4, seed=3, ep_time=0.5, env_id_offset=4 * r, **kw)
+        p.set_next_episode(t['goals'][4 * r:4 * r + 4], t['spawn'][4 * r:4 * r + 4], t['obst'][4 * r:4 * r + 4])
+        parts.append(p)
+    ow = whole.reset()
+    op = torch.cat([p.reset() for p in parts])
+    assert torch.equal(ow, op)
+    a = _actions(60, 8, 8)
+    for t_ in range(60):
+        ow, rw, dw = whole.step(a[t_])
+        outs = [p.step(a[t_, 4 * r:4 * r + 4].contiguous()) for r, p in enumerate(parts)]
+        assert torch.equal(ow, torch.cat([o[0] for o in outs])) and torch.equal(rw, torch.cat([o[1] for o in outs]))
+    whole.close(); [p.close() for p in parts]
+
+
+def test_snapshot_restore_replays_identically():
+    """qs_get_state / qs_set_state: restoring a snapshot and replaying the same actions reproduces the same outputs
+    (what deepcopy(env) gives the reference's replay wrapper, quad_experience_replay.py:99-104)."""
+    eng, _ = _engine(16, C3); eng.reset()
+    a = _actions(30, 16, 8)
+    for t in range(10):
+        eng.step(a[t])
+    snap = {k: v.clone() for k, v in eng.get_state().items()}
+    first = [tuple(x.clone() for x in eng.step(a[t])) for t in range(10, 30)]
+    eng.set_state(snap)
+    for t, ref in zip(range(10, 30), first):
+        out = eng.step(a[t])
+        assert all(torch.equal(x, y) for x, y in zip(out, ref))
+    eng.close()
+
+
+def test_masked_reset_only_touches_selected_envs():
+    eng, _ = _engine(6, C2); eng.reset()
+    a = _actions(5, 6, 8)
+    for t in range(5):
+        eng.step(a[t])
+    before = eng.get_state()
+    obs_before = eng.obs.clone()
+    mask = np.array([0, 1, 0, 0, 1, 0], np.uint8)
+    eng.reset(env_mask=mask)
+    after = eng.get_state()
+    keep = torch.tensor(mask == 0, device='cuda')
+    assert torch.equal(before['agent_f32'][keep], after['agent_f32'][keep]) and torch.equal(obs_before[keep], eng.obs[keep])
+    assert (after['env_i32'][~keep, 0] == 0).all() and (after['env_i32'][keep, 0] == 5).all()
+    eng.close()
+
+
+@pytest.mark.parametrize('cfg', ['c2', 'c3', 'c4'])
+def test_full_size_properties(cfg):
+    """BASELINE.json sizes: properties that need no oracle.  R stays orthonormal, positions stay in the room, rewards are
+    finite and bounded, every env ends its episode on tick ep_len + 1, and a second run is bit-identical."""
+    import bench
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine, STATE_F32_FIELDS as F
+    c = bench.CONFIGS[cfg]
+    E, kw = c['E'], c['kw']
+    N = kw['num_agents']
+    runs = []
+    for rep in range(2):
+        eng = QuadSwarmEngine(num_envs=E, seed=9, ep_time=0.4, rew_coeff=c['rew'], **kw)
+        g, s, o = bench.make_episode_tables(c, 64, seed=1)
+        tile = lambda x: None if x is None else np.tile(x, (E // 64, 1, 1))
+        eng.set_next_episode(tile(g), tile(s), tile(o))
+        eng.reset()
+        a = _actions(45, E, N, seed=21)
+        obs, rew, done = eng.rollout(a)
+        st = eng.get_state()
+        runs.append((obs, rew, done, st['agent_f32'].clone()))
+        if rep == 0:
+            af = st['agent_f32']
+            R = af[..., F['rot'][0]:F['rot'][1]].reshape(E, N, 3, 3)
+            eye = torch.eye(3, device='cuda').expand(E, N, 3, 3)
+            assert (R @ R.transpose(-1, -2) - eye).abs().max() < 1e-4
+            pos = af[..., 0:3]
+            assert (pos[..., :2].abs() <= 5.0).all() and (pos[..., 2] >= 0.0459).all() and (pos[..., 2] <= 10.0).all()
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (rew.abs() < 6.0).all()
+            d = done.view(45, E, N)
+            assert d[40].all() and int(d.sum()) == E * N          # ep_len = 40: done exactly once, on step 41
+            # (|omega| may exceed the 40 rad/s clip right after a contact response: the kick lands after the clip)
+        eng.close()
+    for x, y in zip(runs[0], runs[1]):
+        assert torch.equal(x, y)
+
+
+def test_reference_style_env_object():
+    """QuadrotorEnvMulti keeps the reference's protocol: types, shapes, info keys, auto-reset, mutable rew_coeff."""
+    from quad_swarm_rl_b200.env import QuadrotorEnvMulti
+    env = QuadrotorEnvMulti(
+        num_agents=8, ep_time=0.3, rew_coeff=None, obs_repr='xyz_vxyz_R_omega_floor', neighbor_visible_num=2,
+        neighbor_obs_type='pos_vel', collision_hitbox_radius=2.0, collision_falloff_radius=4.0, use_obstacles=True,
+        obst_density=0.2, obst_size=0.6, obst_spawn_area=[8.0, 8.0], use_downwash=True, use_numba=True,
+        quads_mode='o_random', room_dims=[10., 10., 10.], use_replay_buffer=False, quads_view_mode=['topdown'],
+        quads_render=False, dynamics_params='Crazyflie', raw_control=True, raw_control_zero_middle=True,
+        dynamics_randomize_every=None, dynamics_change=None, dyn_sampler_1=None, sense_noise='default',
+        init_random_state=False, seed=4)
+    assert env.num_agents == 8 and env.is_multiagent and env.observation_space.shape == (40,)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (8, 40) and obs.dtype == np.float64
+    env.rew_coeff['quadcol_bin_obst'] = 7.0              # wrappers mutate this dict mid-run
+    saw_done = False
+    for t in range(35):
+        obs, rewards, dones, infos = env.step([env.action_space.sample() for _ in range(8)])
+        assert obs.shape == (8, 40) and len(rewards) == 8 and isinstance(rewards[0], float) and isinstance(dones[0], bool)
+        keys = set(infos[0]['rewards'])
+        assert {'rew_main', 'rewraw_main', 'rew_quadcol', 'rew_proximity', 'rewraw_quadcol', 'rew_quadcol_obstacle'} <= keys
+        total = sum(infos[3]['rewards'][k] for k in ('rew_pos', 'rew_action', 'rew_crash', 'rew_orient', 'rew_spin',
+                                                      'rew_quadcol', 'rew_proximity', 'rew_quadcol_obstacle'))
+        assert total == pytest.approx(rewards[3], abs=2e-6)
+        if dones[0]:
+            saw_done = True
+            assert all(dones) and env.envs[0].tick == 0
+            st = infos[0]['episode_extra_stats']
+            assert 'num_collisions' in st and 'o_random/distance_to_goal_1s' in st and 'metric/agent_success_rate' in st
+        else:
+            assert env.envs[0].tick == (t + 1) % 31
+    assert saw_done and env.scenario.name() == 'Scenario_o_random'
+    env.close()
+
+
+def test_batched_env_and_dynamic_scenario():
+    from quad_swarm_rl_b200.env import QuadrotorEnvMultiBatched
+    env = QuadrotorEnvMultiBatched(num_envs=16, num_agents=8, ep_time=4.5, neighbor_visible_num=6, quads_mode='swarm_vs_swarm', seed=2)
+    obs, info = env.reset()
+    assert obs.is_cuda and obs.shape == (128, 54) and env.num_agents == 128
+    goals0 = env._goals.copy()
+    ended = []
+    for t in range(455):
+        obs, rew, term, trunc, infos = env.step(torch.rand((128, 4), device='cuda') * 2 - 1)
+        if term.any():
+            assert term.all() and not trunc.any()
+            ended.append(t)
+    assert ended == [450]                                       # ep_len = 450 -> every env ends on its 451st step
+    assert not np.array_equal(goals0, env._goals)               # formation centres swapped / new episode
+    env.close()

@@ -1,0 +1,168 @@
+"""Host-side logic that needs no GPU: episode generators, wrappers (reward shaping / annealing / 5-tuple), spaces,
+the SVD period of the reference's float accumulator, and the multi-GPU sharding helpers (world_size-2 gloo)."""
+import os
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from quad_swarm_rl_b200 import scenarios as sc
+from quad_swarm_rl_b200 import wrappers as wr
+from quad_swarm_rl_b200.spaces import make_observation_space, make_action_space
+from quad_swarm_rl_b200.sharding import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('formation', sc.FORMATIONS)
+@pytest.mark.parametrize('n', [1, 8, 9, 32])
+def test_formation_goals_shape_and_center(formation, n):
+    g = sc.formation_goals(formation, n, 0.5, (1.0, -2.0, 3.0), 0.4, 50 if formation.startswith('grid') else 8)
+    rows = max(n, 3) if formation == 'sphere' else n          # the reference's sphere generator never makes fewer than 3 points
+    assert g.shape == (rows, 3) and np.all(np.isfinite(g))
+    if formation.startswith(('grid', 'cube')):
+        np.testing.assert_allclose(g.mean(axis=0), [1.0, -2.0, 3.0], atol=1e-9)
+
+
+def test_o_random_uses_distinct_free_cells():
+    rs = np.random.RandomState(3)
+    s = sc.create_scenario('o_random', 8, rng=rs, use_obstacles=True)
+    for _ in range(20):
+        obst_map, pos, cells = sc.obstacle_map_given_density(rs, (8.0, 8.0), 0.2)
+        assert obst_map.sum() == 12 and len(pos) == 12
+        s.reset(obst_map=obst_map, cell_centers=cells)
+        pillars = {tuple(p[:2]) for p in pos}
+        for pts in (s.spawn_points, s.goals):
+            xy = [tuple(p[:2]) for p in pts]
+            assert len(set(xy)) == 8 and not (set(xy) & pillars)
+            assert np.all(pts[:, 2] >= 1.0) and np.all(pts[:, 2] <= 3.0)
+    assert s.name() == 'Scenario_o_random' and not s.dynamic
+
+
+def test_swarm_vs_swarm_swaps_centres():
+    s = sc.create_scenario('swarm_vs_swarm', 8, rng=np.random.RandomState(1))
+    s.reset()
+    c1, c2, period = s.c1.copy(), s.c2.copy(), s.period
+    assert 400 <= period <= 600
+    for t in range(1, period):
+        s.step(t)
+    assert np.array_equal(s.c1, c1)
+    s.step(period)
+    assert np.array_equal(s.c1, c2) and np.array_equal(s.c2, c1) and s.goals.shape == (8, 3)
+
+
+def test_unknown_scenario_raises_like_the_reference():
+    with pytest.raises(NameError):
+        sc.create_scenario('o_diagonal', 8)
+
+
+def test_spaces():
+    obs = make_observation_space('xyz_vxyz_R_omega_floor', 2, True, (10., 10., 10.))
+    assert obs.shape == (19 + 12 + 9,) and obs.dtype == np.float32
+    assert make_action_space().shape == (4,) and float(make_action_space().low[0]) == -1.0
+
+
+class _FakeEnv:
+    """Stand-in with the QuadrotorEnvMulti protocol for wrapper tests."""
+    is_multiagent = True
+    num_agents = 2
+
+    def __init__(self):
+        self.rew_coeff = dict(pos=1.0, quadcol_bin=9.0, quadcol_bin_smooth_max=9.0, quadcol_bin_obst=9.0)
+        self.scenario = types.SimpleNamespace(name=lambda: 'Scenario_static_same_goal')
+        self.t = 0
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def reset(self):
+        self.t = 0
+        return np.zeros((2, 3))
+
+    def step(self, action):
+        self.t += 1
+        done = self.t >= 3
+        infos = [{'rewards': {'rew_pos': -0.1, 'rew_crash': 0.0, 'rewraw_main': -0.2, 'rewraw_quadcol': -1.0 if i == 1 and self.t == 2 else 0.0}}
+                 for i in range(2)]
+        return np.ones((2, 3)) * self.t, [0.5, 0.5], [done, done], infos
+
+    def close(self):
+        pass
+
+
+def test_reward_shaping_annealing_and_true_reward():
+    env = _FakeEnv()
+    scheme = dict(quad_rewards=dict(pos=1.0, quadcol_bin=0.0, quadcol_bin_smooth_max=0.0, quadcol_bin_obst=0.0))
+    ann = [wr.AnnealSchedule('quadcol_bin', 5.0, 1000)]
+    w = wr.QuadEnvCompatibility(wr.QuadsRewardShapingWrapper(env, reward_shaping_scheme=scheme, annealing=ann))
+    obs, info = w.reset()
+    assert info == {} and obs.shape == (2, 3)
+    w.env.training_info['approx_total_training_steps'] = 500
+    for t in range(3):
+        obs, rew, term, trunc, infos = w.step(np.full((2, 4), 0.1 * t))
+    assert env.rew_coeff['quadcol_bin'] == 2.5            # annealed: 5.0 * 500 / 1000
+    assert term.all() and not trunc.any()
+    assert infos[0]['true_reward'] == pytest.approx(-0.6)
+    assert infos[1]['true_reward'] == pytest.approx(-0.6 - 1000.0)
+    st = infos[1]['episode_extra_stats']
+    assert st['Scenario_static_same_goal/rew_pos'] == pytest.approx(-0.3) and st['z_anneal_quadcol_bin'] == 2.5
+    assert st['z_action0_mean'] == pytest.approx(0.1)
+
+
+def test_factory_rejects_what_is_out_of_scope():
+    cfg = types.SimpleNamespace(replay_buffer_sample_prob=0.75)
+    with pytest.raises(NotImplementedError):
+        wr.make_quadrotor_env('quadrotor_multi', cfg=cfg)
+    with pytest.raises(NotImplementedError):
+        wr.make_quadrotor_env('quadrotor_single', cfg=cfg)
+
+
+def test_svd_period_is_100_substeps():
+    """quadrotor_dynamics.py:547-551 accumulates 0.005 in float64 and re-orthogonalises when the sum exceeds 0.5;
+    the kernels use an integer period of 100 sub-steps (qs_device.cuh SVD_PERIOD).  Check the float behaviour."""
+    acc, fired = 0.0, []
+    for k in range(1, 1001):
+        acc += 0.005
+        if acc > 0.5:
+            fired.append(k)
+            acc = 0
+    assert fired == list(range(100, 1001, 100))
+
+
+def test_shard_range_partitions():
+    for total, world in ((32768, 8), (10, 3), (7, 8)):
+        spans = [shard_range(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+_GLOO_CHILD = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from quad_swarm_rl_b200.sharding import shard_range, reduce_metrics
+dist.init_process_group('gloo')
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = shard_range(10, w, r)
+m = torch.zeros(4); m[0] = hi - lo; m[1] = sum(range(lo, hi)); m[2] = 1
+reduce_metrics(m)
+assert m.tolist() == [10.0, 45.0, float(w), 0.0], m
+mx = torch.tensor([float(r)]); reduce_metrics(mx, op='max'); assert mx.item() == w - 1
+dist.destroy_process_group()
+print('ok', r)
+'''
+
+
+def test_sharding_two_ranks_gloo(tmp_path):
+    """N>1 host logic on CPU: two gloo ranks shard the env ids without overlap and reduce a metrics vector."""
+    script = tmp_path / 'child.py'
+    script.write_text(_GLOO_CHILD % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29541', OMP_NUM_THREADS='1')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29541', str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('ok') == 2
