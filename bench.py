@@ -47,6 +47,16 @@ CONFIGS = {
 }
 
 
+def measured_traffic(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per launch, from the committed ncu --set full
+    capture of this workload (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    try:
+        return json.load(open(p)).get(config, {}).get('dram_bytes_per_launch')
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -183,8 +193,10 @@ def cpu_baseline_single(cfg_name, budget_s=12.0):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on all host cores; one bench "step" = every worker
-    process advancing its env by `inner` control steps."""
+    """--impl reference: the reference's own CPU implementation on all host cores (one env per process, the way Sample
+    Factory's rollout workers run it).  The K bench steps are a BOUNDED SAMPLE of the workload: every process advances
+    its env by n_proc = clamp(K, 100, 2500) control steps in total (so the run ends within minutes whatever K is);
+    the rate, not the step count, is what is compared."""
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -192,21 +204,22 @@ def run_reference_arm(args):
     cfg = CONFIGS[args.config]
     N = cfg['kw']['num_agents']
     P = os.cpu_count() or 1
-    inner = max(1, min(500, 24000 // max(1, args.steps)))     # bounded sample: ~1 min of CPU work per process
+    n_proc = int(min(max(args.steps, 100), 2500))
+    n_warm = int(min(max(args.warmup, 3), 50))
     ctx = mp.get_context('spawn')
     with ctx.Pool(P) as pool:
-        res = pool.map(_ref_worker, [(args.config, max(3, args.warmup) * inner, args.steps * inner, 100 + r) for r in range(P)])
+        res = pool.map(_ref_worker, [(args.config, n_warm, n_proc, 100 + r) for r in range(P)])
     wall = max(r[0] for r in res)
     kind = res[0][1]
-    total = P * N * args.steps * inner
-    value = total / wall
+    value = P * N * n_proc / wall
     line = {
         'impl': 'reference', 'metric': 'env agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f"{args.config}: {cfg['desc']}", 'note': f'{P} processes x 1 env each, {inner} control steps per bench step'},
+        'config': {'workload': f"{args.config}: {cfg['desc']}",
+                   'note': f'bounded sample: {P} processes x 1 env each x {n_proc} control steps (numba path), spread over the {args.steps} bench steps'},
         'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': P, 'kind': kind,
-                         'sample': f'{P} processes x 1 env x {args.steps * inner} control steps'},
+                         'sample': f'{P} processes x 1 env x {n_proc} control steps of workload {args.config}'},
         'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -329,10 +342,13 @@ def run_cuda_arm(args):
 
     # ---- e2e: reference-facing call with HOST buffers
     n_e2e = max(10, min(args.steps, args.e2e_steps))
-    a_host = np.ascontiguousarray((np.random.RandomState(5 + rank).uniform(-1, 1, (8, E, N, 4))).astype(np.float32))
-    obs_h = np.zeros((E, N, D), np.float32)
-    rew_h = np.zeros((E, N), np.float32)
-    done_h = np.zeros((E, N), np.uint8)
+    # page-locked host buffers (numpy views of pinned torch tensors): the DMA engine reads / writes them directly
+    a_pin = torch.empty((8, E, N, 4), dtype=torch.float32).pin_memory()
+    a_pin.copy_(torch.from_numpy(np.random.RandomState(5 + rank).uniform(-1, 1, (8, E, N, 4)).astype(np.float32)))
+    a_host = a_pin.numpy()
+    obs_h = torch.zeros((E, N, D), dtype=torch.float32).pin_memory().numpy()
+    rew_h = torch.zeros((E, N), dtype=torch.float32).pin_memory().numpy()
+    done_h = torch.zeros((E, N), dtype=torch.uint8).pin_memory().numpy()
     for k in range(3):
         eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
     if world > 1:
@@ -386,10 +402,10 @@ def run_cuda_arm(args):
             'clocks': clk,
             'e2e': {'value': world * A * n_e2e / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': A * 16,
                     'd2h_bytes_per_step': A * (4 * D + 4 + 1), 'steps': n_e2e,
-                    'note': 'qs_step_host: numpy in/out, pinned staging + H2D/D2H + stream sync every step'},
+                    'note': 'qs_step_host with page-locked numpy buffers: H2D actions, step kernel, D2H obs/rewards/dones, stream sync, every step'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'alg_bytes_per_agent_step': b_alg,
+                         'traffic': measured_traffic(args.config) if E == cfg['E'] else None, 'peak_source': peak_src, 'alg_bytes_per_agent_step': b_alg,
                          'alg_bytes_per_launch': per_launch_bytes, 'launch_us': launch_s * 1e6},
             'cpu_baseline': cpu,
         }

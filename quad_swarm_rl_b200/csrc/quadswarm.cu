@@ -443,26 +443,40 @@ extern "C" int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, 
     return launch_step(h, p, (cudaStream_t)stream);
 }
 
+// true when the host pointer is page-locked (cudaHostAlloc / cudaHostRegister): DMA can use it directly
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
                             float* rew_terms_host) {
     if (!h || !actions_host || !obs_host || !rewards_host || !dones_host) return fail(QS_ERR_INVALID_ARG, "null argument");
     QS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
     const long long A = h->A;
-    memcpy(h->h_actions, actions_host, sizeof(float) * 4 * A);
-    QS_CUDA(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * 4 * A, cudaMemcpyHostToDevice, s));
+    // pageable buffers go through the handle's pinned staging; page-locked caller buffers are used as they are
+    const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rewards_host), pd = is_pinned(dones_host),
+               pt = rew_terms_host && is_pinned(rew_terms_host);
+    const float* a_src = actions_host;
+    if (!pa) { memcpy(h->h_actions, actions_host, sizeof(float) * 4 * A); a_src = h->h_actions; }
+    QS_CUDA(cudaMemcpyAsync(h->d_actions, a_src, sizeof(float) * 4 * A, cudaMemcpyHostToDevice, s));
     int rc = qs_step(h, h->d_actions, h->d_obs, h->d_rewards, h->d_dones, rew_terms_host ? h->d_terms : nullptr, s);
     if (rc != QS_OK) return rc;
-    QS_CUDA(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * h->D * A, cudaMemcpyDeviceToHost, s));
-    QS_CUDA(cudaMemcpyAsync(h->h_rewards, h->d_rewards, sizeof(float) * A, cudaMemcpyDeviceToHost, s));
-    QS_CUDA(cudaMemcpyAsync(h->h_dones, h->d_dones, A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(po ? obs_host : h->h_obs, h->d_obs, sizeof(float) * h->D * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(pr ? rewards_host : h->h_rewards, h->d_rewards, sizeof(float) * A, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(pd ? dones_host : h->h_dones, h->d_dones, A, cudaMemcpyDeviceToHost, s));
     if (rew_terms_host)
-        QS_CUDA(cudaMemcpyAsync(h->h_terms, h->d_terms, sizeof(float) * QS_NUM_TERMS * A, cudaMemcpyDeviceToHost, s));
+        QS_CUDA(cudaMemcpyAsync(pt ? rew_terms_host : h->h_terms, h->d_terms, sizeof(float) * QS_NUM_TERMS * A, cudaMemcpyDeviceToHost, s));
     QS_CUDA(cudaStreamSynchronize(s));
-    memcpy(obs_host, h->h_obs, sizeof(float) * h->D * A);
-    memcpy(rewards_host, h->h_rewards, sizeof(float) * A);
-    memcpy(dones_host, h->h_dones, A);
-    if (rew_terms_host) memcpy(rew_terms_host, h->h_terms, sizeof(float) * QS_NUM_TERMS * A);
+    if (!po) memcpy(obs_host, h->h_obs, sizeof(float) * h->D * A);
+    if (!pr) memcpy(rewards_host, h->h_rewards, sizeof(float) * A);
+    if (!pd) memcpy(dones_host, h->h_dones, A);
+    if (rew_terms_host && !pt) memcpy(rew_terms_host, h->h_terms, sizeof(float) * QS_NUM_TERMS * A);
     return QS_OK;
 }
 
