@@ -247,10 +247,15 @@ def run_cuda_arm(args):
     E = args.envs or cfg['E']
     kw = cfg['kw']
     N = kw['num_agents']
+    # o_random episodes (pillars, spawn and goal cells) are re-drawn ON THE DEVICE at every auto-reset; the other
+    # scenarios use host-generated tables uploaded once (static_same_goal is static by definition; swarm_vs_swarm's
+    # timed goal swaps are host-driven in env.py and not part of this loop)
+    dev_scn = 'o_random' if (cfg['mode'] == 'o_random' and not args.host_tables) else None
     eng = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=rank * E, rew_coeff=cfg['rew'],
-                          ep_time=args.ep_time, **kw)
-    goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank)
-    eng.set_next_episode(goals, spawn, obst)
+                          ep_time=args.ep_time, device_scenario=dev_scn, **kw)
+    if dev_scn is None:
+        goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank)
+        eng.set_next_episode(goals, spawn, obst)
     eng.reset()
     A, D, M = E * N, eng.D, eng.M
 
@@ -395,6 +400,7 @@ def run_cuda_arm(args):
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f"{args.config}: {cfg['desc']}", 'envs_per_gpu': E, 'drones': N, 'obs_dim': D,
                        'agents_per_gpu': A, 'ep_len': eng.ep_len,
+                       'episodes': 'generated on the device at every auto-reset' if dev_scn else 'host-generated tables, uploaded once',
                        'l2': f'inputs larger than L2: action ring {R_act} x {A * 16 / 1e6:.2f} MB, observation rollout ring '
                              f'{R_obs} x {A * D * 4 / 1e6:.2f} MB; env state ({A * 192 / 1e6:.1f} MB) is L2-resident by nature',
                        'launch': f'one kernel per control step, CUDA graph of {G} steps' if graph is not None else 'one kernel per control step',
@@ -429,6 +435,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=300)
     ap.add_argument('--rollout', type=int, default=0, help='also time qs_rollout with this many steps per launch')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--host-tables', action='store_true', help='use host-generated episode tables even where a device generator exists')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -38,6 +38,15 @@ extern "C" {
 #define QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR 1 /* 19 floats */
 #define QS_OBS_XYZ_VXYZ_R_OMEGA_WALL 2  /* 24 floats */
 
+/* Episode generation (goal / spawn points, pillar placement), the job of scenario.reset() +
+ * obst_generation_given_density() in the reference (quadrotor_multi.py:304-325,347-353):
+ *   HOST_TABLES  the host uploads tables with qs_set_next_episode (any scenario of scenarios/*.py);
+ *   O_RANDOM     generated on the device at every (auto-)reset: M distinct pillar cells, N distinct free spawn cells and
+ *                N distinct free goal cells, z ~ U(1,3) (scenarios/obstacles/o_random.py:27-52, o_base.py:71-83);
+ *                needs use_obstacles.  No host work per episode. */
+#define QS_SCENARIO_HOST_TABLES 0
+#define QS_SCENARIO_O_RANDOM 1
+
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a
  * non-zero default or a CLI override (swarm_rl/env_wrappers/reward_shaping.py:7-16). */
 enum {
@@ -96,6 +105,8 @@ typedef struct QsConfig {
     float collision_falloff_radius;  /* in arm lengths (quadrotor_multi.py:155) */
     float approch_goal_metric;       /* scenario.approch_goal_metric (scenarios/base.py:31) */
     int32_t env_id_offset;           /* global id of env 0 (multi-GPU shards: rank * E); keys the RNG */
+    int32_t scenario;                /* QS_SCENARIO_*: who generates the episodes consumed by (auto-)resets */
+    int32_t obst_grid[2];            /* pillar grid cells along x / y = int(obst_spawn_area) (quadrotor_multi.py:305) */
     uint64_t seed;
 } QsConfig;
 

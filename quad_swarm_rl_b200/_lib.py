@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libquadswarm.so')
+LIB_PATH = os.environ.get('QS_LIB') or os.path.join(_PKG, 'libquadswarm.so')     # QS_LIB: tuning builds only
 
 QS_OK = 0
 QS_NUM_REW_COEFF = 8
@@ -18,6 +18,7 @@ QS_STATE_F32 = 43
 QS_STATE_U32 = 4
 QS_STATE_ENV_I32 = 16
 QS_MAX_AGENTS = 32
+SCENARIO_HOST_TABLES, SCENARIO_O_RANDOM = 0, 1
 
 REW_KEYS = ('pos', 'effort', 'crash', 'orient', 'spin', 'quadcol_bin', 'quadcol_bin_smooth_max', 'quadcol_bin_obst')
 OBS_REPR = {'xyz_vxyz_R_omega': 0, 'xyz_vxyz_R_omega_floor': 1, 'xyz_vxyz_R_omega_wall': 2}
@@ -41,7 +42,7 @@ class QsConfig(C.Structure):
         ('use_downwash', C.c_int32), ('sense_noise', C.c_int32), ('obst_size', C.c_float),
         ('room_dims', C.c_float * 3), ('ep_time', C.c_float), ('collision_hitbox_radius', C.c_float),
         ('collision_falloff_radius', C.c_float), ('approch_goal_metric', C.c_float),
-        ('env_id_offset', C.c_int32), ('seed', C.c_uint64),
+        ('env_id_offset', C.c_int32), ('scenario', C.c_int32), ('obst_grid', C.c_int32 * 2), ('seed', C.c_uint64),
     ]
 
 

@@ -90,6 +90,7 @@ struct StepParams {
     int env_id_offset;
     // observation staging (coalesced write-out): vector width V, Q = D / V, padded row stride Dp, magic = ceil(2^20 / Q)
     int obs_stage, obs_v, obs_q, obs_dp, obs_magic, smem_tile_off;
+    int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
 };
 
 struct Agent {
@@ -512,6 +513,79 @@ __device__ __noinline__ KickVO downwash_kick(RngKey key, int other, int me, floa
     o.vel.x = acc * ax * CONTROL_DT; o.vel.y = acc * ay * CONTROL_DT; o.vel.z = acc * az * CONTROL_DT;
     o.dom.x = omd * (bx / den) * CONTROL_DT; o.dom.y = omd * (by / den) * CONTROL_DT; o.dom.z = omd * (bz / den) * CONTROL_DT;
     return o;
+}
+
+// ---- device-side episode generator: o_random (scenarios/obstacles/o_random.py:27-52, o_base.py:71-83,
+//      quadrotor_multi.py:304-325).  Sequential uniform sampling without replacement over the grid cells with a
+//      64-bit occupancy mask; every lane of the env runs the same deterministic selection and keeps its own picks, so no
+//      exchange is needed.  Keyed draws (SITE_SCENARIO_U): value v = 0..M-1 pillar cells, 64.. spawn cells, 128.. spawn z,
+//      192.. goal cells, 256.. goal z.  Cell (rid, cid) sits at (cid + 0.5 - L/2, W - 1 - rid + 0.5 - W/2) like the
+//      reference's get_cell_centers / obst_map indexing.  Twin: oracle/scenario_gen.py.
+__device__ __forceinline__ int nth_free_cell(unsigned long long mask, int r, int cells) {
+    int k = 0;
+#pragma unroll 1
+    for (; k < cells; ++k) {
+        if (!((mask >> k) & 1ull)) {
+            if (r == 0) break;
+            --r;
+        }
+    }
+    return k;
+}
+
+__device__ __forceinline__ float scenario_u(const RngKey& key, int v) {
+    const float4 u = rng_uniform4(key, SITE_SCENARIO_U, 0, 0, v >> 2);
+    const int w = v & 3;
+    return w == 0 ? u.x : (w == 1 ? u.y : (w == 2 ? u.z : u.w));
+}
+
+// floor(u * n) for u = k / 2^24, in integer arithmetic so that the fp32 kernel and the fp64 oracle agree exactly
+__device__ __forceinline__ int scenario_pick(const RngKey& key, int v, int n) {
+    const uint32_t k = (uint32_t)(scenario_u(key, v) * 16777216.0f);
+    return (int)((k * (uint32_t)n) >> 24);
+}
+
+__device__ __forceinline__ float2 cell_center(int cell, int L, int W) {
+    const int rid = cell / W, cid = cell - rid * W;
+    return make_float2((float)cid + 0.5f - (float)(L / 2), (float)(W - 1 - rid) + 0.5f - (float)(W / 2));
+}
+
+struct ORandomEpisode { V3 spawn, goal; };
+
+// pillar table of the env -> `obst_out[m]` for m = lane, lane + stride, ... ; this lane's spawn / goal returned
+__device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int i, int n_agents, int M, int L, int W, int lane_i, int stride,
+                                                        float2* obst_smem, float2* obst_glob) {
+    const int cells = L * W;
+    unsigned long long mask = 0ull;
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+        const int r = scenario_pick(key, m, cells - m);
+        const int c = nth_free_cell(mask, r, cells);
+        mask |= 1ull << c;
+        if ((m % stride) == lane_i) {
+            const float2 xy = cell_center(c, L, W);
+            obst_smem[m] = xy;
+            obst_glob[m] = xy;
+        }
+    }
+    ORandomEpisode ep;
+    const int free_cells = cells - M;
+    unsigned long long ms = mask, mg = mask;
+#pragma unroll 1
+    for (int k = 0; k <= i && k < n_agents; ++k) {
+        const int rs = scenario_pick(key, 64 + k, free_cells - k);
+        const int cs = nth_free_cell(ms, rs, cells);
+        ms |= 1ull << cs;
+        const int rg = scenario_pick(key, 192 + k, free_cells - k);
+        const int cg = nth_free_cell(mg, rg, cells);
+        mg |= 1ull << cg;
+        if (k == i) {
+            const float2 a = cell_center(cs, L, W), b = cell_center(cg, L, W);
+            ep.spawn.x = a.x; ep.spawn.y = a.y; ep.spawn.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 128 + k);
+            ep.goal.x = b.x; ep.goal.y = b.y; ep.goal.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 256 + k);
+        }
+    }
+    return ep;
 }
 
 // QuadrotorSingle._reset, quadrotor_single.py:387-447: spawn jitter, z >= 0.75, random yaw facing the origin.

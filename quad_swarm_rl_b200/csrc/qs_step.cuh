@@ -226,16 +226,24 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
             nvel[0] = sv.x; nvel[1] = sv.y; nvel[2] = sv.z;
         }
         st.slots[SL_STALE_VEL * st.a_pad + a] = make_float4(nvel[0], nvel[1], nvel[2], 0.f);
-        const float4 g = st.next_goal[a], sp = st.next_spawn[a];
-        s.goal[0] = g.x; s.goal[1] = g.y; s.goal[2] = g.z;
         V3 spawn;
-        spawn.x = sp.w != 0.f ? sp.x : g.x; spawn.y = sp.w != 0.f ? sp.y : g.y; spawn.z = sp.w != 0.f ? sp.z : g.z;
+        if (p.scenario == QS_SCENARIO_O_RANDOM) {
+            // episode generated on the device; every valid lane also writes its share of the pillar table
+            const ORandomEpisode ep = o_random_episode(key, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, s_obst_env,
+                                                       st.obst + (long long)env * p.M);
+            s.goal[0] = ep.goal.x; s.goal[1] = ep.goal.y; s.goal[2] = ep.goal.z;
+            spawn = ep.spawn;
+        } else {
+            const float4 g = st.next_goal[a], sp = st.next_spawn[a];
+            s.goal[0] = g.x; s.goal[1] = g.y; s.goal[2] = g.z;
+            spawn.x = sp.w != 0.f ? sp.x : g.x; spawn.y = sp.w != 0.f ? sp.y : g.y; spawn.z = sp.w != 0.f ? sp.z : g.z;
+        }
         const ResetPose rp = reset_pose(key, i, spawn, p.use_obst ? 0.1f : 2.0f);      // box: quadrotor_single.py:215-218
         apply_reset(s, rp);
         st.slots[SL_DIST_SUMS * st.a_pad + a] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (p.use_obst) {
-        if (do_reset) {
+        if (do_reset && p.scenario != QS_SCENARIO_O_RANDOM) {
             for (int m = i; m < p.M; m += NP) {
                 const float2 ob = st.next_obst[(long long)env * p.M + m];
                 st.obst[(long long)env * p.M + m] = ob;
@@ -246,8 +254,11 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
     }
 }
 
+#ifndef QS_LB
+#define QS_LB 128
+#endif
 template <int NP>
-__global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ float2 s_obst[];
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
@@ -337,7 +348,11 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         s.ou[1] += OU_THETA * (0.f - s.ou[1]) + OU_SIGMA * ou_z.y;
         s.ou[2] += OU_THETA * (0.f - s.ou[2]) + OU_SIGMA * ou_z.z;
         s.ou[3] += OU_THETA * (0.f - s.ou[3]) + OU_SIGMA * ou_z.w;
+#ifdef QS_UNROLL_SUB
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int sub = 0; sub < SIM_STEPS; ++sub) {
             ctr.svd_count += 1;
             const bool do_svd = ctr.svd_count >= SVD_PERIOD;
@@ -369,7 +384,11 @@ __global__ void __launch_bounds__(128) qs_step_kernel(const __grid_constant__ St
         if (NP > 1) {
             const float max_pen = p.rew[QS_REW_QUADCOL_BIN_SMOOTH_MAX];
             const float pen_ratio = -max_pen / p.falloff_thr;
-#pragma unroll 2
+#ifndef QS_PASSA_UNROLL
+#define QS_PASSA_UNROLL 2
+#endif
+            constexpr int kPassAUnroll = QS_PASSA_UNROLL;
+#pragma unroll kPassAUnroll
             for (int j = 0; j < p.N; ++j) {
                 const float dx = s.pos[0] - shfl<NP>(s.pos[0], j), dy = s.pos[1] - shfl<NP>(s.pos[1], j),
                             dz = s.pos[2] - shfl<NP>(s.pos[2], j);

@@ -84,6 +84,7 @@ static void fill_params(const QsHandle* h, StepParams& p) {
     p.obs_dp = (Q % 2 == 0) ? D + V : D;                 // odd number of V-wide words per row: fewer bank conflicts
     p.obs_magic = ((1 << 20) + Q - 1) / Q;
     p.obs_stage = (D <= 72) ? 1 : 0;
+    p.scenario = c.scenario; p.grid_l = c.obst_grid[0]; p.grid_w = c.obst_grid[1];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,6 +280,16 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     if (K < 0 || K > cfg->num_agents - 1) return fail(QS_ERR_INVALID_ARG, "Incorrect number of neigbors");
     if (cfg->use_obstacles && cfg->num_obstacles < 1) return fail(QS_ERR_INVALID_ARG, "use_obstacles needs num_obstacles >= 1");
     if (cfg->ep_time <= 0.f) return fail(QS_ERR_INVALID_ARG, "ep_time must be positive");
+    if (cfg->scenario != QS_SCENARIO_HOST_TABLES && cfg->scenario != QS_SCENARIO_O_RANDOM)
+        return fail(QS_ERR_INVALID_ARG, "unknown scenario");
+    if (cfg->scenario == QS_SCENARIO_O_RANDOM) {
+        const int cells = cfg->obst_grid[0] * cfg->obst_grid[1];
+        if (!cfg->use_obstacles) return fail(QS_ERR_INVALID_ARG, "scenario o_random needs use_obstacles");
+        if (cfg->obst_grid[0] < 1 || cfg->obst_grid[1] < 1 || cells > 64)
+            return fail(QS_ERR_UNSUPPORTED, "device-side o_random supports pillar grids of at most 64 cells");
+        if (cells - cfg->num_obstacles < cfg->num_agents)
+            return fail(QS_ERR_INVALID_ARG, "o_random: fewer free grid cells than drones");
+    }
     QS_CUDA(cudaSetDevice(device));
     QsHandle* h = new (std::nothrow) QsHandle();
     if (!h) return fail(QS_ERR_INVALID_ARG, "out of host memory");

@@ -24,7 +24,8 @@ class QuadSwarmEngine:
                  neighbor_obs_type='pos_vel', use_obstacles=False, obst_density=0.2, obst_size=0.6,
                  obst_spawn_area=(8.0, 8.0), use_downwash=False, room_dims=(10., 10., 10.), ep_time=15.0,
                  collision_hitbox_radius=2.0, collision_falloff_radius=4.0, sense_noise='default',
-                 approch_goal_metric=0.5, rew_coeff=None, seed=0, device=0, env_id_offset=0):
+                 approch_goal_metric=0.5, rew_coeff=None, seed=0, device=0, env_id_offset=0,
+                 device_scenario=None):
         if not torch.cuda.is_available():
             raise RuntimeError("QuadSwarmEngine needs a CUDA device (the env step has no CPU path)")
         self.lib = L.load()
@@ -48,7 +49,12 @@ class QuadSwarmEngine:
         cfg.collision_falloff_radius = float(collision_falloff_radius)
         cfg.approch_goal_metric = float(approch_goal_metric)
         cfg.env_id_offset = int(env_id_offset)
+        if device_scenario not in (None, 'o_random'):
+            raise ValueError(f"no device-side generator for scenario {device_scenario!r} (host tables handle it)")
+        cfg.scenario = L.SCENARIO_O_RANDOM if device_scenario == 'o_random' else L.SCENARIO_HOST_TABLES
+        cfg.obst_grid = (C.c_int32 * 2)(int(obst_spawn_area[0]), int(obst_spawn_area[1]))
         cfg.seed = int(seed)
+        self.device_scenario = device_scenario
         self.cfg = cfg
         h = C.c_void_p()
         L.check(self.lib.qs_create(C.byref(cfg), int(device), C.byref(h)))

@@ -80,7 +80,7 @@ class _EnvBase:
                  use_downwash, use_numba, quads_mode, room_dims, use_replay_buffer, quads_view_mode, quads_render,
                  dynamics_params, raw_control, raw_control_zero_middle, dynamics_randomize_every, dynamics_change,
                  dyn_sampler_1, sense_noise, init_random_state, render_mode='human', device=0, seed=None,
-                 env_id_offset=0):
+                 env_id_offset=0, device_scenario=None):
         # the env factory's fixed choices (swarm_rl/env_wrappers/quad_utils.py:22-31) are the only supported ones
         if dynamics_params != 'Crazyflie':
             raise NotImplementedError("only the Crazyflie parameter set is built into the CUDA kernels")
@@ -139,7 +139,8 @@ class _EnvBase:
             obst_size=obst_size, obst_spawn_area=obst_spawn_area, use_downwash=use_downwash, room_dims=room_dims,
             ep_time=ep_time, collision_hitbox_radius=collision_hitbox_radius,
             collision_falloff_radius=collision_falloff_radius, sense_noise=sense_noise, rew_coeff=rew_coeff,
-            seed=seed, device=device, env_id_offset=env_id_offset)
+            seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario)
+        self.device_scenario = device_scenario
         self.rew_coeff = self.engine.rew_coeff               # the live, mutable dict (reward_shaping.py:55-61 writes it)
         self.ep_len = self.engine.ep_len
         self.num_obstacles = self.engine.M
@@ -182,6 +183,9 @@ class _EnvBase:
 
     def _begin_episodes(self, envs):
         """Host bookkeeping after the device (auto-)reset of `envs`: current scenario <- next, generate the one after."""
+        if self.device_scenario is not None:          # episodes are generated inside the kernels: only the tick restarts
+            self._tick[list(envs)] = 0
+            return
         for e in envs:
             self._scenarios[e], self._next_scenarios[e] = self._next_scenarios[e], self._make_scenario()
             self._goals[e] = self._next['goals'][e]
@@ -192,6 +196,10 @@ class _EnvBase:
         self._push_next(mask)
 
     def _reset_all(self):
+        if self.device_scenario is not None:
+            obs = self.engine.reset()
+            self._tick[:] = 0
+            return obs
         for e in range(self.num_envs):
             self._generate_episode(self._next_scenarios[e], e)
         self._push_next()
@@ -357,12 +365,15 @@ class QuadrotorEnvMultiBatched(_EnvBase):
                  neighbor_visible_num=-1, neighbor_obs_type='pos_vel', collision_hitbox_radius=2.0,
                  collision_falloff_radius=4.0, use_obstacles=False, obst_density=0.2, obst_size=0.6,
                  obst_spawn_area=(8.0, 8.0), use_downwash=False, quads_mode='static_same_goal',
-                 room_dims=(10., 10., 10.), sense_noise='default', device=0, seed=None, env_id_offset=0):
+                 room_dims=(10., 10., 10.), sense_noise='default', device=0, seed=None, env_id_offset=0,
+                 device_scenarios=True):
+        # o_random has a device-side generator (no host work per episode); every other mode uses host tables
+        dev_scn = 'o_random' if (device_scenarios and quads_mode == 'o_random' and use_obstacles) else None
         super().__init__(num_envs, num_agents, ep_time, rew_coeff, obs_repr, neighbor_visible_num, neighbor_obs_type,
                          collision_hitbox_radius, collision_falloff_radius, use_obstacles, obst_density, obst_size,
                          obst_spawn_area, use_downwash, True, quads_mode, room_dims, False, ['topdown'], False,
                          'Crazyflie', True, True, None, None, None, sense_noise, False, device=device, seed=seed,
-                         env_id_offset=env_id_offset)
+                         env_id_offset=env_id_offset, device_scenario=dev_scn)
         self.num_agents = num_envs * num_agents
         self._truncated = torch.zeros(self.num_agents, dtype=torch.bool, device=self.engine.device)
 

@@ -159,3 +159,37 @@ def test_episode_stats_latch_matches_oracle():
             np.testing.assert_allclose(ags[e, i, 1], si['distance_to_goal_3s'], rtol=1e-4)
             np.testing.assert_allclose(ags[e, i, 2], si['distance_to_goal_5s'], rtol=1e-4)
     pair.engine.close()
+
+
+def test_device_side_o_random_generator_matches_twin():
+    """QS_SCENARIO_O_RANDOM: episodes generated inside the reset path of the kernels equal oracle/scenario_gen.py
+    (same keyed draws), and the whole trajectory stays in parity across auto-resets (no host tables involved)."""
+    import torch
+    from oracle import quadswarm_oracle as qo
+    from oracle.scenario_gen import DeviceORandomSource
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    from tests import parity_util as pu
+    kw = dict(C3, ep_time=0.5)
+    E, seed = 10, 4321
+
+    class DevPair(pu.Pair):
+        def __init__(self):
+            self.E, self.kw, self.N = E, dict(kw), 8
+            self.engine = QuadSwarmEngine(num_envs=E, seed=seed, device_scenario='o_random', **kw)
+            self.ocfg = pu.cfg_to_oracle(kw)
+            self.oracles = [qo.OracleEnv(self.ocfg, qo.PhiloxRng(seed), DeviceORandomSource(), env_id=e) for e in range(E)]
+            self.table_idx = 0
+
+        def _push_table(self, k):
+            pass
+
+    pair = DevPair()
+    rep = pu.run_parity(pair, 130, np.random.RandomState(5), resync=20)
+    assert rep['dones'] >= 2 * E
+    st = pair.engine.get_state()
+    obst_dev = st['obst_xy'].cpu().numpy()
+    goals_dev = st['agent_f32'][..., 30:33].cpu().numpy()
+    for e, o in enumerate(pair.oracles):
+        assert np.array_equal(obst_dev[e], o.obst_xy.astype(np.float32))
+        np.testing.assert_allclose(goals_dev[e], np.array([d.goal for d in o.drones]), rtol=1e-6)
+    pair.engine.close()

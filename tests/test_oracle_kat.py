@@ -112,3 +112,24 @@ def test_keyed_draw_statistics():
     u = np.array([d.uniform(px.SITE_WALL_U, i, 0, v) for i in range(400) for v in range(11)])
     assert abs(z.mean()) < 0.06 and abs(z.std() - 1) < 0.05
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.02
+
+
+def test_device_o_random_twin_properties():
+    """oracle/scenario_gen.py (twin of the device generator): distinct pillar cells, spawn / goal cells distinct and
+    free, heights in [1, 3), every cell equally likely to hold a pillar (12/64)."""
+    from oracle import scenario_gen as sg
+    counts = np.zeros((8, 8))
+    for env in range(400):
+        d = px.KeyedDraws(99, env, 7)
+        goals, spawn, obst = sg.o_random_episode(d, 8, 12, 8, 8)
+        pil = {tuple(o) for o in obst}
+        assert len(pil) == 12
+        for pts in (goals, spawn):
+            xy = [tuple(p[:2]) for p in pts]
+            assert len(set(xy)) == 8 and not (set(xy) & pil)
+            assert np.all(pts[:, 2] >= 1.0) and np.all(pts[:, 2] < 3.0)
+        for o in obst:
+            counts[int(o[0] + 3.5), int(o[1] + 3.5)] += 1
+    assert abs(counts.mean() - 400 * 12 / 64) < 1e-9 and counts.min() > 40 and counts.max() < 115
+    cells = qo.get_cell_centers(8, 8)
+    assert {tuple(c) for c in cells} == {tuple(sg._cell_center(k, 8, 8)) for k in range(64)}
