@@ -37,20 +37,29 @@ __device__ __forceinline__ float min_pillar_dist2(const StepParams& p, const Age
 // SURVEY Appendix D-6); `nz` is the scaled sensor noise of this observation.
 // `row` points either at the drone's row in global memory or at its row of the warp's shared-memory staging tile
 // (see flush_observation_tile).
-template <int NP>
+// Hand-off arrays of the split (physics warp -> observer warp) kernel: 24 arrays of 32 floats in shared memory.
+enum Hand { H_PX = 0, H_PY, H_PZ, H_VX, H_VY, H_VZ, H_NVX, H_NVY, H_NVZ, H_R0, H_OX = H_R0 + 9, H_OY, H_OZ, H_GX, H_GY, H_GZ, H_COUNT };
+constexpr int HAND_FLOATS = H_COUNT * 32 + 32;          // + one flag word per lane slot
+constexpr uint32_t HF_KICKED = 1u, HF_RESET = 2u;
+
+// value of drone j of my env: from the hand-off arrays (SM) or by warp shuffle from the lane that owns it
+template <int NP, bool SM>
+__device__ __forceinline__ float nbv(float mine, const float* hand, int arr, int gbase, int j) {
+    if (SM) return hand[32 * arr + gbase + j];
+    return __shfl_sync(0xffffffffu, mine, j, NP);
+}
+
+template <int NP, bool SM = false>
 __device__ __forceinline__ void write_observation(const StepParams& p, const Agent& s, const float nvel[3], const Noise9& nz,
                                                   int i, bool valid, const float2* s_obst_env, float dmin2,
-                                                  float* __restrict__ row) {
+                                                  float* __restrict__ row, const float* hand = nullptr, int gbase = 0) {
     // ---- self observation
     {
         const float px = s.pos[0] + nz.p[0], py = s.pos[1] + nz.p[1], pz = s.pos[2] + nz.p[2];
-        float rot[9];
-        if (p.sense_noise) {
-            observed_rotation(s.R, rot);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) rot[k] = s.R[k];
-        }
+        // The reference observes quat2R(rot2quat(R)) (sensor_noise.py:205-210); with the default noise set the rotation
+        // noise is exactly zero, the round trip is the identity up to rounding (<= 4e-16 in float64),
+        // so R is emitted directly.  (`observed_rotation()` keeps the explicit round trip for reference.)
+        const float* rot = s.R;
         if (valid) {
             row[0] = px - s.goal[0]; row[1] = py - s.goal[1]; row[2] = pz - s.goal[2];
             row[3] = s.vel[0] + nz.v[0]; row[4] = s.vel[1] + nz.v[1]; row[5] = s.vel[2] + nz.v[2];
@@ -77,8 +86,8 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
             int slot = 0;
 #pragma unroll 1
             for (int j = 0; j < p.N; ++j) {
-                const float qx = shfl<NP>(s.pos[0], j), qy = shfl<NP>(s.pos[1], j), qz = shfl<NP>(s.pos[2], j);
-                const float wx = shfl<NP>(nvel[0], j), wy = shfl<NP>(nvel[1], j), wz = shfl<NP>(nvel[2], j);
+                const float qx = nbv<NP, SM>(s.pos[0], hand, H_PX, gbase, j), qy = nbv<NP, SM>(s.pos[1], hand, H_PY, gbase, j), qz = nbv<NP, SM>(s.pos[2], hand, H_PZ, gbase, j);
+                const float wx = nbv<NP, SM>(nvel[0], hand, H_NVX, gbase, j), wy = nbv<NP, SM>(nvel[1], hand, H_NVY, gbase, j), wz = nbv<NP, SM>(nvel[2], hand, H_NVZ, gbase, j);
                 if (j != i && valid) {
                     float* d = nrow + 6 * slot;
                     d[0] = clampf(qx - s.pos[0], -rx, rx); d[1] = clampf(qy - s.pos[1], -ry, ry);
@@ -93,10 +102,10 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
             float score[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                const float dx = shfl<NP>(s.pos[0], j) - s.pos[0], dy = shfl<NP>(s.pos[1], j) - s.pos[1],
-                            dz = shfl<NP>(s.pos[2], j) - s.pos[2];
-                const float ux = shfl<NP>(nvel[0], j) - nvel[0], uy = shfl<NP>(nvel[1], j) - nvel[1],
-                            uz = shfl<NP>(nvel[2], j) - nvel[2];
+                const float dx = nbv<NP, SM>(s.pos[0], hand, H_PX, gbase, j) - s.pos[0], dy = nbv<NP, SM>(s.pos[1], hand, H_PY, gbase, j) - s.pos[1],
+                            dz = nbv<NP, SM>(s.pos[2], hand, H_PZ, gbase, j) - s.pos[2];
+                const float ux = nbv<NP, SM>(nvel[0], hand, H_NVX, gbase, j) - nvel[0], uy = nbv<NP, SM>(nvel[1], hand, H_NVY, gbase, j) - nvel[1],
+                            uz = nbv<NP, SM>(nvel[2], hand, H_NVZ, gbase, j) - nvel[2];
                 const float dist = fmaxf(norm3(dx, dy, dz), 0.01f);
                 const float sc = dist + (dx * ux + dy * uy + dz * uz) * frcp(dist);
                 score[j] = (j < p.N && j != i) ? sc : __int_as_float(0x7f800000);   // +inf: never selected
@@ -116,8 +125,8 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
                 const int src = bj;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) score[j] = (j == src) ? __int_as_float(0x7f800000) : score[j];
-                const float qx = shfl<NP>(s.pos[0], src), qy = shfl<NP>(s.pos[1], src), qz = shfl<NP>(s.pos[2], src);
-                const float wx = shfl<NP>(nvel[0], src), wy = shfl<NP>(nvel[1], src), wz = shfl<NP>(nvel[2], src);
+                const float qx = nbv<NP, SM>(s.pos[0], hand, H_PX, gbase, src), qy = nbv<NP, SM>(s.pos[1], hand, H_PY, gbase, src), qz = nbv<NP, SM>(s.pos[2], hand, H_PZ, gbase, src);
+                const float wx = nbv<NP, SM>(nvel[0], hand, H_NVX, gbase, src), wy = nbv<NP, SM>(nvel[1], hand, H_NVY, gbase, src), wz = nbv<NP, SM>(nvel[2], hand, H_NVZ, gbase, src);
                 if (valid) {
                     float* d = nrow + 6 * k;
                     d[0] = clampf(qx - s.pos[0], -rx, rx); d[1] = clampf(qy - s.pos[1], -ry, ry);
@@ -257,14 +266,46 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
 #ifndef QS_LB
 #define QS_LB 128
 #endif
-template <int NP>
+// named barriers of the split kernel (physics warp <-> observer warp, 64 threads)
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// physics warp -> shared hand-off arrays
+__device__ __forceinline__ void hand_store(float* hand, int lane, const Agent& s, const float nvel[3]) {
+    hand[32 * H_PX + lane] = s.pos[0]; hand[32 * H_PY + lane] = s.pos[1]; hand[32 * H_PZ + lane] = s.pos[2];
+    hand[32 * H_VX + lane] = s.vel[0]; hand[32 * H_VY + lane] = s.vel[1]; hand[32 * H_VZ + lane] = s.vel[2];
+    hand[32 * H_NVX + lane] = nvel[0]; hand[32 * H_NVY + lane] = nvel[1]; hand[32 * H_NVZ + lane] = nvel[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hand[32 * (H_R0 + k) + lane] = s.R[k];
+    hand[32 * H_OX + lane] = s.om[0]; hand[32 * H_OY + lane] = s.om[1]; hand[32 * H_OZ + lane] = s.om[2];
+    hand[32 * H_GX + lane] = s.goal[0]; hand[32 * H_GY + lane] = s.goal[1]; hand[32 * H_GZ + lane] = s.goal[2];
+}
+
+__device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s, float nvel[3]) {
+    s.pos[0] = hand[32 * H_PX + lane]; s.pos[1] = hand[32 * H_PY + lane]; s.pos[2] = hand[32 * H_PZ + lane];
+    s.vel[0] = hand[32 * H_VX + lane]; s.vel[1] = hand[32 * H_VY + lane]; s.vel[2] = hand[32 * H_VZ + lane];
+    nvel[0] = hand[32 * H_NVX + lane]; nvel[1] = hand[32 * H_NVY + lane]; nvel[2] = hand[32 * H_NVZ + lane];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s.R[k] = hand[32 * (H_R0 + k) + lane];
+    s.om[0] = hand[32 * H_OX + lane]; s.om[1] = hand[32 * H_OY + lane]; s.om[2] = hand[32 * H_OZ + lane];
+    s.goal[0] = hand[32 * H_GX + lane]; s.goal[1] = hand[32 * H_GY + lane]; s.goal[2] = hand[32 * H_GZ + lane];
+}
+
+// The step kernel.  SPLIT = false: one warp does everything for its 32 drones.  SPLIT = true (blocks of 64 threads):
+// warp 0 ("physics") integrates, detects and resolves contacts and keeps the books; warp 1 ("observer") draws the
+// sensor noise while the physics warp integrates, then builds the observation rows from the hand-off arrays in shared
+// memory — speculatively from the post-integration state, re-done only in the rare steps where a contact response or a
+// reset changed it.  The two halves of a drone's ~2.7 k-instruction dependency chain overlap.
+template <int NP, bool SPLIT>
 __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ float2 s_obst[];
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
     const int i = lane & (NP - 1);
-    const int envs_per_block = blockDim.x / NP;
-    const int env_local = threadIdx.x / NP;
+    const int role = SPLIT ? (threadIdx.x >> 5) : 0;                 // 0 physics (or everything), 1 observer
+    const int tid = SPLIT ? lane : threadIdx.x;
+    const int envs_per_block = (SPLIT ? 32 : blockDim.x) / NP;
+    const int env_local = tid / NP;
     const int env = blockIdx.x * envs_per_block + env_local;
     const bool env_ok = env < p.E;
     const bool valid = env_ok && i < p.N;
@@ -279,11 +320,13 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
     float2* s_obst_env = s_obst + env_local * p.M;
-    float* s_tile = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + (threadIdx.x >> 5) * (32 * p.obs_dp);
+    float* s_tile = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + (SPLIT ? 0 : (threadIdx.x >> 5)) * (32 * p.obs_dp);
+    float* s_hand = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + 32 * p.obs_dp;      // SPLIT only
+    uint32_t* s_hflag = reinterpret_cast<uint32_t*>(s_hand + 32 * H_COUNT);
 
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
-    if (valid) load_agent(st, a, s);          // state loads are issued before the pillar staging barrier
+    if (valid && role == 0) load_agent(st, a, s);          // state loads are issued before the pillar staging barrier
     // stage this block's pillar tables (contiguous [envs_per_block][M] float2) in shared memory
     if (p.use_obst) {
         const long long base = (long long)blockIdx.x * envs_per_block * p.M;
@@ -305,6 +348,61 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         const int4 c = st.env_ctr[env];
         ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
     }
+    if (SPLIT && role == 1) {
+        // ============================ observer warp ============================
+        const int gbase = lane & ~(NP - 1);
+        const int slot = (lane / NP) * p.N + i;                       // row of this drone inside the warp's tile
+        const int env_first = blockIdx.x * envs_per_block;
+        const int envs_here = min(envs_per_block, p.E - env_first);
+#pragma unroll 1
+        for (int t = 0; t < p.T; ++t) {
+            RngKey key;
+            key.k0 = p.seed_lo; key.k1 = p.seed_hi;
+            key.env = (uint32_t)(p.env_id_offset + env);
+            key.step = (uint32_t)ctr.step_count;
+            const bool want = !p.last_obs_only || t == p.T - 1;
+            Noise9 nz;
+            {   // first sensor-noise draw (3 Philox blocks, 3-way ILP), overlapped with the physics warp's integration
+                const uint32_t c2[4] = {rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0)};
+                const uint32_t c3[4] = {0u, 1u, 2u, 3u};
+                uint4 blk[4];
+                philox4x32_10_x4(key.env, key.step, c2, c3, key.k0, key.k1, blk);
+                const float4 na = normal4_of(blk[0]), nb = normal4_of(blk[1]);
+                float nc0, nc1;
+                normal_pair(blk[2].x, blk[2].y, nc0, nc1);
+                const float on = p.sense_noise ? 1.f : 0.f;
+                nz.p[0] = on * POS_NOISE_STD * na.x; nz.p[1] = on * POS_NOISE_STD * na.y; nz.p[2] = on * POS_NOISE_STD * na.z;
+                nz.v[0] = on * VEL_NOISE_STD * na.w; nz.v[1] = on * VEL_NOISE_STD * nb.x; nz.v[2] = on * VEL_NOISE_STD * nb.y;
+                nz.w[0] = on * GYRO_NOISE_STD * nb.z; nz.w[1] = on * GYRO_NOISE_STD * nb.w; nz.w[2] = on * GYRO_NOISE_STD * nc0;
+            }
+            Agent o;
+            float nvel[3];
+            bar_sync(1);                                              // post-integration state is in the hand-off arrays
+            if (want) {
+                hand_load(s_hand, lane, o, nvel);
+                const float dmin2 = p.use_obst ? min_pillar_dist2(p, o, s_obst_env) : 1e4f;
+                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand, gbase);
+            }
+            bar_sync(2);                                              // final state + flags
+            const uint32_t hf = s_hflag[gbase];
+            if (want && hf != 0u) {                                   // contact response or reset: rebuild the rows of this env
+                hand_load(s_hand, lane, o, nvel);
+                if (p.sense_noise) nz = sensor_noise(key, (hf & HF_RESET) ? SITE_SENSOR_RESET : SITE_SENSOR1, i);
+                const float dmin2 = p.use_obst ? min_pillar_dist2(p, o, s_obst_env) : 1e4f;
+                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand, gbase);
+            }
+            if (want) {
+                __syncwarp();
+                float* gbase_ptr = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
+                if (envs_here > 0)
+                    flush_observation_tile(p, s_tile, gbase_ptr + (long long)env_first * p.N * p.D, envs_here * p.N, lane);
+            }
+            ctr.step_count += 1;
+            bar_sync(3);                                              // hand-off arrays and tile are free again
+        }
+        return;
+    }
+
     bool goal_dirty = false;
     const float col_thr2 = p.col_thr * p.col_thr, falloff2 = p.falloff_thr * p.falloff_thr;
     const float obst_thr2 = p.obst_col_thr * p.obst_col_thr;
@@ -319,7 +417,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         // the draws every drone needs every step: OU thrust noise + first sensor-noise draw (4 Philox blocks, 4-way ILP)
         Noise9 nz;
         float4 ou_z;
-        {
+        if (SPLIT) {
+            ou_z = rng_normal4(key, SITE_OU, i, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { nz.p[k] = 0.f; nz.v[k] = 0.f; nz.w[k] = 0.f; }
+        } else {
             const uint32_t c2[4] = {rng_c2(SITE_OU, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0)};
             const uint32_t c3[4] = {0u, 0u, 1u, 2u};
             uint4 blk[4];
@@ -358,6 +460,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             const bool do_svd = ctr.svd_count >= SVD_PERIOD;
             if (do_svd) ctr.svd_count = 0;
             dynamics_substep(s, cmd, do_svd, p, key, i, sub);
+        }
+        if (SPLIT) {                                                   // positions are final from here on
+            hand_store(s_hand, lane, s, s.vel);
+            bar_arrive(1);
         }
         // compute_reward_weighted, quadrotor_single.py:34-92 (dt = SIM dt, raw unclipped action)
         const bool on_floor = (s.flags & QS_FLAG_ON_FLOOR) != 0u;
@@ -415,18 +521,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 }
             }
         }
-        // collision bookkeeping, quadrotor_multi.py:433-459 (quirks D-2..D-4 reproduced)
-        const bool in_u = (cur_col != 0u) && (s.prev_col == 0u);                     // flattened-id set difference
-        const uint32_t u_mask = group_ballot<NP>(in_u && valid);
-        const int col_curr_tick = __popc(u_mask) / 2;
-        const bool u_any = (u_mask & ~1u) != 0u;                                      // ids.any(): id 0 alone is falsy
-        const float raw_quadcol = (u_any && in_u) ? -1.0f : 0.0f;
-        const uint32_t new_pairs = cur_col & ~s.prev_col;                             // pair-level novelty (:437-438)
-        const bool settled = (float)ctr.tick >= p.grace_steps;
-        if (col_curr_tick > 0 && settled && in_u) s.flags &= ~QS_FLAG_NO_COL_AGENT;
-        s.prev_col = cur_col;
-
-        // obstacles: first pillar in index order within arm + radius (obstacles/utils.py:31-43), :462-488
+        // obstacles: first pillar in index order within arm + radius (obstacles/utils.py:31-43)
         int hit = -1;
         float dmin2 = 1e4f;                          // smallest squared centre distance to a pillar (prunes the SDF pass)
         if (p.use_obst) {
@@ -439,29 +534,86 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 dmin2 = fminf(dmin2, d2);
             }
         }
-        const bool new_obst = (hit >= 0) && !(s.flags & QS_FLAG_PREV_OBST) && valid;
-        const uint32_t obst_mask = p.use_obst ? group_ballot<NP>(new_obst) : 0u;
-        const float raw_obst = new_obst ? -1.0f : 0.0f;
-        s.flags = (hit >= 0) ? (s.flags | QS_FLAG_PREV_OBST) : (s.flags & ~QS_FLAG_PREV_OBST);
-        bool far35 = false, far5 = false;
-        if (new_obst && settled) {
-            s.flags &= ~QS_FLAG_NO_COL_OBST;
-            // distance to goal of the FIRST-draw noisy position (quadrotor_multi.py:474)
-            const float q = norm3((s.pos[0] + nz.p[0]) - s.goal[0], (s.pos[1] + nz.p[1]) - s.goal[1], (s.pos[2] + nz.p[2]) - s.goal[2]);
-            far35 = q > 3.5f; far5 = q > 5.0f;
-        }
 
-        // room, quadrotor_multi.py:289-302,491-497 (quirk D-5: novelty against the previously RETURNED lists)
-        const bool floor_c = (s.flags & QS_FLAG_CRASHED_FLOOR) != 0u && valid;
-        const bool wall_c = (s.flags & QS_FLAG_CRASHED_WALL) && !(s.flags & QS_FLAG_PREV_WALL) && valid;
-        const bool ceil_c = (s.flags & QS_FLAG_CRASHED_CEILING) && !(s.flags & QS_FLAG_PREV_CEILING) && valid;
-        const bool room_c = (floor_c || wall_c || ceil_c) && !(s.flags & QS_FLAG_PREV_ROOM);
-        s.flags &= ~(QS_FLAG_PREV_WALL | QS_FLAG_PREV_CEILING | QS_FLAG_PREV_ROOM | QS_FLAG_KICKED | QS_FLAG_NEW_QUADCOL | QS_FLAG_NEW_OBSTCOL);
-        if (wall_c) s.flags |= QS_FLAG_PREV_WALL;
-        if (ceil_c) s.flags |= QS_FLAG_PREV_CEILING;
-        if (room_c) s.flags |= QS_FLAG_PREV_ROOM;
-        if (u_any && in_u) s.flags |= QS_FLAG_NEW_QUADCOL;
-        if (new_obst) s.flags |= QS_FLAG_NEW_OBSTCOL;
+        // ---- discrete events of this step.  Almost every step is "quiet" for all 32 drones of a warp (no contact now or
+        //      on the previous tick, no crash flag, no downwash): then the whole bookkeeping below collapses to defaults.
+        float raw_quadcol = 0.f, raw_obst = 0.f;
+        uint32_t new_pairs = 0u;
+        bool new_obst = false, wall_c = false, ceil_c = false, kicked = false;
+        const uint32_t busy_flags = QS_FLAG_CRASHED_FLOOR | QS_FLAG_CRASHED_WALL | QS_FLAG_CRASHED_CEILING | QS_FLAG_PREV_WALL |
+                                    QS_FLAG_PREV_CEILING | QS_FLAG_PREV_ROOM | QS_FLAG_PREV_OBST;
+        const bool quiet = cur_col == 0u && s.prev_col == 0u && hit < 0 && (s.flags & busy_flags) == 0u && !dw_applied;
+        const bool settled = (float)ctr.tick >= p.grace_steps;
+        s.flags &= ~(QS_FLAG_KICKED | QS_FLAG_NEW_QUADCOL | QS_FLAG_NEW_OBSTCOL);
+        if (!__all_sync(0xffffffffu, quiet)) {
+            // collision bookkeeping, quadrotor_multi.py:433-459 (quirks D-2..D-4 reproduced)
+            const bool in_u = (cur_col != 0u) && (s.prev_col == 0u);                     // flattened-id set difference
+            const uint32_t u_mask = group_ballot<NP>(in_u && valid);
+            const int col_curr_tick = __popc(u_mask) / 2;
+            const bool u_any = (u_mask & ~1u) != 0u;                                      // ids.any(): id 0 alone is falsy
+            raw_quadcol = (u_any && in_u) ? -1.0f : 0.0f;
+            new_pairs = cur_col & ~s.prev_col;                                            // pair-level novelty (:437-438)
+            if (col_curr_tick > 0 && settled && in_u) s.flags &= ~QS_FLAG_NO_COL_AGENT;
+            s.prev_col = cur_col;
+
+            // pillar contacts, :462-488
+            new_obst = (hit >= 0) && !(s.flags & QS_FLAG_PREV_OBST) && valid;
+            const uint32_t obst_mask = p.use_obst ? group_ballot<NP>(new_obst) : 0u;
+            raw_obst = new_obst ? -1.0f : 0.0f;
+            s.flags = (hit >= 0) ? (s.flags | QS_FLAG_PREV_OBST) : (s.flags & ~QS_FLAG_PREV_OBST);
+            bool far35 = false, far5 = false;
+            if (new_obst && settled) {
+                s.flags &= ~QS_FLAG_NO_COL_OBST;
+                // distance to goal of the FIRST-draw noisy position (quadrotor_multi.py:474)
+                if (SPLIT && p.sense_noise) {
+                    const float4 n0 = rng_normal4(key, SITE_SENSOR0, i, 0, 0);
+                    nz.p[0] = POS_NOISE_STD * n0.x; nz.p[1] = POS_NOISE_STD * n0.y; nz.p[2] = POS_NOISE_STD * n0.z;
+                }
+                const float q = norm3((s.pos[0] + nz.p[0]) - s.goal[0], (s.pos[1] + nz.p[1]) - s.goal[1], (s.pos[2] + nz.p[2]) - s.goal[2]);
+                far35 = q > 3.5f; far5 = q > 5.0f;
+            }
+
+            // room, quadrotor_multi.py:289-302,491-497 (quirk D-5: novelty against the previously RETURNED lists)
+            const bool floor_c = (s.flags & QS_FLAG_CRASHED_FLOOR) != 0u && valid;
+            wall_c = (s.flags & QS_FLAG_CRASHED_WALL) && !(s.flags & QS_FLAG_PREV_WALL) && valid;
+            ceil_c = (s.flags & QS_FLAG_CRASHED_CEILING) && !(s.flags & QS_FLAG_PREV_CEILING) && valid;
+            const bool room_c = (floor_c || wall_c || ceil_c) && !(s.flags & QS_FLAG_PREV_ROOM);
+            s.flags &= ~(QS_FLAG_PREV_WALL | QS_FLAG_PREV_CEILING | QS_FLAG_PREV_ROOM);
+            if (wall_c) s.flags |= QS_FLAG_PREV_WALL;
+            if (ceil_c) s.flags |= QS_FLAG_PREV_CEILING;
+            if (room_c) s.flags |= QS_FLAG_PREV_ROOM;
+            if (u_any && in_u) s.flags |= QS_FLAG_NEW_QUADCOL;
+            if (new_obst) s.flags |= QS_FLAG_NEW_OBSTCOL;
+
+            // ballots of this step's discrete events.  NB: none of them may sit behind a short-circuit `||` / `&&` whose
+            // left side differs between the envs of a warp.
+            const uint32_t floor_m = group_ballot<NP>(floor_c), wall_m = group_ballot<NP>(wall_c),
+                           ceil_m = group_ballot<NP>(ceil_c), room_m = group_ballot<NP>(room_c);
+            const uint32_t dw_m = p.use_downwash ? group_ballot<NP>(dw_applied) : 0u;
+            const uint32_t new_pair_m = group_ballot<NP>(new_pairs != 0u && valid);
+            const uint32_t f35 = group_ballot<NP>(far35), f5 = group_ballot<NP>(far5);
+            kicked = (dw_m | new_pair_m | obst_mask | wall_m | ceil_m) != 0u;             // self_state_update_flag, :549-587
+
+            // episode counters (lane 0 of the env), quadrotor_multi.py:448-456,468-478,522-526
+            const int n_obst = __popc(obst_mask);
+            const bool any_event = col_curr_tick > 0 || n_obst > 0 || ((floor_m | wall_m | ceil_m | room_m) != 0u && settled);
+            if (any_event && i == 0 && env_ok) {
+                int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
+                c[QS_STAT_NUM_COLLISIONS] += col_curr_tick;
+                if (col_curr_tick > 0 && settled) c[QS_STAT_NUM_COLLISIONS_AFTER_SETTLE] += col_curr_tick;
+                if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) c[QS_STAT_NUM_COLLISIONS_FINAL_5S] += col_curr_tick;
+                c[QS_STAT_NUM_COLLISIONS_OBST] += n_obst;
+                if (settled) {
+                    c[QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE] += n_obst;
+                    c[QS_STAT_NUM_COLLISIONS_OBST_3_5] += __popc(f35);
+                    c[QS_STAT_NUM_COLLISIONS_OBST_5] += __popc(f5);
+                    c[QS_STAT_NUM_COLLISIONS_ROOM] += __popc(room_m);
+                    c[QS_STAT_NUM_COLLISIONS_FLOOR] += __popc(floor_m);
+                    c[QS_STAT_NUM_COLLISIONS_WALL] += __popc(wall_m);
+                    c[QS_STAT_NUM_COLLISIONS_CEILING] += __popc(ceil_m);
+                }
+            }
+        }
 
         // rewards, quadrotor_multi.py:499-540
         const float rew_prox = -1.0f * (CONTROL_DT * prox);
@@ -482,39 +634,6 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 if (ctr.tick > len - min(len, 300)) sums.y += dist;
                 sums.z += dist;
                 st.slots[SL_DIST_SUMS * st.a_pad + a] = sums;
-            }
-        }
-
-        // ballots of this step's discrete events.  NB: none of them may sit behind a short-circuit `||` / `&&` whose
-        // left side differs between the envs of a warp.
-        const uint32_t floor_m = group_ballot<NP>(floor_c), wall_m = group_ballot<NP>(wall_c),
-                       ceil_m = group_ballot<NP>(ceil_c), room_m = group_ballot<NP>(room_c);
-        const uint32_t dw_m = p.use_downwash ? group_ballot<NP>(dw_applied) : 0u;
-        const uint32_t new_pair_m = group_ballot<NP>(new_pairs != 0u && valid);
-        const bool kicked = (dw_m | new_pair_m | obst_mask | wall_m | ceil_m) != 0u;     // self_state_update_flag, :549-587
-
-        // episode counters (lane 0 of the env), quadrotor_multi.py:448-456,468-478,522-526
-        {
-            const int n_obst = __popc(obst_mask);
-            const bool any_event = col_curr_tick > 0 || n_obst > 0 || ((floor_m | wall_m | ceil_m | room_m) != 0u && settled);
-            if (__any_sync(0xffffffffu, any_event)) {
-                const uint32_t f35 = group_ballot<NP>(far35), f5 = group_ballot<NP>(far5);
-                if (any_event && i == 0 && env_ok) {
-                    int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
-                    c[QS_STAT_NUM_COLLISIONS] += col_curr_tick;
-                    if (col_curr_tick > 0 && settled) c[QS_STAT_NUM_COLLISIONS_AFTER_SETTLE] += col_curr_tick;
-                    if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) c[QS_STAT_NUM_COLLISIONS_FINAL_5S] += col_curr_tick;
-                    c[QS_STAT_NUM_COLLISIONS_OBST] += n_obst;
-                    if (settled) {
-                        c[QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE] += n_obst;
-                        c[QS_STAT_NUM_COLLISIONS_OBST_3_5] += __popc(f35);
-                        c[QS_STAT_NUM_COLLISIONS_OBST_5] += __popc(f5);
-                        c[QS_STAT_NUM_COLLISIONS_ROOM] += __popc(room_m);
-                        c[QS_STAT_NUM_COLLISIONS_FLOOR] += __popc(floor_m);
-                        c[QS_STAT_NUM_COLLISIONS_WALL] += __popc(wall_m);
-                        c[QS_STAT_NUM_COLLISIONS_CEILING] += __popc(ceil_m);
-                    }
-                }
             }
         }
 
@@ -577,7 +696,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             }
             if (kicked) {
                 s.flags |= QS_FLAG_KICKED;
-                if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR1, i);      // fresh noise for every drone of the env (:598-599)
+                if (!SPLIT && p.sense_noise) nz = sensor_noise(key, SITE_SENSOR1, i);      // fresh noise for every drone of the env (:598-599)
             }
         }
 
@@ -622,13 +741,24 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
                 goal_dirty = true;
-                if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
-                dmin2 = min_pillar_dist2(p, s, s_obst_env);          // new pose, new pillar table
+                if (!SPLIT) {
+                    if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
+                    dmin2 = min_pillar_dist2(p, s, s_obst_env);          // new pose, new pillar table
+                }
             }
+        }
+        if (SPLIT) {
+            // hand-off 2: final velocities / rates (and the whole state after a reset) + per-env flags
+            const uint32_t hf = (kicked ? HF_KICKED : 0u) | (do_reset ? HF_RESET : 0u);
+            if (hf != 0u) hand_store(s_hand, lane, s, nvel);
+            s_hflag[lane] = hf;
+            bar_arrive(2);
         }
 
         // ================= observation (of the post-response, or freshly reset, state) =================
-        if (!p.last_obs_only || t == p.T - 1) {
+        if (SPLIT) {
+            bar_sync(3);                                               // observer is done with this step's hand-off
+        } else if (!p.last_obs_only || t == p.T - 1) {
             float* gbase = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
             if (p.obs_stage) {
                 // rows go to the warp's shared-memory tile, then out with coalesced vector stores

@@ -22,6 +22,7 @@ struct QsHandle {
     DevState st;
     float rew[QS_NUM_REW_COEFF];
     int64_t launches;
+    int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
     // staging for the *_host entry points (pinned host + device mirrors)
     float *d_actions, *d_obs, *d_rewards, *d_terms;
     uint8_t *d_dones, *d_mask;
@@ -222,14 +223,22 @@ static int dispatch_np(int NP, F&& f) {
 }
 
 static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
-    const int kBlock = block_size();
-    const int envs_per_block = kBlock / h->NP;
+    // split kernel: physics warp + observer warp per 32 drones (QS_SPLIT=0/1 at qs_create overrides the heuristic)
+    // Measured (profiles/r01_notes.md): splitting shortens one warp's dependency chain (32 envs: 6.9 -> 5.8 us per
+    // launch, 8 x 1024 envs: 8.05 -> 7.17 us) but adds work, so it only pays while the GPU has idle issue slots, i.e.
+    // up to about one physics warp per SM sub-partition (4 x 148 on B200).
+    StepParams p = p_in;
+    const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
+    const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
+    const bool split = want_split && p.obs_stage && h->NP > 1;
+    const int kBlock = split ? 64 : block_size();
+    const int envs_per_block = (split ? 32 : kBlock) / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
     smem = (smem + 15) / 16 * 16;
-    StepParams p = p_in;
     p.smem_tile_off = (int)(smem / sizeof(float));
-    if (p.obs_stage) smem += (size_t)(kBlock / 32) * 32 * p.obs_dp * sizeof(float);
+    if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
+    if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
     // Programmatic dependent launch (opt-in, QS_PDL=1): measured SLOWER than plain graph edges on this kernel
     // (11.96 vs 9.97 us/step on c3, profiles/r01_notes.md), so it stays off by default.
     static const bool use_pdl = [] { const char* e = getenv("QS_PDL"); return e ? atoi(e) != 0 : false; }();
@@ -241,7 +250,9 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
     cudaError_t lerr = cudaSuccess;
     int rc = dispatch_np(h->NP, [&](auto np) {
-        lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<decltype(np)::value>, p);
+        constexpr int NPv = decltype(np)::value;
+        if (split) lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true>, p);
+        else lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false>, p);
         return QS_OK;
     });
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
@@ -303,6 +314,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     h->D = h->S + 6 * K + (cfg->use_obstacles ? 9 : 0);
     h->ep_len = (int)((double)cfg->ep_time / (0.005 * 2));      // quadrotor_single.py:158
     h->A = (long long)cfg->num_envs * cfg->num_agents;
+    {
+        const char* e = getenv("QS_SPLIT");
+        h->split_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }
     h->a_pad = (h->A + 31) / 32 * 32;
     // QuadrotorEnvMulti defaults, quadrotor_multi.py:91-94
     const float def[QS_NUM_REW_COEFF] = {1.f, 0.05f, 1.f, 1.f, 0.1f, 5.f, 4.f, 5.f};

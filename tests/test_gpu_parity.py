@@ -193,3 +193,26 @@ def test_device_side_o_random_generator_matches_twin():
         assert np.array_equal(obst_dev[e], o.obst_xy.astype(np.float32))
         np.testing.assert_allclose(goals_dev[e], np.array([d.goal for d in o.drones]), rtol=1e-6)
     pair.engine.close()
+
+
+@pytest.mark.parametrize('split', ['0', '1'])
+def test_both_step_kernels_against_oracle(split, monkeypatch):
+    """The single-warp kernel (QS_SPLIT=0) and the physics/observer split kernel (QS_SPLIT=1) are the same function:
+    both must match the oracle on c3 with planted pillar contacts (kicks exercise the observer's re-build path), and
+    their outputs are bit-identical to each other."""
+    import torch
+    from tests.parity_util import Pair
+    monkeypatch.setenv('QS_SPLIT', split)
+    rep = _run(dict(C3, ep_time=0.6), E=6, T=90, seed=1100, hook=_obst_hook(15))
+    assert rep['obstcol'] > 3 and rep['dones'] >= 6
+    outs = []
+    for mode in ('0', '1'):
+        monkeypatch.setenv('QS_SPLIT', mode)
+        pair = Pair(5, dict(C3, ep_time=0.3), seed=77, table_seed=78)
+        pair.engine.reset()
+        g = torch.Generator(device='cuda'); g.manual_seed(3)
+        a = (torch.rand((50, 5, 8, 4), device='cuda', generator=g) * 2 - 1).contiguous()
+        outs.append([x.clone() for x in pair.engine.rollout(a)] + [pair.engine.get_state()['agent_f32'].clone()])
+        pair.engine.close()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
