@@ -91,6 +91,7 @@ struct StepParams {
     // observation staging (coalesced write-out): vector width V, Q = D / V, padded row stride Dp, magic = ceil(2^20 / Q)
     int obs_stage, obs_v, obs_q, obs_dp, obs_magic, smem_tile_off;
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
+    int pdl_mode;                       // 0 off, 1 trigger dependents at kernel start, 2 trigger before the final stores
 };
 
 struct Agent {

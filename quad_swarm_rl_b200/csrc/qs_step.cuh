@@ -312,10 +312,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     const long long a = (long long)env * p.N + i;
     const long long A = (long long)p.E * p.N;
 
-    // Programmatic dependent launch: let the NEXT step's grid start launching while this one runs, and wait here for
-    // the PREVIOUS step's grid to complete (and flush) before touching any state.  Without the launch attribute
-    // both instructions are no-ops.
-    asm volatile("griddepcontrol.launch_dependents;");
+    // Programmatic dependent launch: wait here for the PREVIOUS step's grid to complete (and flush) before touching any
+    // state; the trigger that lets the NEXT step's grid start launching is issued just before this grid's final stores
+    // (mode 2, default: hides ~0.3 us of launch latency per step; triggering at kernel start, mode 1, is 2 us SLOWER
+    // because the early grid competes for issue slots while it spins).  Without the launch attribute both are no-ops.
+    if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             ctr.step_count += 1;
             bar_sync(3);                                              // hand-off arrays and tile are free again
         }
+        if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");
         return;
     }
 
@@ -777,6 +779,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         ctr.step_count += 1;
     }
 
+    if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
     if (valid) store_agent(st, a, s, goal_dirty);
     if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
 }

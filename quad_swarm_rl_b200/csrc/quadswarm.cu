@@ -239,9 +239,11 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     p.smem_tile_off = (int)(smem / sizeof(float));
     if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
     if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
-    // Programmatic dependent launch (opt-in, QS_PDL=1): measured SLOWER than plain graph edges on this kernel
-    // (11.96 vs 9.97 us/step on c3, profiles/r01_notes.md), so it stays off by default.
-    static const bool use_pdl = [] { const char* e = getenv("QS_PDL"); return e ? atoi(e) != 0 : false; }();
+    // Programmatic dependent launch: QS_PDL = 0 off, 1 trigger at kernel start (measured 2 us slower), 2 (default) trigger
+    // before the final stores (measured 0.2-0.4 us faster per step on c3; profiles/r01_notes.md)
+    static const int pdl_mode = [] { const char* e = getenv("QS_PDL"); const int m = e ? atoi(e) : 2; return (m < 0 || m > 2) ? 2 : m; }();
+    const bool use_pdl = pdl_mode != 0;
+    p.pdl_mode = pdl_mode;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute attr[1];

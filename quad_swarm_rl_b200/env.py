@@ -11,6 +11,9 @@ observations / rewards / dones stay on the device as torch tensors (what a batch
 Episode generation (goal formations, spawn points, pillar placement) stays on the host (scenarios.py): the tables of
 the NEXT episode are uploaded one episode ahead, because the device auto-resets inside the step kernel.
 """
+import copy
+from collections import deque
+
 import numpy as np
 import torch
 
@@ -117,6 +120,8 @@ class _EnvBase:
         self.collision_falloff_threshold = collision_falloff_radius * ARM
         self.activate_replay_buffer = False
         self.saved_in_replay_buffer = False
+        self.crashes_in_recent_episodes = deque([], maxlen=100)     # quadrotor_multi.py:174-175
+        self.crashes_last_episode = 0
         self.render_mode = render_mode
         self.scenes = []
         obs_self_size = QUADS_OBS_REPR[obs_repr]             # KeyError on unknown names, as the reference
@@ -181,8 +186,16 @@ class _EnvBase:
         self.engine.set_next_episode(self._next['goals'], self._next['spawn'],
                                      self._next['obst'][:, :self.num_obstacles] if self.use_obstacles else None, env_mask=mask)
 
+    def can_drones_fly(self):
+        """quadrotor_multi.py:281-287: fewer than one floor crash per episode on average over >= 10 episodes."""
+        return abs(np.mean(self.crashes_in_recent_episodes)) < 1 and len(self.crashes_in_recent_episodes) >= 10
+
     def _begin_episodes(self, envs):
         """Host bookkeeping after the device (auto-)reset of `envs`: current scenario <- next, generate the one after."""
+        if self.use_replay_buffer and not self.activate_replay_buffer:          # quadrotor_multi.py:356-359
+            self.crashes_in_recent_episodes.append(self.crashes_last_episode)
+            self.activate_replay_buffer = self.can_drones_fly()
+            self.crashes_last_episode = 0
         if self.device_scenario is not None:          # episodes are generated inside the kernels: only the tick restarts
             self._tick[list(envs)] = 0
             return
@@ -344,10 +357,17 @@ class QuadrotorEnvMulti(_EnvBase):
         # new, which the reference lists but never penalises
         self.last_step_unique_collisions = np.where(self._terms[0, :, L_TERM_RAW_QUADCOL] < 0)[0]
         self.curr_quad_col = np.where(self._terms[0, :, L_TERM_RAW_QUADCOL_OBST] < 0)[0]
+        if self.use_replay_buffer and not self.activate_replay_buffer:          # quadrotor_multi.py:611-612
+            self.crashes_last_episode += infos[0]['rewards']['rew_crash']
         if done:
             stats = self._episode_stats(0, self._scenarios[0].name())
             for i in range(N):
-                infos[i]['episode_extra_stats'] = stats[i]
+                if self.saved_in_replay_buffer:                               # quadrotor_multi.py:629-633
+                    infos[i]['episode_extra_stats'] = {
+                        'num_collisions_replay': stats[i]['num_collisions'],
+                        'num_collisions_obst_replay': stats[i].get('num_collisions_obst_quad', 0)}
+                else:
+                    infos[i]['episode_extra_stats'] = stats[i]
             self._begin_episodes([0])
         else:
             self._scenario_ticks()
@@ -355,6 +375,34 @@ class QuadrotorEnvMulti(_EnvBase):
         rewards = [float(r) for r in self._rew[0]]
         dones = [done] * N
         return obs, rewards, dones, infos
+
+
+    # ---- snapshot / restore: what deepcopy(env) gives the reference's replay wrapper (quad_experience_replay.py:99-104)
+    def snapshot(self):
+        st = self.engine.get_state()
+        return dict(device={k: (v.clone() if v is not None else None) for k, v in st.items()},
+                    scenarios=copy.deepcopy((self._scenarios, self._next_scenarios)), tick=self._tick.copy(),
+                    goals=self._goals.copy(), next={k: v.copy() for k, v in self._next.items()},
+                    obst_density=self.obst_density, saved_in_replay_buffer=True,
+                    activate_replay_buffer=self.activate_replay_buffer)
+
+    def restore(self, snap, zero_collision_counters=False):
+        dev = {k: (v.clone() if v is not None else None) for k, v in snap['device'].items()}
+        if zero_collision_counters:          # quad_experience_replay.py:188-190: accurate per-replay statistics
+            for k in (0, 1, 7, 8):           # QS_STAT_NUM_COLLISIONS, _AFTER_SETTLE, _OBST, _OBST_AFTER_SETTLE
+                dev['env_i32'][:, 4 + k] = 0
+        self.engine.set_state(dev)
+        self._scenarios, self._next_scenarios = copy.deepcopy(snap['scenarios'])
+        for sc in self._scenarios + self._next_scenarios:
+            sc.rng = self._host_rng
+            if hasattr(sc, 'scenario') and sc.scenario is not None:
+                sc.scenario.rng = self._host_rng
+        self._tick = snap['tick'].copy()
+        self._goals = snap['goals'].copy()
+        self._next = {k: v.copy() for k, v in snap['next'].items()}
+        self._push_next()
+        self.obst_density = snap['obst_density']
+        self.saved_in_replay_buffer = snap['saved_in_replay_buffer']
 
 
 class QuadrotorEnvMultiBatched(_EnvBase):

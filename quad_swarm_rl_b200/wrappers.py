@@ -142,9 +142,6 @@ def make_quadrotor_env_multi(cfg, render_mode=None, **kwargs):
     from .env import QuadrotorEnvMulti
     rew_coeff = DEFAULT_QUAD_REWARD_SHAPING['quad_rewards']
     use_replay_buffer = cfg.replay_buffer_sample_prob > 0.0
-    if use_replay_buffer:
-        raise NotImplementedError("the collision-event replay wrapper is not available yet (SURVEY.md §8f-2); "
-                                  "run with --replay_buffer_sample_prob=0")
     if getattr(cfg, 'visualize_v_value', False):
         raise NotImplementedError("V-value visualisation is out of scope")
     env = QuadrotorEnvMulti(
@@ -163,6 +160,13 @@ def make_quadrotor_env_multi(cfg, render_mode=None, **kwargs):
         dyn_sampler_1=None, sense_noise='default', init_random_state=False, render_mode=render_mode,
         device=getattr(cfg, 'quads_device', 0), seed=getattr(cfg, 'seed', None),
     )
+    if use_replay_buffer:                                  # quad_utils.py:67-70
+        from .replay import ExperienceReplayWrapper
+        env = ExperienceReplayWrapper(env, cfg.replay_buffer_sample_prob, cfg.quads_obst_density, cfg.quads_obst_size,
+                                      getattr(cfg, 'quads_domain_random', False), getattr(cfg, 'quads_obst_density_random', False),
+                                      getattr(cfg, 'quads_obst_size_random', False), getattr(cfg, 'quads_obst_density_min', 0.),
+                                      getattr(cfg, 'quads_obst_density_max', 0.), getattr(cfg, 'quads_obst_size_min', 0.),
+                                      getattr(cfg, 'quads_obst_size_max', 0.))
     reward_shaping = copy.deepcopy(DEFAULT_QUAD_REWARD_SHAPING)
     reward_shaping['quad_rewards']['quadcol_bin'] = cfg.quads_collision_reward
     reward_shaping['quad_rewards']['quadcol_bin_smooth_max'] = cfg.quads_collision_smooth_max_penalty

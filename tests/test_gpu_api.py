@@ -204,3 +204,54 @@ def test_batched_env_and_dynamic_scenario():
     assert ended == [450]                                       # ep_len = 450 -> every env ends on its 451st step
     assert not np.array_equal(goals0, env._goals)               # formation centres swapped / new episode
     env.close()
+
+
+def _ref_style_env(**over):
+    from quad_swarm_rl_b200.env import QuadrotorEnvMulti
+    kw = dict(num_agents=8, ep_time=4.0, rew_coeff=None, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=6,
+              neighbor_obs_type='pos_vel', collision_hitbox_radius=2.0, collision_falloff_radius=4.0, use_obstacles=False,
+              obst_density=0.2, obst_size=0.6, obst_spawn_area=[8.0, 8.0], use_downwash=False, use_numba=True,
+              quads_mode='static_same_goal', room_dims=[10., 10., 10.], use_replay_buffer=True, quads_view_mode=['topdown'],
+              quads_render=False, dynamics_params='Crazyflie', raw_control=True, raw_control_zero_middle=True,
+              dynamics_randomize_every=None, dynamics_change=None, dyn_sampler_1=None, sense_noise='default',
+              init_random_state=False, seed=12)
+    kw.update(over)
+    return QuadrotorEnvMulti(**kw)
+
+
+def test_env_snapshot_restore_and_replay_wrapper():
+    """env.snapshot()/restore() (device SoA state + host episode state) replays bit-identically, and the replay wrapper
+    (quad_experience_replay.py semantics) stores the checkpoint taken 1.5 s before a collision and replays it."""
+    from quad_swarm_rl_b200.replay import ExperienceReplayWrapper
+    env = _ref_style_env()
+    env.reset()
+    rs = np.random.RandomState(0)
+    acts = rs.uniform(-1, 1, (40, 8, 4)).astype(np.float32)
+    for t in range(10):
+        env.step(acts[t])
+    snap = env.snapshot()
+    first = [env.step(acts[t])[0].copy() for t in range(10, 40)]
+    env.restore(snap)
+    assert env.envs[0].tick == 10
+    for t, ref in zip(range(10, 40), first):
+        assert np.array_equal(env.step(acts[t])[0], ref)
+    env.close()
+
+    env = _ref_style_env(ep_time=4.0)
+    w = ExperienceReplayWrapper(env, 1.0, 0.2, 0.6)
+    w.reset()
+    env.activate_replay_buffer = True                 # as if the drones had already learnt to fly
+    ended = 0
+    for t in range(420):
+        if t == 320:                                  # plant a collision: all drones on top of each other
+            st = env.engine.get_state()
+            st['agent_f32'][0, :, 0:3] = torch.tensor([0.3, 0.2, 2.0], device='cuda') + 0.01 * torch.arange(8, device='cuda')[:, None]
+            env.engine.set_state(st)
+        obs, rew, dones, infos = w.step(rs.uniform(-1, 1, (8, 4)).astype(np.float32))
+        if dones[0]:
+            ended += 1
+            assert infos[0]['episode_extra_stats']['replay/replay_buffer_size'] == 1
+            assert set(infos[0]['episode_extra_stats']) >= {'num_collisions_replay', 'replay/replay_rate'}
+            assert env.envs[0].tick == 200            # replayed from the checkpoint 1.5 s before tick 321
+    assert ended == 1 and env.saved_in_replay_buffer and len(w.replay_buffer) == 1 and w.replayed_events == 1
+    env.close()

@@ -113,11 +113,68 @@ def test_reward_shaping_annealing_and_true_reward():
 
 
 def test_factory_rejects_what_is_out_of_scope():
-    cfg = types.SimpleNamespace(replay_buffer_sample_prob=0.75)
+    cfg = types.SimpleNamespace(replay_buffer_sample_prob=0.0, visualize_v_value=True)
     with pytest.raises(NotImplementedError):
         wr.make_quadrotor_env('quadrotor_multi', cfg=cfg)
     with pytest.raises(NotImplementedError):
         wr.make_quadrotor_env('quadrotor_single', cfg=cfg)
+
+
+class _FakeReplayEnv(_FakeEnv):
+    """Adds what ExperienceReplayWrapper reads (quad_experience_replay.py:71,140-151,183-188)."""
+    use_replay_buffer = True
+    use_obstacles = False
+    collisions_grace_period_seconds = 1.5
+    obst_density = 0.2
+
+    def __init__(self):
+        super().__init__()
+        self.activate_replay_buffer = True
+        self.saved_in_replay_buffer = False
+        self.tick = 0
+        self.envs = [types.SimpleNamespace(control_freq=100.0)]
+        self.last_step_unique_collisions = np.array([], dtype=int)
+        self.curr_quad_col = []
+        self.restored = []
+
+    def reset(self, obst_density=None, obst_size=None):
+        self.tick = 0
+        return np.zeros((2, 3))
+
+    def step(self, action):
+        self.tick += 1
+        self.envs[0].tick = self.tick
+        done = self.tick >= 400
+        self.last_step_unique_collisions = np.array([1, 2]) if self.tick == 320 else np.array([], dtype=int)
+        infos = [{'rewards': {}} for _ in range(2)]
+        if done:
+            self.tick = 0
+            self.envs[0].tick = 0
+        return np.full((2, 3), float(self.tick)), [0., 0.], [done, done], infos
+
+    def snapshot(self):
+        return {'tick': self.tick}
+
+    def restore(self, snap, zero_collision_counters=False):
+        self.restored.append(snap['tick'])
+        self.tick = snap['tick']
+        self.saved_in_replay_buffer = True
+
+
+def test_replay_wrapper_saves_the_checkpoint_from_1_5_s_before_a_collision():
+    from quad_swarm_rl_b200.replay import ExperienceReplayWrapper
+    env = _FakeReplayEnv()
+    w = ExperienceReplayWrapper(env, 1.0, 0.2, 0.6)
+    w.reset()
+    for t in range(400):
+        obs, rew, dones, infos = w.step(None)
+    assert env.saved_in_replay_buffer and len(w.replay_buffer) == 1
+    # collision at tick 320; checkpoints every 50 ticks -> [..., 200, 250, 300]; 1.5 s = 3 checkpoints back -> tick 200
+    assert w.replay_buffer.buffer[0].snapshot == {'tick': 200}
+    assert dones[0] and env.restored == [200] and w.replayed_events == 1
+    assert obs[0, 0] == 200.0                                          # the observation stored with that checkpoint
+    st = infos[0]['episode_extra_stats']
+    assert st['replay/replay_rate'] == 1.0 and st['replay/replay_buffer_size'] == 1
 
 
 def test_svd_period_is_100_substeps():
