@@ -280,14 +280,18 @@ def run_cuda_arm(args):
         counter[0] = k + 1
 
     # CUDA graph of G consecutive steps (G divides both rings' periods so replays stay consistent)
-    G = max(R_act, R_obs)          # both are powers of two: ring indices baked into the graph stay periodic
+    # graph of G consecutive steps; G is a power of two (ring indices baked into the graph stay periodic) and no larger
+    # than the number of timed steps, so that short runs are still graph-replayed
+    G = max(R_act, R_obs)
+    while G > max(1, args.steps):
+        G //= 2
     stream = torch.cuda.Stream(device=dev)
     graph = None
     with torch.cuda.stream(stream):
         for _ in range(3):
             one_step()
         stream.synchronize()
-        if not args.no_graph:
+        if not args.no_graph and G >= 4:
             counter[0] = 0
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
@@ -369,22 +373,57 @@ def run_cuda_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    # ---- optional: T steps per launch (qs_rollout), reported as an extra
+    # ---- extras (rank 0, single GPU): the same kernel (a) T steps per launch (qs_rollout: env block stays in registers,
+    #      every observation still written) and (b) at a 4x larger batch, where the GPU has enough warps to fill its
+    #      issue slots.  They explain the headline (which is latency-bound at 1.7 warps per SM sub-partition); they are
+    #      not the headline.
     extra = {}
-    if args.rollout > 0 and rank == 0:
-        T = args.rollout
-        acts = act_ring[:T] if R_act >= T else act_ring.repeat((T + R_act - 1) // R_act, 1, 1, 1)[:T].contiguous()
-        o, r, d_ = eng.rollout(acts, last_obs_only=True)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 5
-        for _ in range(reps):
-            eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_, last_obs_only=True)
-        e1.record()
-        torch.cuda.synchronize()
-        extra['rollout'] = {'steps_per_launch': T, 'agent_steps_per_s': A * T * reps / (e0.elapsed_time(e1) * 1e-3),
-                            'note': 'qs_rollout: T control steps per launch, last observation only'}
+    if rank == 0 and world == 1 and not args.no_extras:
+        def _events(fn, reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); [fn() for _ in range(reps)]; e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / reps
+        T = 64
+        acts = act_ring[:T].contiguous()
+        o = torch.empty((T, E, N, D), device=dev); r = torch.empty((T, E, N), device=dev)
+        d_ = torch.empty((T, E, N), dtype=torch.uint8, device=dev)
+        eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_)
+        sec = _events(lambda: eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_), 8)
+        b_alg_ = 292 + 4 * D + (8.0 * M / N if M else 0.0)
+        extra['rollout'] = {'steps_per_launch': T, 'us_per_step': sec / T * 1e6, 'agent_steps_per_s': A * T / sec,
+                            'roofline_frac': b_alg_ * A * T / sec / 1e9 / hbm_peak()[0],
+                            'note': 'qs_rollout: T control steps per launch, all observations written'}
+        del o, r, d_
+        E4 = 4 * E
+        big = QuadSwarmEngine(num_envs=E4, seed=args.seed, device=local_rank, rew_coeff=cfg['rew'], ep_time=args.ep_time,
+                              device_scenario=dev_scn, **kw)
+        if dev_scn is None:
+            g4, s4, o4 = make_episode_tables(cfg, min(E4, 512), seed=77)
+            rep = E4 // min(E4, 512)
+            big.set_next_episode(np.tile(g4, (rep, 1, 1)), np.tile(s4, (rep, 1, 1)), None if o4 is None else np.tile(o4, (rep, 1, 1)))
+        big.reset()
+        Rb = 8
+        ab = (torch.rand((Rb, E4, N, 4), device=dev) * 2 - 1).contiguous()
+        ob = torch.empty((Rb, E4, N, D), device=dev); rb = torch.empty((Rb, E4, N), device=dev)
+        db = torch.empty((Rb, E4, N), dtype=torch.uint8, device=dev)
+        st2 = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st2):
+            for k in range(Rb):
+                big.step(ab[k], obs_out=ob[k], rewards_out=rb[k], dones_out=db[k])
+            st2.synchronize()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=st2):
+                for k in range(Rb):
+                    big.step(ab[k], obs_out=ob[k], rewards_out=rb[k], dones_out=db[k])
+            gb.replay(); st2.synchronize()
+            sec = _events(gb.replay, 40) / Rb
+        extra['large_batch'] = {'envs': E4, 'agents': E4 * N, 'us_per_step': sec * 1e6, 'agent_steps_per_s': E4 * N / sec,
+                                'roofline_frac': b_alg_ * E4 * N / sec / 1e9 / hbm_peak()[0],
+                                'note': 'same kernel, one launch per control step, 4x the envs of the headline workload'}
+        big.close()
+        del ab, ob, rb, db
 
     if rank == 0:
         value = world * A * args.steps / (ms * 1e-3)
@@ -433,7 +472,7 @@ def main():
     ap.add_argument('--ep-time', type=float, default=15.0)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=300)
-    ap.add_argument('--rollout', type=int, default=0, help='also time qs_rollout with this many steps per launch')
+    ap.add_argument('--no-extras', action='store_true', help='skip the rollout / large-batch explanatory measurements')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--host-tables', action='store_true', help='use host-generated episode tables even where a device generator exists')
     ap.add_argument('--no-cpu-baseline', action='store_true')
