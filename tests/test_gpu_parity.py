@@ -216,3 +216,46 @@ def test_both_step_kernels_against_oracle(split, monkeypatch):
         pair.engine.close()
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+def test_wide_observation_unstaged_path_32_drones_all_neighbours():
+    """N = 32 with all 31 neighbours observed: D = 18 + 186 = 204 floats, too wide for the shared-memory staging tile,
+    so rows are written straight to global memory (and the split kernel is not used)."""
+    rep = _run(dict(num_agents=32, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega', ep_time=0.3), E=2, T=40, seed=1200)
+    assert rep['dones'] >= 2
+
+
+def test_dense_pillars_more_than_32_and_no_sensor_noise():
+    """density 0.8 -> 51 pillars per env: exercises the tail scan of the SDF pass beyond the 32-bit candidate mask and
+    many simultaneous pillar contacts; sense_noise=None bypasses the sensor noise (SensorNoise(bypass=True))."""
+    kw = dict(num_agents=4, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, obst_density=0.8,
+              use_downwash=False, ep_time=0.5, sense_noise=None)
+    from tests import parity_util as pu
+    import types
+
+    def dense_tables(rs, E, N, M, use_obst, episodes=3, spread=1.5):
+        cells = pu.qo.get_cell_centers(8, 8)
+        eps = []
+        for _ in range(episodes):
+            goals = rs.uniform(-3, 3, (E, N, 3)).astype(np.float32); goals[..., 2] = rs.uniform(1, 3, (E, N))
+            spawn = np.zeros((E, N, 3), np.float32); obst = np.zeros((E, M, 2), np.float32)
+            for e in range(E):
+                idx = rs.permutation(64)
+                obst[e] = cells[idx[:M]]
+                spawn[e, :, :2] = cells[idx[M:M + N]]
+                spawn[e, :, 2] = rs.uniform(1.0, 3.0, N)
+            eps.append(dict(goals=goals, spawn=spawn, obst=obst))
+        return eps
+
+    orig = pu.make_tables
+    pu.make_tables = dense_tables
+    try:
+        rep = _run(kw, E=6, T=110, seed=1300)
+    finally:
+        pu.make_tables = orig
+    assert rep['dones'] >= 6
+
+
+def test_two_drones_one_env_minimal():
+    """smallest multi-drone case: E = 1, N = 2, K = 1 (all neighbours)."""
+    _run(dict(num_agents=2, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega', ep_time=0.4), E=1, T=60, seed=1400)
