@@ -565,7 +565,7 @@ __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int i, int n
         mask |= 1ull << c;
         if ((m % stride) == lane_i) {
             const float2 xy = cell_center(c, L, W);
-            obst_smem[m] = xy;
+            if (obst_smem != nullptr) obst_smem[m] = xy;
             obst_glob[m] = xy;
         }
     }

@@ -39,7 +39,7 @@ __device__ __forceinline__ float min_pillar_dist2(const StepParams& p, const Age
 // (see flush_observation_tile).
 // Hand-off arrays of the split (physics warp -> observer warp) kernel: 24 arrays of 32 floats in shared memory.
 enum Hand { H_PX = 0, H_PY, H_PZ, H_VX, H_VY, H_VZ, H_NVX, H_NVY, H_NVZ, H_R0, H_OX = H_R0 + 9, H_OY, H_OZ, H_GX, H_GY, H_GZ, H_COUNT };
-constexpr int HAND_FLOATS = H_COUNT * 32 + 32;          // + one flag word per lane slot
+constexpr int HAND_FLOATS = 2 * H_COUNT * 32 + 32;      // post-integration buffer, final-state buffer, one flag word per lane
 constexpr uint32_t HF_KICKED = 1u, HF_RESET = 2u;
 
 // value of drone j of my env: from the hand-off arrays (SM) or by warp shuffle from the lane that owns it
@@ -256,7 +256,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
             for (int m = i; m < p.M; m += NP) {
                 const float2 ob = st.next_obst[(long long)env * p.M + m];
                 st.obst[(long long)env * p.M + m] = ob;
-                s_obst_env[m] = ob;
+                if (s_obst_env != nullptr) s_obst_env[m] = ob;
             }
         }
         __syncwarp();
@@ -266,9 +266,14 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
 #ifndef QS_LB
 #define QS_LB 128
 #endif
-// named barriers of the split kernel (physics warp <-> observer warp, 64 threads)
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// named barriers of the split kernel (physics warp <-> observer warp, 64 threads).  Both warps use bar.sync: the
+// observer reaches barrier 1 first, the physics warp reaches barrier 2 first and has only its stores left to do.
+// Out of line on purpose: both warps then execute the SAME bar.sync instruction (what compute-sanitizer's synccheck
+// expects of a CTA-wide barrier), and the call boundary keeps the compiler from moving shared-memory traffic across it.
+__device__ __noinline__ void bar_sync(int id) {
+    __syncwarp();          // bar.sync is warp-aligned: lanes that diverged in the preceding code must reconverge first
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 
 // physics warp -> shared hand-off arrays
 __device__ __forceinline__ void hand_store(float* hand, int lane, const Agent& s, const float nvel[3]) {
@@ -323,7 +328,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     float2* s_obst_env = s_obst + env_local * p.M;
     float* s_tile = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + (SPLIT ? 0 : (threadIdx.x >> 5)) * (32 * p.obs_dp);
     float* s_hand = reinterpret_cast<float*>(s_obst) + p.smem_tile_off + 32 * p.obs_dp;      // SPLIT only
-    uint32_t* s_hflag = reinterpret_cast<uint32_t*>(s_hand + 32 * H_COUNT);
+    float* s_hand2 = s_hand + 32 * H_COUNT;                                                  // final state after a response / reset
+    uint32_t* s_hflag = reinterpret_cast<uint32_t*>(s_hand2 + 32 * H_COUNT);
 
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
@@ -386,11 +392,19 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             }
             bar_sync(2);                                              // final state + flags
             const uint32_t hf = s_hflag[gbase];
+            if (p.use_obst && __any_sync(0xffffffffu, (hf & HF_RESET) != 0u)) {
+                // a reset replaced this env's pillars: the physics warp wrote them to global memory only, the observer
+                // refreshes the shared-memory table (the physics warp reads it again only after barrier 3)
+                if (hf & HF_RESET) {
+                    for (int m = i; m < p.M; m += NP) s_obst_env[m] = st.obst[(long long)env * p.M + m];
+                }
+                __syncwarp();
+            }
             if (want && hf != 0u) {                                   // contact response or reset: rebuild the rows of this env
-                hand_load(s_hand, lane, o, nvel);
+                hand_load(s_hand2, lane, o, nvel);
                 if (p.sense_noise) nz = sensor_noise(key, (hf & HF_RESET) ? SITE_SENSOR_RESET : SITE_SENSOR1, i);
                 const float dmin2 = p.use_obst ? min_pillar_dist2(p, o, s_obst_env) : 1e4f;
-                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand, gbase);
+                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand2, gbase);
             }
             if (want) {
                 __syncwarp();
@@ -465,7 +479,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         }
         if (SPLIT) {                                                   // positions are final from here on
             hand_store(s_hand, lane, s, s.vel);
-            bar_arrive(1);
+            bar_sync(1);
         }
         // compute_reward_weighted, quadrotor_single.py:34-92 (dt = SIM dt, raw unclipped action)
         const bool on_floor = (s.flags & QS_FLAG_ON_FLOOR) != 0u;
@@ -738,7 +752,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = c[k]; c[k] = 0; }
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
             }
-            reset_env<NP>(p, key, s, a, env, i, do_reset, valid, ctr.tick, s_obst_env, nvel);
+            reset_env<NP>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel);
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -752,9 +766,9 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         if (SPLIT) {
             // hand-off 2: final velocities / rates (and the whole state after a reset) + per-env flags
             const uint32_t hf = (kicked ? HF_KICKED : 0u) | (do_reset ? HF_RESET : 0u);
-            if (hf != 0u) hand_store(s_hand, lane, s, nvel);
+            if (hf != 0u) hand_store(s_hand2, lane, s, nvel);
             s_hflag[lane] = hf;
-            bar_arrive(2);
+            bar_sync(2);
         }
 
         // ================= observation (of the post-response, or freshly reset, state) =================
