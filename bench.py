@@ -247,10 +247,10 @@ def run_cuda_arm(args):
     E = args.envs or cfg['E']
     kw = cfg['kw']
     N = kw['num_agents']
-    # o_random episodes (pillars, spawn and goal cells) are re-drawn ON THE DEVICE at every auto-reset; the other
-    # scenarios use host-generated tables uploaded once (static_same_goal is static by definition; swarm_vs_swarm's
-    # timed goal swaps are host-driven in env.py and not part of this loop)
-    dev_scn = 'o_random' if (cfg['mode'] == 'o_random' and not args.host_tables) else None
+    # Episodes are generated ON THE DEVICE inside the reset path of the kernels (o_random: pillars, spawn and goal cells;
+    # static_same_goal / swarm_vs_swarm: goal formations), and swarm_vs_swarm's goal swaps every 4-6 s happen inside the
+    # step kernel: no host work per episode or per tick.  --host-tables uploads host-generated tables once instead.
+    dev_scn = None if args.host_tables else cfg['mode']
     # Optional (--groups G > 1): the E envs of this GPU are stepped as G independent blocks, each with its own chain of
     # kernel launches and no edge between the chains (double-buffered sampling, as Sample Factory runs its rollout
     # workers).  Every env still advances one control step per bench step; results do not depend on the grouping (global

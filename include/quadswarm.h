@@ -46,6 +46,20 @@ extern "C" {
  *                needs use_obstacles.  No host work per episode. */
 #define QS_SCENARIO_HOST_TABLES 0
 #define QS_SCENARIO_O_RANDOM 1
+/* The obstacle-free scenario family, generated and TICKED on the device (formation picks, goal formations, the timed
+ * goal switches every 4-6 s, per-tick goal motion; `mix` draws one of the eight per episode; scenarios/base.py:39-150,
+ * dynamic_same_goal.py, dynamic_diff_goal.py, swap_goals.py, dynamic_formations.py, ep_lissajous3D.py,
+ * swarm_vs_swarm.py, mix.py:37-93).  They need use_obstacles = 0.  The ids 2..9 are contiguous on purpose. */
+#define QS_SCENARIO_STATIC_SAME_GOAL 2
+#define QS_SCENARIO_STATIC_DIFF_GOAL 3
+#define QS_SCENARIO_DYNAMIC_SAME_GOAL 4
+#define QS_SCENARIO_DYNAMIC_DIFF_GOAL 5
+#define QS_SCENARIO_SWAP_GOALS 6
+#define QS_SCENARIO_DYNAMIC_FORMATIONS 7
+#define QS_SCENARIO_EP_LISSAJOUS3D 8
+#define QS_SCENARIO_SWARM_VS_SWARM 9
+#define QS_SCENARIO_MIX 10
+#define QS_SCENARIO_DEVICE_FAMILY_FIRST QS_SCENARIO_STATIC_SAME_GOAL
 
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a
  * non-zero default or a CLI override (swarm_rl/env_wrappers/reward_shaping.py:7-16). */
@@ -76,6 +90,7 @@ enum {
     QS_STAT_NUM_COLLISIONS_ROOM, QS_STAT_NUM_COLLISIONS_FLOOR, QS_STAT_NUM_COLLISIONS_WALL,
     QS_STAT_NUM_COLLISIONS_CEILING, QS_STAT_NUM_COLLISIONS_OBST, QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE,
     QS_STAT_NUM_COLLISIONS_OBST_3_5, QS_STAT_NUM_COLLISIONS_OBST_5, QS_STAT_EPISODES_DONE,
+    QS_STAT_SCENARIO,        /* QS_SCENARIO_* of the episode that ended (for `mix`: the scenario drawn for it) */
     QS_NUM_ENV_STATS
 };
 /* per-agent episode statistics latched with them */
@@ -163,10 +178,12 @@ int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, float* obs_
  * and what parity tests use for teacher forcing.  agent_f32_dev [E,N,QS_STATE_F32]: pos3 vel3 rot9(row-major)
  * omega3 thrust_rot_damp4 thrust_cmds_damp4 ou4 goal3 dist_ring4 dist_sums3 stale_vel3;
  * agent_u32_dev [E,N,QS_STATE_U32]: flags, prev_collision_row, 0, 0;
- * env_i32_dev [E,QS_STATE_ENV_I32]: tick, step_count, svd_count, episode_idx, then the QS_STAT_* counters. */
+ * env_i32_dev [E,QS_STATE_ENV_I32]: tick, step_count, svd_count, episode_idx, the QS_NUM_ENV_STATS running counters,
+ * then the device-side scenario state (4 ints: scenario, period, next event tick, formation | growing << 8; 12 floats as
+ * bit patterns: formation size, layer distance, largest size, speed, centre 1 xyz_, centre 2 xyz_). */
 #define QS_STATE_F32 43
 #define QS_STATE_U32 4
-#define QS_STATE_ENV_I32 16
+#define QS_STATE_ENV_I32 36
 int qs_get_state(QsHandle* h, float* agent_f32_dev, uint32_t* agent_u32_dev, int32_t* env_i32_dev,
                  float* obst_xy_dev, void* stream);
 int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f32_dev, const uint32_t* agent_u32_dev,

@@ -74,3 +74,237 @@ class DeviceORandomSource:
 
     def step(self, env, tick):
         return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Obstacle-free scenario family (twin of quad_swarm_rl_b200/csrc/qs_scenario.cuh; reference: scenarios/base.py:39-150,
+# utils.py:24-175, dynamic_same_goal.py, dynamic_diff_goal.py, swap_goals.py, dynamic_formations.py,
+# ep_lissajous3D.py, swarm_vs_swarm.py, mix.py:37-93).  float64; the draws and every integer decision are the kernels'.
+# ------------------------------------------------------------------------------------------------------------------
+STATIC_SAME_GOAL, STATIC_DIFF_GOAL, DYNAMIC_SAME_GOAL, DYNAMIC_DIFF_GOAL, SWAP_GOALS, DYNAMIC_FORMATIONS, \
+    EP_LISSAJOUS3D, SWARM_VS_SWARM, MIX = range(2, 11)
+MODE_NAMES = {STATIC_SAME_GOAL: 'static_same_goal', STATIC_DIFF_GOAL: 'static_diff_goal',
+              DYNAMIC_SAME_GOAL: 'dynamic_same_goal', DYNAMIC_DIFF_GOAL: 'dynamic_diff_goal', SWAP_GOALS: 'swap_goals',
+              DYNAMIC_FORMATIONS: 'dynamic_formations', EP_LISSAJOUS3D: 'ep_lissajous3D',
+              SWARM_VS_SWARM: 'swarm_vs_swarm', MIX: 'mix'}
+MODE_IDS = {v: k for k, v in MODE_NAMES.items()}
+FORMATION_NAMES = ('circle_horizontal', 'circle_vertical_xz', 'circle_vertical_yz', 'sphere',
+                   'grid_horizontal', 'grid_vertical_xz', 'grid_vertical_yz', 'cube')          # utils.py:24-25
+
+SV_MIX, SV_PERIOD, SV_FORMATION, SV_SIZE, SV_LAYER, SV_CX, SV_CY, SV_CZ, SV_DIST, SV_PHI, SV_THETA, SV_GROW, SV_SPEED = range(13)
+SV_SHUFFLE = 16
+STREAM_RESET, STREAM_TICK = 1, 2
+NEVER = 0x7fffffff
+BOX = 2.0
+CONTROL_FREQ = 100.0
+
+
+def _u24(draws, stream, v):
+    return int(draws.uniform(px.SITE_SCENARIO_U, 0, stream, v) * 16777216.0)
+
+
+def _u(draws, stream, v):
+    return draws.uniform(px.SITE_SCENARIO_U, 0, stream, v)
+
+
+def _pk(draws, stream, v, n):
+    return (_u24(draws, stream, v) * n) >> 24
+
+
+def grid_dims(num):
+    d1 = int(np.floor(np.sqrt(num)))
+    while d1 > 1 and num % d1 != 0:
+        d1 -= 1
+    d1 = max(d1, 1)
+    return d1, num // d1
+
+
+def _place(plane, a, b, l):
+    return np.array([[a, b, l], [a, l, b], [l, a, b]][plane], dtype=np.float64)
+
+
+def per_layer_of(f):
+    return 50 if 4 <= f <= 6 else 8
+
+
+def formation_raw(f, n, k, size, layer_dist, per_layer):
+    if f <= 2:
+        layer = k // per_layer
+        m = (per_layer if layer < n // per_layer else n % per_layer) if n > per_layer else n
+        ang = 2.0 * np.pi * (k % m) / m
+        return _place(f, size * np.cos(ang), size * np.sin(ang), layer * layer_dist)
+    if f == 3:
+        nn = float(max(n, 3))
+        x = 0.1 + 1.2 * nn
+        start = -1.0 + 1.0 / (nn - 1.0)
+        inc = (2.0 - 2.0 / (nn - 1.0)) / (nn - 1.0)
+        s = start + inc * k
+        lon = s * x
+        lat = 0.5 * np.pi * np.sign(s) * (1.0 - np.sqrt(1.0 - abs(s)))
+        return size * np.array([np.cos(lon) * np.cos(lat), np.sin(lon) * np.cos(lat), np.sin(lat)])
+    if f <= 6:
+        layer = k // per_layer
+        nl = n if n <= per_layer else (per_layer if layer < n // per_layer else n % per_layer)
+        d1, d2 = grid_dims(nl)
+        return _place(f - 4, size * (k % d2), size * ((k // d2) % d1), layer * layer_dist)
+    side = int(np.power(n, 1.0 / 3))                      # base.py:98-99 (27 -> 2: the cube root rounds below 3)
+    return np.array([size * (k // (side * side)), size * ((k // side) % side), size * (k % side)], dtype=np.float64)
+
+
+def formation_point(f, n, k, size, c, layer_dist, per_layer):
+    r = formation_raw(f, n, k, size, layer_dist, per_layer)
+    if f >= 4:
+        r = r - np.mean([formation_raw(f, n, q, size, layer_dist, per_layer) for q in range(n)], axis=0)
+    return r + np.asarray(c, dtype=np.float64)
+
+
+def pick_formation(draws, stream, mode, n):
+    count, low, high = 8, 0.25, 0.5
+    if mode in (STATIC_SAME_GOAL, DYNAMIC_SAME_GOAL, EP_LISSAJOUS3D):
+        count, low, high = 1, 0.0, 0.0
+    elif mode == SWAP_GOALS:
+        low, high = 0.4, 0.8
+    elif mode == DYNAMIC_FORMATIONS:
+        low, high = 0.0, 1.0
+    f = _pk(draws, stream, SV_FORMATION, count) if count > 1 else 0
+    per_layer = per_layer_of(f)
+    if f <= 2:
+        inv = 0.5 / np.sin(np.pi / per_layer)
+        lo, hi = low * inv, high * inv
+    elif f == 3:
+        A, B, C, D = 1.75388487222762, 0.860487305801679, 10.3632729642351, 0.0920858134405214
+        inv = 1.0 / ((A - D) / (1.0 + (n / C) ** B) + D)
+        lo, hi = low * inv, high * inv
+    else:
+        lo, hi = low, high
+    size = lo + (hi - lo) * _u(draws, stream, SV_SIZE)
+    layer = lo + (hi - lo) * _u(draws, stream, SV_LAYER)
+    return dict(f=f, per_layer=per_layer, lo=lo, hi=hi, size=size, layer=layer)
+
+
+def z_above_ground(u, num_agents, per_layer, f, size):
+    z = (-0.5 * BOX + BOX * u) + 2.0
+    lower = 0.25
+    if 1 <= f <= 3:
+        lower = size + 0.25
+    elif f in (5, 6):
+        lower = grid_dims(min(num_agents, per_layer))[0] * size + 0.25
+    return max(lower, z)
+
+
+def shuffle_rank(draws, stream, i, g0, g1):
+    ui = _u24(draws, stream, SV_SHUFFLE + i)
+    r = 0
+    for j in range(g0, g1):
+        uj = _u24(draws, stream, SV_SHUFFLE + j)
+        r += 1 if (uj < ui or (uj == ui and j < i)) else 0
+    return r
+
+
+class DeviceScenarioSource:
+    """Episode source for OracleEnv that mirrors the device-side scenario family (needs a PhiloxRng).  `mode` is a
+    QS_SCENARIO_* id (2..10) or its reference name."""
+
+    approch_goal_metric = 0.5
+
+    def __init__(self, mode):
+        self.cfg_mode = MODE_IDS[mode] if isinstance(mode, str) else int(mode)
+        self.s = None
+        self.events = 0                 # goal events so far (tests)
+
+    def name(self):
+        return 'Scenario_' + MODE_NAMES[self.s['mode'] if self.s else self.cfg_mode]
+
+    def _svs_goal(self, N, k):
+        s = self.s
+        h = N // 2
+        if k < h:
+            return formation_point(s['f'], h, k, s['size'], s['c1'], s['layer'], per_layer_of(s['f']))
+        return formation_point(s['f'], N - h, k - h, s['size'], s['c2'], s['layer'], per_layer_of(s['f']))
+
+    def reset(self, env):
+        d, N = env.rng.draws, env.num_agents
+        mode = self.cfg_mode
+        if mode == MIX:
+            if N == 1:
+                mode = (STATIC_SAME_GOAL, STATIC_DIFF_GOAL, EP_LISSAJOUS3D, DYNAMIC_SAME_GOAL)[_pk(d, STREAM_RESET, SV_MIX, 4)]
+            else:
+                mode = STATIC_SAME_GOAL + _pk(d, STREAM_RESET, SV_MIX, 8)
+        svs = mode == SWARM_VS_SWARM
+        fm = pick_formation(d, STREAM_RESET, mode, N // 2 if svs else N)
+        s = dict(mode=mode, period=0, next=NEVER, growing=0, speed=0.0, f=fm['f'], size=fm['size'], layer=fm['layer'],
+                 hi=fm['hi'], c1=np.array([0.0, 0.0, 2.0]), c2=np.array([0.0, 0.0, 2.0]))
+        self.s = s
+        if mode in (DYNAMIC_SAME_GOAL, DYNAMIC_DIFF_GOAL, SWAP_GOALS, SWARM_VS_SWARM):
+            s['period'] = 400 + _pk(d, STREAM_RESET, SV_PERIOD, 200)
+            s['next'] = s['period']
+        if svs:
+            c1 = np.array([-BOX + 2.0 * BOX * _u(d, STREAM_RESET, SV_CX), -BOX + 2.0 * BOX * _u(d, STREAM_RESET, SV_CY),
+                           z_above_ground(_u(d, STREAM_RESET, SV_CZ), N, fm['per_layer'], fm['f'], fm['size'])])
+            dist = 0.25 * BOX + (BOX - 0.25 * BOX) * _u(d, STREAM_RESET, SV_DIST)
+            phi = -np.pi + 2.0 * np.pi * _u(d, STREAM_RESET, SV_PHI)
+            theta = -0.5 * np.pi + np.pi * _u(d, STREAM_RESET, SV_THETA)
+            c2 = c1 + dist * np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+            plane = fm['f'] if fm['f'] <= 2 else (fm['f'] - 4 if 4 <= fm['f'] <= 6 else -1)
+            if plane >= 0:
+                ax = (2, 1, 0)[plane]
+                diff = c2[ax] - c1[ax]
+                if abs(diff) < fm['lo']:
+                    c2[ax] = np.sign(diff) * fm['lo'] + c1[ax]
+            s['c1'], s['c2'] = c1, c2
+            goals = np.array([self._svs_goal(N, i) for i in range(N)])
+        elif mode == EP_LISSAJOUS3D:
+            s['c1'] = np.array([-2.0, 0.0, 2.0])
+            s['period'], s['next'] = 1, 1
+            goals = np.tile(s['c1'], (N, 1))
+        else:
+            if mode == DYNAMIC_FORMATIONS:
+                s['growing'] = 1 if _u24(d, STREAM_RESET, SV_GROW) < (1 << 23) else 0
+                s['speed'] = 1.0 + 2.0 * _u(d, STREAM_RESET, SV_SPEED)
+                s['period'], s['next'] = 1, 1
+            goals = np.array([formation_point(s['f'], N, shuffle_rank(d, STREAM_RESET, i, 0, N), s['size'], s['c1'],
+                                              s['layer'], fm['per_layer']) for i in range(N)])
+        self.goals = goals
+        return goals, None, None
+
+    def step(self, env, tick):
+        s = self.s
+        if s is None or tick != s['next']:
+            return None
+        d, N = env.rng.draws, env.num_agents
+        mode = s['mode']
+        g = self.goals
+        if mode == SWAP_GOALS:
+            g = np.array([g[shuffle_rank(d, STREAM_TICK, i, 0, N)] for i in range(N)])
+        elif mode == DYNAMIC_SAME_GOAL:
+            s['c1'] = np.array([-BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CX), -BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CY),
+                                max(0.25, (-0.5 * BOX + BOX * _u(d, STREAM_TICK, SV_CZ)) + 2.0)])
+            g = np.array([formation_point(s['f'], N, i, s['size'], s['c1'], 0.0, per_layer_of(s['f'])) for i in range(N)])
+        elif mode == DYNAMIC_DIFF_GOAL:
+            s['c1'] = np.array([-BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CX), -BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CY),
+                                z_above_ground(_u(d, STREAM_TICK, SV_CZ), N, per_layer_of(s['f']), s['f'], s['size'])])
+            fm = pick_formation(d, STREAM_TICK, mode, N)
+            s.update(f=fm['f'], size=fm['size'], layer=fm['layer'], hi=fm['hi'])
+            g = np.array([formation_point(s['f'], N, shuffle_rank(d, STREAM_TICK, i, 0, N), s['size'], s['c1'], s['layer'],
+                                          fm['per_layer']) for i in range(N)])
+        elif mode == DYNAMIC_FORMATIONS:
+            if s['size'] <= -s['hi']:
+                s['growing'], s['speed'] = 1, 1.0 + 2.0 * _u(d, STREAM_TICK, SV_SPEED)
+            elif s['size'] >= s['hi']:
+                s['growing'], s['speed'] = 0, 1.0 + 2.0 * _u(d, STREAM_TICK, SV_SPEED)
+            s['size'] += (0.001 if s['growing'] else -0.001) * s['speed']
+            g = np.array([formation_point(s['f'], N, i, s['size'], s['c1'], s['layer'], per_layer_of(s['f'])) for i in range(N)])
+        elif mode == EP_LISSAJOUS3D:
+            t = tick / CONTROL_FREQ
+            g = np.tile(g[0] + np.array([0.03 * np.sin(t), 0.01 * np.sin(2 * t + 90), 0.01 * np.cos(2 * t + 90)]), (N, 1))
+        elif mode == SWARM_VS_SWARM:
+            s['c1'], s['c2'] = s['c2'], s['c1']
+            fm = pick_formation(d, STREAM_TICK, mode, N // 2)
+            s.update(f=fm['f'], size=fm['size'], layer=fm['layer'], hi=fm['hi'])
+            h = N // 2
+            g = np.array([self._svs_goal(N, shuffle_rank(d, STREAM_TICK, i, 0, h) if i < h
+                                         else h + shuffle_rank(d, STREAM_TICK, i, h, N)) for i in range(N)])
+        s['next'] = tick + s['period'] if s['period'] > 0 else NEVER
+        self.events += 1
+        self.goals = g
+        return g

@@ -12,13 +12,18 @@ LIB_PATH = os.environ.get('QS_LIB') or os.path.join(_PKG, 'libquadswarm.so')    
 QS_OK = 0
 QS_NUM_REW_COEFF = 8
 QS_NUM_TERMS = 8
-QS_NUM_ENV_STATS = 12
+QS_NUM_ENV_STATS = 13
 QS_NUM_AGENT_STATS = 4
 QS_STATE_F32 = 43
 QS_STATE_U32 = 4
-QS_STATE_ENV_I32 = 16
+QS_STATE_ENV_I32 = 36
 QS_MAX_AGENTS = 32
 SCENARIO_HOST_TABLES, SCENARIO_O_RANDOM = 0, 1
+# scenarios with a device-side generator (QS_SCENARIO_* of include/quadswarm.h), by their reference names
+DEVICE_SCENARIOS = {'o_random': 1, 'static_same_goal': 2, 'static_diff_goal': 3, 'dynamic_same_goal': 4,
+                    'dynamic_diff_goal': 5, 'swap_goals': 6, 'dynamic_formations': 7, 'ep_lissajous3D': 8,
+                    'swarm_vs_swarm': 9, 'mix': 10}
+SCENARIO_NAMES = {v: k for k, v in DEVICE_SCENARIOS.items()}
 
 REW_KEYS = ('pos', 'effort', 'crash', 'orient', 'spin', 'quadcol_bin', 'quadcol_bin_smooth_max', 'quadcol_bin_obst')
 OBS_REPR = {'xyz_vxyz_R_omega': 0, 'xyz_vxyz_R_omega_floor': 1, 'xyz_vxyz_R_omega_wall': 2}
@@ -32,7 +37,7 @@ FLAG_KICKED, FLAG_NEW_QUADCOL, FLAG_NEW_OBSTCOL = 1 << 11, 1 << 12, 1 << 13
 ENV_STAT_KEYS = ('num_collisions', 'num_collisions_after_settle', 'num_collisions_final_5_s', 'num_collisions_with_room',
                  'num_collisions_with_floor', 'num_collisions_with_wall', 'num_collisions_with_ceiling',
                  'num_collisions_obst_quad', 'num_collisions_obst_quad_after_settle', 'num_collisions_obst_quad_3_5',
-                 'num_collisions_obst_quad_5', 'episodes_done')
+                 'num_collisions_obst_quad_5', 'episodes_done', 'scenario')
 
 
 class QsConfig(C.Structure):

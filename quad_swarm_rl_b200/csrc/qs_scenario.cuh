@@ -1,0 +1,331 @@
+// Device-side episode generators of the obstacle-free scenario family: goal formations, the per-episode
+// scenario draw of `mix`, and the timed goal switches, all inside the step / reset kernels — no host work per episode or
+// per tick.  Reference behaviour (paths under gym_art/quadrotor_multi/scenarios/):
+//   formations           base.py:39-113, utils.py:74-121,149-175
+//   pick of a formation  base.py:123-136, utils.py:32-65,124-146
+//   static_same_goal / static_diff_goal      base.py:138-150 (standard_reset)
+//   dynamic_same_goal    dynamic_same_goal.py      dynamic_diff_goal   dynamic_diff_goal.py
+//   swap_goals           swap_goals.py             dynamic_formations  dynamic_formations.py:21-35
+//   ep_lissajous3D       ep_lissajous3D.py         swarm_vs_swarm      swarm_vs_swarm.py:8-101
+//   mix                  mix.py:37-93 (the two bezier modes need a third-party package and are left out, as in scenarios.py)
+// The reference draws from numpy's global stream; here every draw is a keyed Philox value (SITE_SCENARIO_U, stream 1 = at
+// reset, stream 2 = at a tick event, slot v below), so an episode is a pure function of (seed, env id, step counter).
+// oracle/scenario_gen.py restates this file draw for draw; the formation geometry of both is pinned to the reference by
+// tests/golden/formations.npz.
+//
+// Everything here is lane-local except the goal permutation of swap_goals (one warp shuffle): each lane evaluates the
+// formation point of the index it was dealt, so no shared memory and no exchange is needed.
+#pragma once
+#include "qs_device.cuh"
+
+namespace qs {
+
+// draw slots (v) inside a stream
+enum ScnSlot {
+    SV_MIX = 0, SV_PERIOD = 1, SV_FORMATION = 2, SV_SIZE = 3, SV_LAYER = 4, SV_CX = 5, SV_CY = 6, SV_CZ = 7,
+    SV_DIST = 8, SV_PHI = 9, SV_THETA = 10, SV_GROW = 11, SV_SPEED = 12, SV_SHUFFLE = 16      // SV_SHUFFLE + drone index
+};
+constexpr int SCN_STREAM_RESET = 1, SCN_STREAM_TICK = 2;
+constexpr int SCN_NEVER = 0x7fffffff;
+constexpr float SCN_BOX = 2.0f;                    // scenario box of the obstacle-free family (base.py:18, quadrotor_multi.py:118)
+constexpr float SCN_CONTROL_FREQ = 100.0f;
+
+struct Formation { int f, per_layer; float lo, hi, size, layer; };
+struct ScnState {
+    int mode, period, next, f, growing;
+    float size, layer, hi, speed;
+    V3 c1, c2;
+};
+struct ScnOut { V3 goal; int next; };
+
+__device__ __forceinline__ uint32_t scn_u24(const RngKey& key, int stream, int v) {
+    const uint4 b = rng_block(key, SITE_SCENARIO_U, 0, stream, v >> 2);
+    const int w = v & 3;
+    const uint32_t x = w == 0 ? b.x : (w == 1 ? b.y : (w == 2 ? b.z : b.w));
+    return x >> 8;
+}
+__device__ __forceinline__ float scn_u(const RngKey& key, int stream, int v) { return (float)scn_u24(key, stream, v) * (1.0f / 16777216.0f); }
+// floor(u * n) in integer arithmetic (identical in the fp64 twin)
+__device__ __forceinline__ int scn_pick(const RngKey& key, int stream, int v, int n) {
+    return (int)(((unsigned long long)scn_u24(key, stream, v) * (unsigned long long)n) >> 24);
+}
+
+// utils.py:109-121: largest divisor of num not above sqrt(num), and its cofactor
+__device__ __forceinline__ void grid_dims(int num, int& d1, int& d2) {
+    d1 = (int)floorf(sqrtf((float)num));
+    while (d1 > 1 && (num % d1) != 0) --d1;
+    d1 = max(d1, 1);
+    d2 = num / d1;
+}
+
+__device__ __forceinline__ V3 place(int plane, float a, float b, float l) {       // utils.py:149-160
+    V3 r;
+    if (plane == 0) { r.x = a; r.y = b; r.z = l; }             // horizontal
+    else if (plane == 1) { r.x = a; r.y = l; r.z = b; }        // vertical_xz
+    else { r.x = l; r.y = a; r.z = b; }                        // vertical_yz
+    return r;
+}
+
+// point k of an n-point formation before centring (base.py:39-113).  f: 0-2 circle_{horizontal,vertical_xz,vertical_yz},
+// 3 sphere, 4-6 grid_*, 7 cube.
+__device__ V3 formation_raw(int f, int n, int k, float size, float layer_dist, int per_layer) {
+    if (f <= 2) {
+        const int layer = k / per_layer;
+        const int m = (n > per_layer) ? ((layer < n / per_layer) ? per_layer : (n % per_layer)) : n;
+        const float ang = 2.0f * PI_F * (float)(k % m) / (float)m;
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        return place(f, size * cs, size * sn, (float)layer * layer_dist);
+    }
+    if (f == 3) {                                               // utils.py:74-90 (at least 3 points are generated)
+        const float nn = (float)max(n, 3);
+        const float x = 0.1f + 1.2f * nn;
+        const float start = -1.0f + 1.0f / (nn - 1.0f);
+        const float inc = (2.0f - 2.0f / (nn - 1.0f)) / (nn - 1.0f);
+        const float s = start + inc * (float)k;
+        const float lon = s * x;
+        const float sg = s > 0.f ? 1.f : (s < 0.f ? -1.f : 0.f);
+        const float lat = 0.5f * PI_F * sg * (1.0f - sqrtf(1.0f - fabsf(s)));
+        float sl, cl, sa, ca;
+        sincosf(lon, &sl, &cl);
+        sincosf(lat, &sa, &ca);
+        V3 r = {size * cl * ca, size * sl * ca, size * sa};
+        return r;
+    }
+    if (f <= 6) {
+        const int layer = k / per_layer;
+        const int nl = (n <= per_layer) ? n : ((layer < n / per_layer) ? per_layer : (n % per_layer));
+        int d1, d2;
+        grid_dims(nl, d1, d2);
+        return place(f - 4, size * (float)(k % d2), size * (float)((k / d2) % d1), (float)layer * layer_dist);
+    }
+    // cube, base.py:97-109: side = int(np.power(n, 1/3)) — float64 gives 2.9999999999999996 for n = 27, so the side is
+    // 2 for 8 <= n <= 27 and 3 for 28 <= n <= 32 (tests/test_host_logic.py checks this table against numpy)
+    const int side = n >= 28 ? 3 : (n >= 8 ? 2 : 1);
+    V3 r = {size * (float)(k / (side * side)), size * (float)((k / side) % side), size * (float)(k % side)};
+    return r;
+}
+
+__device__ V3 formation_point(int f, int n, int k, float size, V3 c, float layer_dist, int per_layer) {
+    V3 r = formation_raw(f, n, k, size, layer_dist, per_layer);
+    if (f >= 4) {                                               // grids and the cube are centred on their mean
+        float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < n; ++q) {
+            const V3 t = formation_raw(f, n, q, size, layer_dist, per_layer);
+            mx += t.x; my += t.y; mz += t.z;
+        }
+        const float inv = 1.0f / (float)n;
+        r.x -= mx * inv; r.y -= my * inv; r.z -= mz * inv;
+    }
+    r.x += c.x; r.y += c.y; r.z += c.z;
+    return r;
+}
+
+// base.py:123-136 + utils.py:32-65,124-146.  `n` = drones per formation (N/2 for swarm_vs_swarm).
+__device__ Formation pick_formation(const RngKey& key, int stream, int mode, int n) {
+    int count = 8;
+    float low = 0.25f, high = 0.5f;                              // 5 / 10 nominal arm lengths (utils.py:31-51)
+    if (mode == QS_SCENARIO_STATIC_SAME_GOAL || mode == QS_SCENARIO_DYNAMIC_SAME_GOAL || mode == QS_SCENARIO_EP_LISSAJOUS3D) {
+        count = 1; low = 0.f; high = 0.f;
+    } else if (mode == QS_SCENARIO_SWAP_GOALS) {
+        low = 0.4f; high = 0.8f;
+    } else if (mode == QS_SCENARIO_DYNAMIC_FORMATIONS) {
+        low = 0.f; high = 1.0f;
+    }
+    Formation fm;
+    fm.f = count > 1 ? scn_pick(key, stream, SV_FORMATION, count) : 0;
+    fm.per_layer = (fm.f >= 4 && fm.f <= 6) ? 50 : 8;
+    if (fm.f <= 2) {                                             // utils.py:102-106 with num = drones per layer
+        const float inv = 0.5f / sinf(PI_F / (float)fm.per_layer);
+        fm.lo = low * inv; fm.hi = high * inv;
+    } else if (fm.f == 3) {                                      // utils.py:92-99
+        const float A = 1.75388487222762f, B = 0.860487305801679f, C = 10.3632729642351f, D = 0.0920858134405214f;
+        const float inv = 1.0f / ((A - D) / (1.0f + powf((float)n / C, B)) + D);
+        fm.lo = low * inv; fm.hi = high * inv;
+    } else {
+        fm.lo = low; fm.hi = high;
+    }
+    fm.size = fm.lo + (fm.hi - fm.lo) * scn_u(key, stream, SV_SIZE);
+    fm.layer = fm.lo + (fm.hi - fm.lo) * scn_u(key, stream, SV_LAYER);
+    return fm;
+}
+
+// utils.py:163-175
+__device__ float z_above_ground(float u, int num_agents, int per_layer, int f, float size) {
+    const float z = (-0.5f * SCN_BOX + SCN_BOX * u) + 2.0f;
+    float lower = 0.25f;
+    if (f >= 1 && f <= 3) lower = size + 0.25f;
+    else if (f == 5 || f == 6) {
+        int d1, d2;
+        grid_dims(min(num_agents, per_layer), d1, d2);
+        lower = (float)d1 * size + 0.25f;
+    }
+    return fmaxf(lower, z);
+}
+
+// rank of drone i among drones [g0, g1) by their shuffle keys = the index it is dealt by a uniform random permutation
+__device__ int shuffle_rank(const RngKey& key, int stream, int i, int g0, int g1) {
+    const uint32_t ui = scn_u24(key, stream, SV_SHUFFLE + i);
+    int r = 0;
+#pragma unroll 1
+    for (int j = g0; j < g1; ++j) {
+        const uint32_t uj = scn_u24(key, stream, SV_SHUFFLE + j);
+        r += (uj < ui || (uj == ui && j < i)) ? 1 : 0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void scn_store(const DevState& st, int env, const ScnState& s) {
+    st.scn_i[env] = make_int4(s.mode, s.period, s.next, s.f | (s.growing << 8));
+    st.scn_f[3 * (long long)env + 0] = make_float4(s.size, s.layer, s.hi, s.speed);
+    st.scn_f[3 * (long long)env + 1] = make_float4(s.c1.x, s.c1.y, s.c1.z, 0.f);
+    st.scn_f[3 * (long long)env + 2] = make_float4(s.c2.x, s.c2.y, s.c2.z, 0.f);
+}
+__device__ __forceinline__ ScnState scn_load(const DevState& st, int env) {
+    ScnState s;
+    const int4 a = st.scn_i[env];
+    const float4 b = st.scn_f[3 * (long long)env + 0], c = st.scn_f[3 * (long long)env + 1], d = st.scn_f[3 * (long long)env + 2];
+    s.mode = a.x; s.period = a.y; s.next = a.z; s.f = a.w & 0xff; s.growing = (a.w >> 8) & 1;
+    s.size = b.x; s.layer = b.y; s.hi = b.z; s.speed = b.w;
+    s.c1.x = c.x; s.c1.y = c.y; s.c1.z = c.z; s.c2.x = d.x; s.c2.y = d.y; s.c2.z = d.z;
+    return s;
+}
+
+__device__ __forceinline__ int per_layer_of(int f) { return (f >= 4 && f <= 6) ? 50 : 8; }
+
+// swarm_vs_swarm.py:31-72: the two formation centres
+__device__ void svs_centers(const RngKey& key, int N, const Formation& fm, V3& c1, V3& c2) {
+    const float box = SCN_BOX;
+    c1.x = -box + 2.0f * box * scn_u(key, SCN_STREAM_RESET, SV_CX);
+    c1.y = -box + 2.0f * box * scn_u(key, SCN_STREAM_RESET, SV_CY);
+    c1.z = z_above_ground(scn_u(key, SCN_STREAM_RESET, SV_CZ), N, fm.per_layer, fm.f, fm.size);
+    const float dist = 0.25f * box + (box - 0.25f * box) * scn_u(key, SCN_STREAM_RESET, SV_DIST);
+    const float phi = -PI_F + 2.0f * PI_F * scn_u(key, SCN_STREAM_RESET, SV_PHI);
+    const float theta = -0.5f * PI_F + PI_F * scn_u(key, SCN_STREAM_RESET, SV_THETA);
+    float sp, cp, st, ct;
+    sincosf(phi, &sp, &cp);
+    sincosf(theta, &st, &ct);
+    c2.x = c1.x + dist * st * cp; c2.y = c1.y + dist * st * sp; c2.z = c1.z + dist * ct;
+    // formations that lie in a plane are kept apart along the plane's normal (swarm_vs_swarm.py:52-70)
+    const int plane = fm.f <= 2 ? fm.f : (fm.f >= 4 && fm.f <= 6 ? fm.f - 4 : -1);
+    if (plane >= 0) {
+        float* a2 = plane == 0 ? &c2.z : (plane == 1 ? &c2.y : &c2.x);
+        const float a1 = plane == 0 ? c1.z : (plane == 1 ? c1.y : c1.x);
+        const float diff = *a2 - a1;
+        if (fabsf(diff) < fm.lo) *a2 = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * fm.lo + a1;
+    }
+}
+
+__device__ V3 svs_goal(const ScnState& s, int N, int k) {
+    const int h = N / 2;
+    return k < h ? formation_point(s.f, h, k, s.size, s.c1, s.layer, per_layer_of(s.f))
+                 : formation_point(s.f, N - h, k - h, s.size, s.c2, s.layer, per_layer_of(s.f));
+}
+
+// scenario.reset() of the env's mode (for `mix`: of the scenario drawn for this episode).  Every lane of the env computes
+// the same scenario state; lane 0 stores it.
+__device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, int i, DevState st, int env) {
+    ScnState s;
+    s.mode = cfg_mode;
+    if (cfg_mode == QS_SCENARIO_MIX) {
+        // mix.py:59-63 draws uniformly from the mode list; the bezier entries are not available
+        if (N == 1) {
+            const int m4[4] = {QS_SCENARIO_STATIC_SAME_GOAL, QS_SCENARIO_STATIC_DIFF_GOAL, QS_SCENARIO_EP_LISSAJOUS3D,
+                               QS_SCENARIO_DYNAMIC_SAME_GOAL};
+            s.mode = m4[scn_pick(key, SCN_STREAM_RESET, SV_MIX, 4)];
+        } else {
+            s.mode = QS_SCENARIO_STATIC_SAME_GOAL + scn_pick(key, SCN_STREAM_RESET, SV_MIX, 8);
+        }
+    }
+    s.period = 0; s.next = SCN_NEVER; s.growing = 0; s.speed = 0.f;
+    const bool svs = s.mode == QS_SCENARIO_SWARM_VS_SWARM;
+    const Formation fm = pick_formation(key, SCN_STREAM_RESET, s.mode, svs ? N / 2 : N);
+    s.f = fm.f; s.size = fm.size; s.layer = fm.layer; s.hi = fm.hi;
+    s.c1.x = 0.f; s.c1.y = 0.f; s.c1.z = 2.0f;
+    s.c2 = s.c1;
+    if (s.mode == QS_SCENARIO_DYNAMIC_SAME_GOAL || s.mode == QS_SCENARIO_DYNAMIC_DIFF_GOAL || s.mode == QS_SCENARIO_SWAP_GOALS || svs) {
+        s.period = 400 + scn_pick(key, SCN_STREAM_RESET, SV_PERIOD, 200);       // int(U(4, 6) s * 100 Hz)
+        s.next = s.period;
+    }
+    ScnOut o;
+    if (svs) {
+        svs_centers(key, N, fm, s.c1, s.c2);
+        o.goal = svs_goal(s, N, i);                                               // not shuffled at reset
+    } else if (s.mode == QS_SCENARIO_EP_LISSAJOUS3D) {
+        s.c1.x = -2.0f; s.c1.y = 0.f; s.c1.z = 2.0f;
+        s.period = 1; s.next = 1;
+        o.goal = s.c1;                                                            // size 0, layer distance 0
+    } else {
+        if (s.mode == QS_SCENARIO_DYNAMIC_FORMATIONS) {
+            s.growing = scn_u24(key, SCN_STREAM_RESET, SV_GROW) < (1u << 23) ? 1 : 0;
+            s.speed = 1.0f + 2.0f * scn_u(key, SCN_STREAM_RESET, SV_SPEED);
+            s.period = 1; s.next = 1;
+        }
+        const int k = shuffle_rank(key, SCN_STREAM_RESET, i, 0, N);               // standard_reset shuffles the goals
+        o.goal = formation_point(s.f, N, k, s.size, s.c1, s.layer, fm.per_layer);
+    }
+    o.next = s.next;
+    if (i == 0) scn_store(st, env, s);
+    return o;
+}
+
+// scenario.step() on a tick where something happens (`active` lanes; the others pass through).  Called from a
+// warp-uniform branch: swap_goals permutes the goals with a shuffle.
+template <int NP>
+__device__ __noinline__ ScnOut scenario_tick(RngKey key, int N, int i, int tick, V3 goal, bool active, DevState st, int env) {
+    ScnOut o;
+    o.goal = goal; o.next = SCN_NEVER;
+    ScnState s;
+    s.mode = -1;
+    if (active) s = scn_load(st, env);
+    // swap_goals.py: goals are permuted among the drones
+    const int src = (active && s.mode == QS_SCENARIO_SWAP_GOALS) ? shuffle_rank(key, SCN_STREAM_TICK, i, 0, N) : i;
+    const float gx = shfl<NP>(goal.x, src), gy = shfl<NP>(goal.y, src), gz = shfl<NP>(goal.z, src);
+    if (active) {
+        if (s.mode == QS_SCENARIO_SWAP_GOALS) {
+            o.goal.x = gx; o.goal.y = gy; o.goal.z = gz;
+        } else if (s.mode == QS_SCENARIO_DYNAMIC_SAME_GOAL) {
+            s.c1.x = -SCN_BOX + 2.0f * SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CX);
+            s.c1.y = -SCN_BOX + 2.0f * SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CY);
+            s.c1.z = fmaxf(0.25f, (-0.5f * SCN_BOX + SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CZ)) + 2.0f);
+            o.goal = formation_point(s.f, N, i, s.size, s.c1, 0.0f, per_layer_of(s.f));
+        } else if (s.mode == QS_SCENARIO_DYNAMIC_DIFF_GOAL) {
+            s.c1.x = -SCN_BOX + 2.0f * SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CX);
+            s.c1.y = -SCN_BOX + 2.0f * SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CY);
+            s.c1.z = z_above_ground(scn_u(key, SCN_STREAM_TICK, SV_CZ), N, per_layer_of(s.f), s.f, s.size);   // old formation
+            const Formation fm = pick_formation(key, SCN_STREAM_TICK, s.mode, N);
+            s.f = fm.f; s.size = fm.size; s.layer = fm.layer; s.hi = fm.hi;
+            o.goal = formation_point(s.f, N, shuffle_rank(key, SCN_STREAM_TICK, i, 0, N), s.size, s.c1, s.layer, fm.per_layer);
+        } else if (s.mode == QS_SCENARIO_DYNAMIC_FORMATIONS) {
+            if (s.size <= -s.hi) {
+                s.growing = 1; s.speed = 1.0f + 2.0f * scn_u(key, SCN_STREAM_TICK, SV_SPEED);
+            } else if (s.size >= s.hi) {
+                s.growing = 0; s.speed = 1.0f + 2.0f * scn_u(key, SCN_STREAM_TICK, SV_SPEED);
+            }
+            s.size += (s.growing ? 0.001f : -0.001f) * s.speed;
+            o.goal = formation_point(s.f, N, i, s.size, s.c1, s.layer, per_layer_of(s.f));      // unshuffled
+        } else if (s.mode == QS_SCENARIO_EP_LISSAJOUS3D) {
+            const float t = (float)tick / SCN_CONTROL_FREQ;
+            // every drone follows drone 0's goal (ep_lissajous3D.py:20-27) — all goals are equal from the reset on, so each
+            // lane advances its own copy; the "+ 90" is in radians, as in the reference
+            o.goal.x = goal.x + 0.03f * sinf(t);
+            o.goal.y = goal.y + 0.01f * sinf(2.0f * t + 90.0f);
+            o.goal.z = goal.z + 0.01f * cosf(2.0f * t + 90.0f);
+        } else if (s.mode == QS_SCENARIO_SWARM_VS_SWARM) {
+            const V3 t = s.c1; s.c1 = s.c2; s.c2 = t;
+            const Formation fm = pick_formation(key, SCN_STREAM_TICK, s.mode, N / 2);
+            s.f = fm.f; s.size = fm.size; s.layer = fm.layer; s.hi = fm.hi;
+            const int h = N / 2;
+            const int k = i < h ? shuffle_rank(key, SCN_STREAM_TICK, i, 0, h) : h + shuffle_rank(key, SCN_STREAM_TICK, i, h, N);
+            o.goal = svs_goal(s, N, k);
+        }
+        s.next = s.period > 0 ? tick + s.period : SCN_NEVER;
+        o.next = s.next;
+        if (i == 0) scn_store(st, env, s);
+    }
+    __syncwarp();
+    return o;
+}
+
+}  // namespace qs

@@ -13,6 +13,7 @@
 // responses, random yaw, reset, re-drawn sensor noise) out of line.
 #pragma once
 #include "qs_device.cuh"
+#include "qs_scenario.cuh"
 
 namespace qs {
 
@@ -224,7 +225,7 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
 template <int NP>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
-                                          float nvel[3]) {
+                                          float nvel[3], int& scn_next) {
     const DevState& st = p.st;
     if (do_reset && valid) {
         // stale velocity (Appendix D-6): the multi-env's self.vel is only refreshed by step()
@@ -242,6 +243,12 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
                                                        st.obst + (long long)env * p.M);
             s.goal[0] = ep.goal.x; s.goal[1] = ep.goal.y; s.goal[2] = ep.goal.z;
             spawn = ep.spawn;
+        } else if (p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST) {
+            // goal formation of the env's scenario, drawn on the device; drones spawn around their goals
+            const ScnOut o = scenario_reset(key, p.scenario, p.N, i, st, env);
+            s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
+            spawn = o.goal;
+            scn_next = o.next;
         } else {
             const float4 g = st.next_goal[a], sp = st.next_spawn[a];
             s.goal[0] = g.x; s.goal[1] = g.y; s.goal[2] = g.z;
@@ -355,6 +362,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         const int4 c = st.env_ctr[env];
         ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
     }
+    // device-side scenarios: the tick of the env's next goal event (qs_scenario.cuh); never for the other scenarios
+    const bool dev_scn = p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST;
+    int scn_next = SCN_NEVER;
+    if (dev_scn && env_ok && role == 0) scn_next = st.scn_i[env].z;
     if (SPLIT && role == 1) {
         // ============================ observer warp ============================
         const int gbase = lane & ~(NP - 1);
@@ -716,6 +727,22 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             }
         }
 
+        // ================= scenario tick, quadrotor_multi.py:590 (reads the post-increment tick) =================
+        // The observation of this step shows the NEW goal only if a contact response forces its re-computation
+        // (quadrotor_multi.py:598-599); otherwise it was computed before the tick.  Single-warp kernel: event envs without
+        // a response are ticked after the observation instead (site B below).  An env that ends its episode now is reset.
+        const bool scn_ev = dev_scn && env_ok && ctr.tick == scn_next && !done;
+        if (dev_scn && __any_sync(0xffffffffu, scn_ev && (SPLIT || kicked))) {
+            const V3 g = {s.goal[0], s.goal[1], s.goal[2]};
+            const bool act = scn_ev && (SPLIT || kicked);
+            const ScnOut o = scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
+            if (act) {
+                s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
+                scn_next = o.next;
+                goal_dirty = true;
+            }
+        }
+
         // ================= outputs of this step =================
         const long long ta = (long long)t * A + a;
         if (valid) {
@@ -751,8 +778,9 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 int32_t* o = st.stats_env + (long long)env * QS_NUM_ENV_STATS;
                 for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = c[k]; c[k] = 0; }
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
+                o[QS_STAT_SCENARIO] = dev_scn ? st.scn_i[env].x : p.scenario;
             }
-            reset_env<NP>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel);
+            reset_env<NP>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next);
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -788,6 +816,16 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 __syncwarp();
             } else {
                 write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, gbase + a * p.D);
+            }
+        }
+        if (!SPLIT && dev_scn && __any_sync(0xffffffffu, scn_ev && !kicked)) {      // scenario tick, site B
+            const V3 g = {s.goal[0], s.goal[1], s.goal[2]};
+            const bool act = scn_ev && !kicked;
+            const ScnOut o = scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
+            if (act) {
+                s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
+                scn_next = o.next;
+                goal_dirty = true;
             }
         }
         ctr.step_count += 1;
@@ -835,7 +873,8 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     key.step = (uint32_t)ctr.step_count;
     float nvel[3] = {0.f, 0.f, 0.f};
     // every lane of the warp takes part in the shuffles below; lanes of unmasked envs write nothing
-    reset_env<NP>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel);
+    int scn_next = SCN_NEVER;
+    reset_env<NP>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next);
     if (env_ok && i == 0) {
         int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) c[k] = 0;

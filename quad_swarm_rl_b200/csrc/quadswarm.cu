@@ -145,6 +145,14 @@ __global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_
         int32_t* e = ei + t * QS_STATE_ENV_I32;
         e[0] = c.x; e[1] = c.y; e[2] = c.z; e[3] = c.w;
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) e[4 + k] = st.env_cnt[t * QS_NUM_ENV_STATS + k];
+        int32_t* sc = e + 4 + QS_NUM_ENV_STATS;
+        const int4 si = st.scn_i[t];
+        sc[0] = si.x; sc[1] = si.y; sc[2] = si.z; sc[3] = si.w;
+        for (int q = 0; q < 3; ++q) {
+            const float4 f = st.scn_f[3 * t + q];
+            sc[4 + 4 * q] = __float_as_int(f.x); sc[5 + 4 * q] = __float_as_int(f.y);
+            sc[6 + 4 * q] = __float_as_int(f.z); sc[7 + 4 * q] = __float_as_int(f.w);
+        }
     }
     if (obst != nullptr && t < (long long)E * M) {
         const float2 ob = st.obst[t];
@@ -180,6 +188,11 @@ __global__ void k_set_state(DevState st, int E, int N, int M, const uint8_t* mas
         const int32_t* e = ei + t * QS_STATE_ENV_I32;
         st.env_ctr[t] = make_int4(e[0], e[1], e[2], e[3]);
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) st.env_cnt[t * QS_NUM_ENV_STATS + k] = e[4 + k];
+        const int32_t* sc = e + 4 + QS_NUM_ENV_STATS;
+        st.scn_i[t] = make_int4(sc[0], sc[1], sc[2], sc[3]);
+        for (int q = 0; q < 3; ++q)
+            st.scn_f[3 * t + q] = make_float4(__int_as_float(sc[4 + 4 * q]), __int_as_float(sc[5 + 4 * q]),
+                                              __int_as_float(sc[6 + 4 * q]), __int_as_float(sc[7 + 4 * q]));
     }
     if (obst != nullptr && t < (long long)E * M && (mask == nullptr || mask[t / M]))
         st.obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
@@ -293,8 +306,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     if (K < 0 || K > cfg->num_agents - 1) return fail(QS_ERR_INVALID_ARG, "Incorrect number of neigbors");
     if (cfg->use_obstacles && cfg->num_obstacles < 1) return fail(QS_ERR_INVALID_ARG, "use_obstacles needs num_obstacles >= 1");
     if (cfg->ep_time <= 0.f) return fail(QS_ERR_INVALID_ARG, "ep_time must be positive");
-    if (cfg->scenario != QS_SCENARIO_HOST_TABLES && cfg->scenario != QS_SCENARIO_O_RANDOM)
+    if (cfg->scenario < QS_SCENARIO_HOST_TABLES || cfg->scenario > QS_SCENARIO_MIX)
         return fail(QS_ERR_INVALID_ARG, "unknown scenario");
+    if (cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->use_obstacles)
+        return fail(QS_ERR_INVALID_ARG, "the device-side goal-formation scenarios are obstacle-free (use_obstacles must be 0)");
     if (cfg->scenario == QS_SCENARIO_O_RANDOM) {
         const int cells = cfg->obst_grid[0] * cfg->obst_grid[1];
         if (!cfg->use_obstacles) return fail(QS_ERR_INVALID_ARG, "scenario o_random needs use_obstacles");
@@ -341,6 +356,8 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.next_obst, sizeof(float2) * E * M);
     QS_ALLOC0(st.stats_env, sizeof(int32_t) * E * QS_NUM_ENV_STATS);
     QS_ALLOC0(st.stats_agent, sizeof(float4) * A);
+    QS_ALLOC0(st.scn_i, sizeof(int4) * E);
+    QS_ALLOC0(st.scn_f, sizeof(float4) * 3 * E);
     // rotation = identity so that a never-reset env still holds a valid state
     {
         std::string tmp;
@@ -385,6 +402,7 @@ extern "C" int qs_destroy(QsHandle* h) {
     DevState& st = h->st;
     cudaFree(st.slots); cudaFree(st.env_ctr); cudaFree(st.env_cnt); cudaFree(st.obst); cudaFree(st.next_goal);
     cudaFree(st.next_spawn); cudaFree(st.next_obst); cudaFree(st.stats_env); cudaFree(st.stats_agent);
+    cudaFree(st.scn_i); cudaFree(st.scn_f);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_rewards); cudaFree(h->d_terms); cudaFree(h->d_dones);
     cudaFree(h->d_mask);
     cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);

@@ -222,6 +222,8 @@ class _EnvBase:
 
     def _scenario_ticks(self):
         """scenario.step() for every env (quadrotor_multi.py:590); uploads goals that moved."""
+        if self.device_scenario is not None:          # goals move inside the step kernel
+            return
         changed = []
         for e, sc in enumerate(self._scenarios):
             if not sc.dynamic:
@@ -270,6 +272,8 @@ class _EnvBase:
         es, ags = es[e].cpu().numpy(), ags[e].cpu().numpy()
         N = self.num_agents_per_env
         name = scenario_name[9:]
+        if self.device_scenario is not None:          # the scenario of the episode that ended (for mix: the one drawn)
+            name = L.SCENARIO_NAMES.get(int(es[L.ENV_STAT_KEYS.index('scenario')]), name)
         common = {
             'num_collisions': int(es[0]), 'num_collisions_with_room': int(es[3]), 'num_collisions_with_floor': int(es[4]),
             'num_collisions_with_wall': int(es[5]), 'num_collisions_with_ceiling': int(es[6]),
@@ -415,8 +419,11 @@ class QuadrotorEnvMultiBatched(_EnvBase):
                  obst_spawn_area=(8.0, 8.0), use_downwash=False, quads_mode='static_same_goal',
                  room_dims=(10., 10., 10.), sense_noise='default', device=0, seed=None, env_id_offset=0,
                  device_scenarios=True):
-        # o_random has a device-side generator (no host work per episode); every other mode uses host tables
-        dev_scn = 'o_random' if (device_scenarios and quads_mode == 'o_random' and use_obstacles) else None
+        # device-side generators (no host work per episode or per tick): o_random with obstacles, the goal-formation
+        # family and mix without; every other mode uses host tables
+        dev_scn = None
+        if device_scenarios and quads_mode in L.DEVICE_SCENARIOS and (quads_mode == 'o_random') == bool(use_obstacles):
+            dev_scn = quads_mode
         super().__init__(num_envs, num_agents, ep_time, rew_coeff, obs_repr, neighbor_visible_num, neighbor_obs_type,
                          collision_hitbox_radius, collision_falloff_radius, use_obstacles, obst_density, obst_size,
                          obst_spawn_area, use_downwash, True, quads_mode, room_dims, False, ['topdown'], False,

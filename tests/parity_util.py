@@ -155,6 +155,12 @@ class Pair:
                                o.distance_to_goal_3_5, o.distance_to_goal_5]
             if M > 0 and o.obst_xy is not None:
                 ob[e, :M] = o.obst_xy
+            sc = getattr(o.source, 's', None)                 # twin of the device-side scenario state (scenario_gen.py)
+            if sc is not None:
+                base = 4 + L.QS_NUM_ENV_STATS
+                ei[e, base:base + 4] = [sc['mode'], sc['period'], sc['next'], sc['f'] | (sc['growing'] << 8)]
+                fl32 = np.array([sc['size'], sc['layer'], sc['hi'], sc['speed'], *sc['c1'], 0.0, *sc['c2'], 0.0], np.float32)
+                ei[e, base + 4:base + 16] = fl32.view(np.int32)
         au32 = au.astype(np.uint32).view(np.int32)
         return dict(agent_f32=torch.from_numpy(af), agent_u32=torch.from_numpy(au32.copy()), env_i32=torch.from_numpy(ei),
                     obst_xy=torch.from_numpy(ob[:, :M].copy()) if M > 0 else None)
@@ -163,6 +169,9 @@ class Pair:
         st = self.oracle_state()
         cur = self.engine.get_state()
         st['env_i32'][:, 3] = cur['env_i32'][:, 3].cpu()          # episode_idx is engine-private
+        if getattr(self.oracles[0].source, 's', None) is None:    # no twin of the scenario state: keep the device's
+            base = 4 + L.QS_NUM_ENV_STATS
+            st['env_i32'][:, base:] = cur['env_i32'][:, base:].cpu()
         self.engine.set_state(st)
 
     def device_fields(self):
@@ -182,6 +191,23 @@ class Pair:
                     thrust_rot_damp=f('thrust_rot_damp'), thrust_cmds_damp=f('thrust_cmds_damp'), ou=f('ou'),
                     goal=f('goal'),
                     on_floor=np.array([[d.on_floor for d in e.drones] for e in o], dtype=bool))
+
+
+class DevicePair(Pair):
+    """Engine with a device-side episode generator + oracle envs fed by its CPU twin (oracle/scenario_gen.py): no host
+    tables on either side."""
+
+    def __init__(self, E, kw, seed, device_scenario, source_factory, env_id_offset=0):
+        self.E, self.kw, self.N = E, dict(kw), kw['num_agents']
+        self.engine = QuadSwarmEngine(num_envs=E, seed=seed, device_scenario=device_scenario,
+                                      env_id_offset=env_id_offset, **kw)
+        self.ocfg = cfg_to_oracle(kw)
+        self.oracles = [qo.OracleEnv(self.ocfg, qo.PhiloxRng(seed), source_factory(), env_id=env_id_offset + e)
+                        for e in range(E)]
+        self.table_idx = 0
+
+    def _push_table(self, k):
+        pass
 
 
 def run_parity(pair, T, rs, resync=20, rtol=1e-4, atol=1e-4, action_scale=1.0, check_state=True, hook=None):

@@ -195,6 +195,49 @@ def test_device_side_o_random_generator_matches_twin():
     pair.engine.close()
 
 
+DEVICE_FAMILY = ['static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals',
+                 'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix']
+
+
+@pytest.mark.parametrize('mode', DEVICE_FAMILY)
+def test_device_side_scenario_family_matches_twin(mode):
+    """QS_SCENARIO_STATIC_SAME_GOAL .. QS_SCENARIO_MIX: formation picks, goal formations and the timed / per-tick goal
+    changes happen inside the kernels and equal oracle/scenario_gen.py (same keyed draws); the trajectory — goals
+    included, compared every step — stays in parity across goal events and auto-resets."""
+    from oracle.scenario_gen import DeviceScenarioSource
+    from tests import parity_util as pu
+    periodic = mode in ('dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals', 'swarm_vs_swarm')
+    kw = dict(num_agents=8, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=3, ep_time=6.3 if periodic else 1.2)
+    E = 3 if periodic else 4
+    pair = pu.DevicePair(E, kw, 97531, mode, lambda: DeviceScenarioSource(mode))
+    T = 660 if periodic else (400 if mode == 'mix' else 260)
+    rep = pu.run_parity(pair, T, np.random.RandomState(11), resync=20)
+    assert rep['dones'] >= E
+    if mode not in ('static_same_goal', 'static_diff_goal', 'mix'):     # every env saw goal events (period <= 599 ticks)
+        assert all(o.source.events >= 1 for o in pair.oracles)
+    es, _ = pair.engine.episode_stats()
+    names = {int(x) for x in es[:, 12].cpu().numpy()}
+    assert names <= set(range(2, 10)) and (mode == 'mix' or names == {pu.L.DEVICE_SCENARIOS[mode]})
+    pair.engine.close()
+
+
+def test_device_side_swarm_vs_swarm_32_drones_split_and_single(monkeypatch):
+    """c4's scenario on the device at N = 32 (two 16-drone formations), in both kernel shapes; identical outputs."""
+    import torch
+    from oracle.scenario_gen import DeviceScenarioSource
+    from tests import parity_util as pu
+    kw = dict(num_agents=32, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=6, ep_time=0.3)
+    outs = []
+    for split in ('0', '1'):
+        monkeypatch.setenv('QS_SPLIT', split)
+        pair = pu.DevicePair(2, kw, 2468, 'swarm_vs_swarm', lambda: DeviceScenarioSource('swarm_vs_swarm'))
+        rep = pu.run_parity(pair, 40, np.random.RandomState(3), resync=10)
+        assert rep['dones'] >= 2
+        outs.append(pair.engine.obs.clone())
+        pair.engine.close()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize('split', ['0', '1'])
 def test_both_step_kernels_against_oracle(split, monkeypatch):
     """The single-warp kernel (QS_SPLIT=0) and the physics/observer split kernel (QS_SPLIT=1) are the same function:

@@ -1,0 +1,165 @@
+"""CPU checks of the device-side scenario family's twin (oracle/scenario_gen.py) against golden vectors of the
+reference (tests/golden/formations.npz, made by oracle/gen_golden_formations.py) and against the host generators
+(quad_swarm_rl_b200/scenarios.py, themselves replayed against reference trajectories in test_oracle_vs_reference.py).
+The GPU tests (test_gpu_parity.py) then compare the kernels with this twin."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import philox as px
+from oracle import quadswarm_oracle as qo
+from oracle import scenario_gen as sg
+from quad_swarm_rl_b200 import scenarios as hs
+from tests import parity_util as pc
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'formations.npz'))
+SIZE, LAYER = float(GOLD['params'][0]), float(GOLD['params'][1])
+CENTER = GOLD['params'][2:5]
+
+
+class FixedDraws:
+    """Stand-in for philox.KeyedDraws: every uniform is the same number."""
+
+    def __init__(self, u):
+        self.u = u
+
+    def uniform(self, site, i, j, v):
+        return self.u
+
+
+def test_formation_names_and_order():
+    assert tuple(GOLD['formations']) == sg.FORMATION_NAMES == hs.FORMATIONS
+
+
+@pytest.mark.parametrize('f', range(8))
+def test_formation_geometry_equals_reference(f):
+    for n in range(1, 33):
+        ref = GOLD[f'goals_{f}_{n}']
+        pl = sg.per_layer_of(f)
+        twin = np.array([sg.formation_point(f, n, k, SIZE, CENTER, LAYER, pl) for k in range(n)])
+        np.testing.assert_allclose(twin, ref, rtol=0, atol=1e-12, err_msg=f'twin {sg.FORMATION_NAMES[f]} n={n}')
+        host = hs.formation_goals(sg.FORMATION_NAMES[f], n, SIZE, CENTER, LAYER, pl)[:n]
+        np.testing.assert_allclose(host, ref, rtol=0, atol=1e-12, err_msg=f'host {sg.FORMATION_NAMES[f]} n={n}')
+
+
+def test_cube_side_table_of_the_kernel():
+    # qs_scenario.cuh hard-codes int(np.power(n, 1/3)) for n <= 32 (27 -> 2: the float64 cube root is below 3)
+    for n in range(1, 33):
+        assert int(np.power(n, 1.0 / 3)) == (3 if n >= 28 else (2 if n >= 8 else 1))
+
+
+def test_formation_size_ranges_equal_reference():
+    modes = {'static_diff_goal': sg.STATIC_DIFF_GOAL, 'swap_goals': sg.SWAP_GOALS, 'dynamic_formations': sg.DYNAMIC_FORMATIONS}
+    for name, mode in modes.items():
+        for f in range(8):
+            for n in range(1, 33):
+                lo, hi = GOLD[f'range_{name}_{f}_{n}']
+                # force the formation pick to f: u = (f + 0.5) / 8
+                fm = sg.pick_formation(FixedDraws((f + 0.5) / 8.0), 1, mode, n)
+                assert fm['f'] == f and fm['per_layer'] == (50 if 4 <= f <= 6 else 8)
+                np.testing.assert_allclose([fm['lo'], fm['hi']], [lo, hi], rtol=1e-12, atol=0)
+                assert fm['lo'] <= fm['size'] <= fm['hi'] and fm['lo'] <= fm['layer'] <= fm['hi']
+    for mode in (sg.STATIC_SAME_GOAL, sg.DYNAMIC_SAME_GOAL, sg.EP_LISSAJOUS3D):     # one formation, zero size
+        fm = sg.pick_formation(FixedDraws(0.7), 1, mode, 8)
+        assert fm['f'] == 0 and fm['size'] == 0.0 and fm['layer'] == 0.0
+
+
+def test_centre_height_equals_reference():
+    for f in range(8):
+        for n in range(1, 33):
+            u, z = GOLD[f'z_{f}_{n}']                 # u ~ U(-1, 1) as drawn by the reference, z = get_z_value(...)
+            got = sg.z_above_ground((u + 1.0) / 2.0, n, sg.per_layer_of(f), f, SIZE)
+            assert abs(got - z) < 1e-12
+
+
+def test_shuffle_rank_is_a_permutation_and_uniform_enough():
+    counts = np.zeros((6, 6), int)
+    for step in range(600):
+        d = px.KeyedDraws(99, 3, step)
+        perm = [sg.shuffle_rank(d, sg.STREAM_TICK, i, 0, 6) for i in range(6)]
+        assert sorted(perm) == list(range(6))
+        for i, k in enumerate(perm):
+            counts[i, k] += 1
+    assert counts.min() > 50 and counts.max() < 160          # 100 expected per cell
+    d = px.KeyedDraws(99, 3, 7)                               # ranks inside a sub-range (swarm_vs_swarm halves)
+    assert sorted(sg.shuffle_rank(d, sg.STREAM_TICK, i, 4, 8) for i in range(4, 8)) == [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize('mode', sorted(sg.MODE_IDS))
+def test_twin_episode_semantics(mode):
+    """Run the twin inside the oracle env: the reference's scenario semantics hold (scenarios/*.py)."""
+    N = 8
+    cfg = pc.cfg_to_oracle(dict(num_agents=N, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=2, ep_time=6.2))
+    src = sg.DeviceScenarioSource(mode)
+    env = qo.OracleEnv(cfg, qo.PhiloxRng(2024), src, env_id=5)
+    env.reset()
+    s0 = dict(src.s)
+    g0 = np.array([d.goal for d in env.drones])
+    rs = np.random.RandomState(0)
+    assert src.name() == 'Scenario_' + sg.MODE_NAMES[s0['mode']]
+    if s0['mode'] in (sg.STATIC_SAME_GOAL, sg.DYNAMIC_SAME_GOAL):
+        assert np.all(g0 == np.array([0.0, 0.0, 2.0]))
+    if s0['mode'] == sg.EP_LISSAJOUS3D:
+        assert np.all(g0 == np.array([-2.0, 0.0, 2.0]))
+    if s0['mode'] in (sg.STATIC_DIFF_GOAL, sg.DYNAMIC_DIFF_GOAL, sg.SWAP_GOALS, sg.DYNAMIC_FORMATIONS):
+        # a shuffled formation of the picked type around (0, 0, 2): same point set as the host generator's
+        want = hs.formation_goals(sg.FORMATION_NAMES[s0['f']], N, s0['size'], np.array([0., 0., 2.]), s0['layer'],
+                                  sg.per_layer_of(s0['f']))[:N]
+        assert np.allclose(sorted(map(tuple, np.round(g0, 9))), sorted(map(tuple, np.round(want, 9))))
+    if s0['mode'] == sg.SWARM_VS_SWARM:
+        h = N // 2
+        for half, c in ((slice(0, h), s0['c1']), (slice(h, N), s0['c2'])):
+            want = hs.formation_goals(sg.FORMATION_NAMES[s0['f']], h, s0['size'], c, s0['layer'], sg.per_layer_of(s0['f']))[:h]
+            assert np.allclose(g0[half], want)                 # not shuffled at reset (swarm_vs_swarm.py:74-84)
+        assert BOX_DIST_OK(s0['c1'], s0['c2'])
+    periodic = s0['mode'] in (sg.DYNAMIC_SAME_GOAL, sg.DYNAMIC_DIFF_GOAL, sg.SWAP_GOALS, sg.SWARM_VS_SWARM)
+    if periodic:
+        assert 400 <= s0['period'] <= 599 and s0['next'] == s0['period']
+    prev = g0
+    for t in range(1, 611):
+        env.step(rs.uniform(-1, 1, (N, 4)))
+        g = np.array([d.goal for d in env.drones])
+        if periodic:
+            if t == s0['period']:
+                assert src.events == 1
+                if s0['mode'] == sg.SWAP_GOALS:
+                    assert sorted(map(tuple, g)) == sorted(map(tuple, prev))
+                if s0['mode'] == sg.SWARM_VS_SWARM:
+                    assert np.allclose(src.s['c1'], s0['c2']) and np.allclose(src.s['c2'], s0['c1'])
+                if s0['mode'] == sg.DYNAMIC_SAME_GOAL:
+                    assert np.all(g == g[0]) and abs(g[0, 0]) <= 2 and abs(g[0, 1]) <= 2 and 0.25 <= g[0, 2] <= 3.0
+            elif t < s0['period']:
+                assert np.array_equal(g, prev)
+        if s0['mode'] == sg.EP_LISSAJOUS3D:
+            tt = t / 100.0
+            step = np.array([0.03 * np.sin(tt), 0.01 * np.sin(2 * tt + 90), 0.01 * np.cos(2 * tt + 90)])
+            assert np.allclose(g, prev[0] + step)
+        if s0['mode'] == sg.DYNAMIC_FORMATIONS:
+            assert abs(abs(src.s['size']) - 0) <= s0['hi'] + 0.004
+        assert g[:, 2].min() > 0.0
+        prev = g
+    assert env.tick == 610 and (src.events >= 1 or s0['mode'] in (sg.STATIC_SAME_GOAL, sg.STATIC_DIFF_GOAL))
+
+
+def BOX_DIST_OK(c1, c2):
+    d = np.linalg.norm(np.asarray(c2) - np.asarray(c1))
+    return 0.5 - 1e-9 <= d <= 2.0 + 1.5          # U(box/4, box) plus the push-apart along the formation normal
+
+
+def test_mix_draws_every_available_scenario():
+    seen = set()
+    cfg = pc.cfg_to_oracle(dict(num_agents=4, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=0, ep_time=0.05))
+    for env_id in range(60):
+        src = sg.DeviceScenarioSource('mix')
+        env = qo.OracleEnv(cfg, qo.PhiloxRng(7), src, env_id=env_id)
+        env.reset()
+        seen.add(src.s['mode'])
+    assert seen == set(range(sg.STATIC_SAME_GOAL, sg.SWARM_VS_SWARM + 1))
+    single = set()
+    cfg1 = pc.cfg_to_oracle(dict(num_agents=1, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=0, ep_time=0.05))
+    for env_id in range(40):
+        src = sg.DeviceScenarioSource('mix')
+        qo.OracleEnv(cfg1, qo.PhiloxRng(7), src, env_id=env_id).reset()
+        single.add(src.s['mode'])
+    assert single == {sg.STATIC_SAME_GOAL, sg.STATIC_DIFF_GOAL, sg.EP_LISSAJOUS3D, sg.DYNAMIC_SAME_GOAL}
