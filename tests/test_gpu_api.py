@@ -189,20 +189,59 @@ def test_reference_style_env_object():
     env.close()
 
 
-def test_batched_env_and_dynamic_scenario():
+@pytest.mark.parametrize('device_scenarios', [False, True])
+def test_batched_env_and_dynamic_scenario(device_scenarios):
+    """swarm_vs_swarm behind the batched env: goals stay put until an env's swap tick (400..599), some envs have swapped
+    by tick 449, every env ends on its 451st step.  With device_scenarios the host does nothing per tick or per episode."""
     from quad_swarm_rl_b200.env import QuadrotorEnvMultiBatched
-    env = QuadrotorEnvMultiBatched(num_envs=16, num_agents=8, ep_time=4.5, neighbor_visible_num=6, quads_mode='swarm_vs_swarm', seed=2)
+    env = QuadrotorEnvMultiBatched(num_envs=16, num_agents=8, ep_time=4.5, neighbor_visible_num=6, quads_mode='swarm_vs_swarm',
+                                   seed=2, device_scenarios=device_scenarios)
+    assert env.device_scenario == ('swarm_vs_swarm' if device_scenarios else None)
     obs, info = env.reset()
     assert obs.is_cuda and obs.shape == (128, 54) and env.num_agents == 128
-    goals0 = env._goals.copy()
+
+    def goals():
+        return env.engine.get_state()['agent_f32'][..., 30:33].cpu().numpy().copy()
+
+    snaps = {0: goals()}
     ended = []
     for t in range(455):
         obs, rew, term, trunc, infos = env.step(torch.rand((128, 4), device='cuda') * 2 - 1)
         if term.any():
             assert term.all() and not trunc.any()
             ended.append(t)
+        if t + 1 in (399, 449, 455):
+            snaps[t + 1] = goals()
     assert ended == [450]                                       # ep_len = 450 -> every env ends on its 451st step
-    assert not np.array_equal(goals0, env._goals)               # formation centres swapped / new episode
+    assert np.array_equal(snaps[0], snaps[399])                 # no goal event before tick 400
+    swapped = (snaps[399] != snaps[449]).any(axis=(1, 2))
+    assert swapped.any() and not swapped.all()                  # periods are U(4, 6) s: some envs have swapped by 4.49 s
+    assert (snaps[449] != snaps[455]).any(axis=(1, 2)).all()    # new episode, new formations everywhere
+    if device_scenarios:
+        es, _ = env.engine.episode_stats()
+        assert set(es[:, 12].cpu().numpy().tolist()) == {9}      # QS_SCENARIO_SWARM_VS_SWARM latched with the statistics
+    env.close()
+
+
+def test_batched_env_mix_on_device_reports_scenario_names():
+    """quads_mode='mix' with the device-side generators: every episode draws its scenario on the device; the single-env
+    API reports it in the episode statistics' key prefix (reward_shaping.py:95-98 consumes those keys)."""
+    from quad_swarm_rl_b200 import _lib as L
+    from quad_swarm_rl_b200.env import QuadrotorEnvMultiBatched
+    env = QuadrotorEnvMultiBatched(num_envs=64, num_agents=4, ep_time=0.2, neighbor_visible_num=2, quads_mode='mix', seed=5)
+    assert env.device_scenario == 'mix'
+    env.reset()
+    seen = set()
+    for t in range(64):
+        env.step(torch.rand((256, 4), device='cuda') * 2 - 1)
+        if (t + 1) % 21 == 0:
+            es, _ = env.engine.episode_stats()
+            seen |= set(es[:, 12].cpu().numpy().tolist())
+    assert seen == set(range(2, 10))                            # all eight obstacle-free scenarios were drawn
+    stats = env._episode_stats(0, 'Scenario_mix')
+    es, _ = env.engine.episode_stats()
+    name = L.SCENARIO_NAMES[int(es[0, 12])]
+    assert f'{name}/num_collisions' in stats[0] and f'{name}/distance_to_goal_1s' in stats[0]
     env.close()
 
 

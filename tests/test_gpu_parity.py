@@ -235,7 +235,11 @@ def test_device_side_swarm_vs_swarm_32_drones_split_and_single(monkeypatch):
         assert rep['dones'] >= 2
         outs.append(pair.engine.obs.clone())
         pair.engine.close()
-    assert torch.equal(outs[0], outs[1])
+    # same function, two instantiations: equal up to fp32 contraction differences over the <= 10 steps since the last
+    # teacher-forcing point
+    diff = (outs[0] - outs[1]).abs().max().item()
+    print('split vs single max |diff|', diff)
+    assert diff < 1e-4
 
 
 @pytest.mark.parametrize('split', ['0', '1'])
