@@ -222,7 +222,7 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
 // Copy the next-episode tables into the live episode of one env and respawn its drones
 // (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).  Called by ALL lanes of a warp (the branch around it is
 // warp-uniform); `do_reset` is per env.  Sets nvel to the velocity the neighbour block must see.
-template <int NP>
+template <int NP, bool SCN>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
                                           float nvel[3], int& scn_next) {
@@ -243,7 +243,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
                                                        st.obst + (long long)env * p.M);
             s.goal[0] = ep.goal.x; s.goal[1] = ep.goal.y; s.goal[2] = ep.goal.z;
             spawn = ep.spawn;
-        } else if (p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST) {
+        } else if (SCN && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST) {
             // goal formation of the env's scenario, drawn on the device; drones spawn around their goals
             const ScnOut o = scenario_reset(key, p.scenario, p.N, i, st, env);
             s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
@@ -308,7 +308,9 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 // sensor noise while the physics warp integrates, then builds the observation rows from the hand-off arrays in shared
 // memory — speculatively from the post-integration state, re-done only in the rare steps where a contact response or a
 // reset changed it.  The two halves of a drone's ~2.7 k-instruction dependency chain overlap.
-template <int NP, bool SPLIT>
+// SCN = true: the env's goals come from the device-side scenario family (qs_scenario.cuh); the other instantiations do
+// not carry that code (instruction-cache footprint of the hot loop: +1.3 % step time on c3 when it was compiled in).
+template <int NP, bool SPLIT, bool SCN>
 __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ float2 s_obst[];
     const DevState& st = p.st;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
     }
     // device-side scenarios: the tick of the env's next goal event (qs_scenario.cuh); never for the other scenarios
-    const bool dev_scn = p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST;
+    constexpr bool dev_scn = SCN;
     int scn_next = SCN_NEVER;
     if (dev_scn && env_ok && role == 0) scn_next = st.scn_i[env].z;
     if (SPLIT && role == 1) {
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
                 o[QS_STAT_SCENARIO] = dev_scn ? st.scn_i[env].x : p.scenario;
             }
-            reset_env<NP>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next);
+            reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next);
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     float nvel[3] = {0.f, 0.f, 0.f};
     // every lane of the warp takes part in the shuffles below; lanes of unmasked envs write nothing
     int scn_next = SCN_NEVER;
-    reset_env<NP>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next);
+    reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next);
     if (env_ok && i == 0) {
         int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) c[k] = 0;

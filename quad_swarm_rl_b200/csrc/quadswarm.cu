@@ -117,6 +117,7 @@ __global__ void k_set_goals(DevState st, int E, int N, const uint8_t* mask, cons
         st.slots[SL_GOAL * st.a_pad + t] = make_float4(goals[3 * t], goals[3 * t + 1], goals[3 * t + 2], 0.f);
 }
 
+static_assert(QS_STATE_ENV_I32 >= 4 + QS_NUM_ENV_STATS + 16, "env state row too short");
 __global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_t* au, int32_t* ei, float* obst) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long A = (long long)E * N;
@@ -153,6 +154,7 @@ __global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_
             sc[4 + 4 * q] = __float_as_int(f.x); sc[5 + 4 * q] = __float_as_int(f.y);
             sc[6 + 4 * q] = __float_as_int(f.z); sc[7 + 4 * q] = __float_as_int(f.w);
         }
+        for (int k = 4 + QS_NUM_ENV_STATS + 16; k < QS_STATE_ENV_I32; ++k) e[k] = 0;      // reserved
     }
     if (obst != nullptr && t < (long long)E * M) {
         const float2 ob = st.obst[t];
@@ -266,8 +268,11 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     cudaError_t lerr = cudaSuccess;
     int rc = dispatch_np(h->NP, [&](auto np) {
         constexpr int NPv = decltype(np)::value;
-        if (split) lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true>, p);
-        else lerr = cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false>, p);
+        const bool scn = p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST;
+        if (split) lerr = scn ? cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true, true>, p)
+                              : cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true, false>, p);
+        else lerr = scn ? cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false, true>, p)
+                        : cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false, false>, p);
         return QS_OK;
     });
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
