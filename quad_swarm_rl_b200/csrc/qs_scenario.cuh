@@ -184,8 +184,9 @@ __device__ __forceinline__ void scn_store(const DevState& st, int env, const Scn
 }
 __device__ __forceinline__ ScnState scn_load(const DevState& st, int env) {
     ScnState s;
-    const int4 a = st.scn_i[env];
-    const float4 b = st.scn_f[3 * (long long)env + 0], c = st.scn_f[3 * (long long)env + 1], d = st.scn_f[3 * (long long)env + 2];
+    const int4 a = QS_LD(st.scn_i + env);
+    const float4 b = QS_LD(st.scn_f + 3 * (long long)env + 0), c = QS_LD(st.scn_f + 3 * (long long)env + 1),
+                 d = QS_LD(st.scn_f + 3 * (long long)env + 2);
     s.mode = a.x; s.period = a.y; s.next = a.z; s.f = a.w & 0xff; s.growing = (a.w >> 8) & 1;
     s.size = b.x; s.layer = b.y; s.hi = b.z; s.speed = b.w;
     s.c1.x = c.x; s.c1.y = c.y; s.c1.z = c.z; s.c2.x = d.x; s.c2.y = d.y; s.c2.z = d.z;

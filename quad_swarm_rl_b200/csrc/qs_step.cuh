@@ -232,7 +232,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
         if (tick_before_reset > 0) {
             nvel[0] = s.vel[0]; nvel[1] = s.vel[1]; nvel[2] = s.vel[2];
         } else {
-            const float4 sv = st.slots[SL_STALE_VEL * st.a_pad + a];
+            const float4 sv = QS_LD(st.slots + SL_STALE_VEL * st.a_pad + a);
             nvel[0] = sv.x; nvel[1] = sv.y; nvel[2] = sv.z;
         }
         st.slots[SL_STALE_VEL * st.a_pad + a] = make_float4(nvel[0], nvel[1], nvel[2], 0.f);
@@ -282,6 +282,30 @@ __device__ __noinline__ void bar_sync(int id) {
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
+// running episode counter += v (L2 read: see load_agent)
+__device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { c[k] = QS_LD(c + k) + v; }
+
+// ---- per-block hand-over between consecutive step grids (pdl_mode 3) ----
+// Envs are independent, so block b of step t+1 only needs block b of step t.  Every step launch carries the programmatic
+// stream-serialization attribute; instead of griddepcontrol.wait (a grid-wide barrier: every step then costs the launch
+// latency plus the SLOWEST warp of the grid) a block waits for its own predecessor's `ready` word, takes it, and only
+// then lets the next grid start launching — so at most two step grids overlap and a block of step t+2 can never see the
+// word block b(t) left for b(t+1).  The writer publishes with barrier + __threadfence + st.release; the reader acquires
+// and reads the state with ld.global.cg (L1 is not coherent across the grids).  Any other kernel / copy on the stream
+// never triggers early, so it still sees, and is seen by, whole step grids.
+__device__ __forceinline__ void handover_acquire(int* ready) {
+    int v = 0, spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+        if (v == 0) __nanosleep(40);
+    } while (v == 0 && ++spins < (1 << 24));          // ~1 s: a lost hand-over must not hang the GPU
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(0) : "memory");
+}
+__device__ __forceinline__ void handover_release(int* ready) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(1) : "memory");
+}
+
 // physics warp -> shared hand-off arrays
 __device__ __forceinline__ void hand_store(float* hand, int lane, const Agent& s, const float nvel[3]) {
     hand[32 * H_PX + lane] = s.pos[0]; hand[32 * H_PY + lane] = s.pos[1]; hand[32 * H_PZ + lane] = s.pos[2];
@@ -310,7 +334,9 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 // reset changed it.  The two halves of a drone's ~2.7 k-instruction dependency chain overlap.
 // SCN = true: the env's goals come from the device-side scenario family (qs_scenario.cuh); the other instantiations do
 // not carry that code (instruction-cache footprint of the hot loop: +1.3 % step time on c3 when it was compiled in).
-template <int NP, bool SPLIT, bool SCN>
+// HO = true: per-block hand-over between consecutive step grids instead of the grid-wide wait (handover_acquire above);
+// chosen by the launcher when a step grid does not fit the GPU in one wave or the split shape is used.
+template <int NP, bool SPLIT, bool SCN, bool HO>
 __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ float2 s_obst[];
     const DevState& st = p.st;
@@ -330,8 +356,14 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     // state; the trigger that lets the NEXT step's grid start launching is issued just before this grid's final stores
     // (mode 2, default: hides ~0.3 us of launch latency per step; triggering at kernel start, mode 1, is 2 us SLOWER
     // because the early grid competes for issue slots while it spins).  Without the launch attribute both are no-ops.
-    if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (HO) {
+        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x);
+        __syncthreads();
+        asm volatile("griddepcontrol.launch_dependents;");
+    } else {
+        if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
     float2* s_obst_env = s_obst + env_local * p.M;
@@ -342,13 +374,13 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
 
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
-    if (valid && role == 0) load_agent(st, a, s);          // state loads are issued before the pillar staging barrier
+    if (valid && role == 0) load_agent<HO>(st, a, s);      // state loads are issued before the pillar staging barrier
     // stage this block's pillar tables (contiguous [envs_per_block][M] float2) in shared memory
     if (p.use_obst) {
         const long long base = (long long)blockIdx.x * envs_per_block * p.M;
         const long long total = (long long)p.E * p.M;
         for (int k = threadIdx.x; k < envs_per_block * p.M; k += blockDim.x)
-            if (base + k < total) s_obst[k] = st.obst[base + k];
+            if (base + k < total) s_obst[k] = ld_state<HO>(st.obst + base + k);
         __syncthreads();
     }
     if (!valid) {
@@ -361,13 +393,13 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         s.flags = 0u; s.prev_col = 0u;
     }
     if (env_ok) {
-        const int4 c = st.env_ctr[env];
+        const int4 c = ld_state<HO>(st.env_ctr + env);
         ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
     }
     // device-side scenarios: the tick of the env's next goal event (qs_scenario.cuh); never for the other scenarios
     constexpr bool dev_scn = SCN;
     int scn_next = SCN_NEVER;
-    if (dev_scn && env_ok && role == 0) scn_next = st.scn_i[env].z;
+    if (dev_scn && env_ok && role == 0) scn_next = QS_LD(st.scn_i + env).z;
     if (SPLIT && role == 1) {
         // ============================ observer warp ============================
         const int gbase = lane & ~(NP - 1);
@@ -409,7 +441,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 // a reset replaced this env's pillars: the physics warp wrote them to global memory only, the observer
                 // refreshes the shared-memory table (the physics warp reads it again only after barrier 3)
                 if (hf & HF_RESET) {
-                    for (int m = i; m < p.M; m += NP) s_obst_env[m] = st.obst[(long long)env * p.M + m];
+                    for (int m = i; m < p.M; m += NP) s_obst_env[m] = QS_LD(st.obst + (long long)env * p.M + m);
                 }
                 __syncwarp();
             }
@@ -429,6 +461,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             bar_sync(3);                                              // hand-off arrays and tile are free again
         }
         if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");
+        if (HO) bar_sync(4);                                          // the physics warp publishes the block's state
         return;
     }
 
@@ -628,18 +661,18 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             const bool any_event = col_curr_tick > 0 || n_obst > 0 || ((floor_m | wall_m | ceil_m | room_m) != 0u && settled);
             if (any_event && i == 0 && env_ok) {
                 int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
-                c[QS_STAT_NUM_COLLISIONS] += col_curr_tick;
-                if (col_curr_tick > 0 && settled) c[QS_STAT_NUM_COLLISIONS_AFTER_SETTLE] += col_curr_tick;
-                if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) c[QS_STAT_NUM_COLLISIONS_FINAL_5S] += col_curr_tick;
-                c[QS_STAT_NUM_COLLISIONS_OBST] += n_obst;
+                cnt_add(c, QS_STAT_NUM_COLLISIONS, col_curr_tick);
+                if (col_curr_tick > 0 && settled) cnt_add(c, QS_STAT_NUM_COLLISIONS_AFTER_SETTLE, col_curr_tick);
+                if (col_curr_tick > 0 && (float)time_remain <= p.final_steps) cnt_add(c, QS_STAT_NUM_COLLISIONS_FINAL_5S, col_curr_tick);
+                cnt_add(c, QS_STAT_NUM_COLLISIONS_OBST, n_obst);
                 if (settled) {
-                    c[QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE] += n_obst;
-                    c[QS_STAT_NUM_COLLISIONS_OBST_3_5] += __popc(f35);
-                    c[QS_STAT_NUM_COLLISIONS_OBST_5] += __popc(f5);
-                    c[QS_STAT_NUM_COLLISIONS_ROOM] += __popc(room_m);
-                    c[QS_STAT_NUM_COLLISIONS_FLOOR] += __popc(floor_m);
-                    c[QS_STAT_NUM_COLLISIONS_WALL] += __popc(wall_m);
-                    c[QS_STAT_NUM_COLLISIONS_CEILING] += __popc(ceil_m);
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_OBST_AFTER_SETTLE, n_obst);
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_OBST_3_5, __popc(f35));
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_OBST_5, __popc(f5));
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_ROOM, __popc(room_m));
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_FLOOR, __popc(floor_m));
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_WALL, __popc(wall_m));
+                    cnt_add(c, QS_STAT_NUM_COLLISIONS_CEILING, __popc(ceil_m));
                 }
             }
         }
@@ -658,7 +691,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             const int len = p.ep_len + 1;
             const int w5 = min(len, 500);
             if (valid && ctr.tick > len - w5) {
-                float4 sums = st.slots[SL_DIST_SUMS * st.a_pad + a];
+                float4 sums = ld_state<HO>(st.slots + SL_DIST_SUMS * st.a_pad + a);
                 if (ctr.tick > len - min(len, 100)) sums.x += dist;
                 if (ctr.tick > len - min(len, 300)) sums.y += dist;
                 sums.z += dist;
@@ -768,7 +801,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         const bool do_reset = done && env_ok;
         if (__any_sync(0xffffffffu, do_reset)) {          // warp-uniform branch
             if (do_reset && valid) {
-                const float4 sums = st.slots[SL_DIST_SUMS * st.a_pad + a];
+                const float4 sums = QS_LD(st.slots + SL_DIST_SUMS * st.a_pad + a);
                 const int len = p.ep_len + 1;
                 const uint32_t fbits = ((s.flags & QS_FLAG_NO_COL_AGENT) ? 1u : 0u) | ((s.flags & QS_FLAG_NO_COL_OBST) ? 2u : 0u) |
                                        ((s.flags & QS_FLAG_REACHED_GOAL) ? 4u : 0u);
@@ -778,9 +811,9 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             if (do_reset && i == 0) {
                 int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
                 int32_t* o = st.stats_env + (long long)env * QS_NUM_ENV_STATS;
-                for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = c[k]; c[k] = 0; }
+                for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = QS_LD(c + k); c[k] = 0; }
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
-                o[QS_STAT_SCENARIO] = dev_scn ? st.scn_i[env].x : p.scenario;
+                o[QS_STAT_SCENARIO] = dev_scn ? QS_LD(st.scn_i + env).x : p.scenario;
             }
             reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next);
             if (do_reset) {
@@ -836,6 +869,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
     if (valid) store_agent(st, a, s, goal_dirty);
     if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
+    if (HO) {
+        if (SPLIT) bar_sync(4); else __syncthreads();
+        if (threadIdx.x == 0) handover_release(st.ready + blockIdx.x);
+    }
 }
 
 // Explicit reset of the masked envs: QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411.

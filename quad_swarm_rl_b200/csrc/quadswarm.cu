@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "qs_step.cuh"
 
@@ -23,6 +24,8 @@ struct QsHandle {
     float rew[QS_NUM_REW_COEFF];
     int64_t launches;
     int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
+    int pdl_env;          // QS_PDL at the first step launch (-2 = not read yet, -1 = unset)
+    int handover;         // -1 not decided yet, 0 grid-wide wait between step grids, 1 per-block hand-over (launch_step)
     // staging for the *_host entry points (pinned host + device mirrors)
     float *d_actions, *d_obs, *d_rewards, *d_terms;
     uint8_t *d_dones, *d_mask;
@@ -254,9 +257,43 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     p.smem_tile_off = (int)(smem / sizeof(float));
     if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
     if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
-    // Programmatic dependent launch: QS_PDL = 0 off, 1 trigger at kernel start (measured 2 us slower), 2 (default) trigger
-    // before the final stores (measured 0.2-0.4 us faster per step on c3; profiles/r01_notes.md)
-    static const int pdl_mode = [] { const char* e = getenv("QS_PDL"); const int m = e ? atoi(e) : 2; return (m < 0 || m > 2) ? 2 : m; }();
+    // Programmatic dependent launch between consecutive step grids (QS_PDL overrides; default -1 = choose per handle):
+    //   0 off; 1 grid-wide wait, trigger at kernel start (measured 2 us slower); 2 grid-wide wait, trigger before the final
+    //   stores (0.2-0.4 us faster per step than 0); 3 per-block hand-over, no grid-wide wait (qs_step.cuh).
+    // Measured (profiles/r01_notes.md): 3 wins when a step grid needs more than one wave of CTAs (c4: 29.3 -> 20.1 us,
+    // 16384 x 8 drones: 22.4 -> 19.8 us) and for the split shape (c2: 7.18 -> 6.99 us); for a single-wave grid whose
+    // warps run in lock-step anyway (c3) its acquire / release costs what the hidden launch latency saves, so 2 stays.
+    if (h->pdl_env == -2) {          // read once per handle
+        const char* e = getenv("QS_PDL");
+        const int m = e ? atoi(e) : -1;
+        h->pdl_env = (m < -1 || m > 3) ? -1 : m;
+    }
+    const int pdl_env = h->pdl_env;
+    using KernelFn = void (*)(StepParams);
+    const bool scn = p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST;
+    KernelFn fn_wait = nullptr, fn_ho = nullptr;
+    int rc = dispatch_np(h->NP, [&](auto np) {
+        constexpr int NPv = decltype(np)::value;
+        if (split) {
+            fn_wait = scn ? (KernelFn)qs_step_kernel<NPv, true, true, false> : (KernelFn)qs_step_kernel<NPv, true, false, false>;
+            fn_ho = scn ? (KernelFn)qs_step_kernel<NPv, true, true, true> : (KernelFn)qs_step_kernel<NPv, true, false, true>;
+        } else {
+            fn_wait = scn ? (KernelFn)qs_step_kernel<NPv, false, true, false> : (KernelFn)qs_step_kernel<NPv, false, false, false>;
+            fn_ho = scn ? (KernelFn)qs_step_kernel<NPv, false, true, true> : (KernelFn)qs_step_kernel<NPv, false, false, true>;
+        }
+        return QS_OK;
+    });
+    if (rc != QS_OK) return rc;
+    if (h->handover < 0) {
+        if (pdl_env >= 0) h->handover = pdl_env == 3;
+        else {
+            int per_sm = 0, sms = 0;
+            QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_ho, kBlock, smem));
+            QS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->handover = split || (long long)grid > (long long)per_sm * sms;
+        }
+    }
+    const int pdl_mode = h->handover ? 3 : (pdl_env >= 0 ? pdl_env : 2);
     const bool use_pdl = pdl_mode != 0;
     p.pdl_mode = pdl_mode;
     cudaLaunchConfig_t lc = {};
@@ -265,18 +302,8 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t lerr = cudaSuccess;
-    int rc = dispatch_np(h->NP, [&](auto np) {
-        constexpr int NPv = decltype(np)::value;
-        const bool scn = p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST;
-        if (split) lerr = scn ? cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true, true>, p)
-                              : cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, true, false>, p);
-        else lerr = scn ? cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false, true>, p)
-                        : cudaLaunchKernelEx(&lc, qs_step_kernel<NPv, false, false>, p);
-        return QS_OK;
-    });
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, h->handover ? fn_ho : fn_wait, p);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
-    if (rc != QS_OK) return rc;
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
     return QS_OK;
@@ -339,6 +366,8 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     {
         const char* e = getenv("QS_SPLIT");
         h->split_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+        h->handover = -1;
+        h->pdl_env = -2;
     }
     h->a_pad = (h->A + 31) / 32 * 32;
     // QuadrotorEnvMulti defaults, quadrotor_multi.py:91-94
@@ -363,6 +392,11 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.stats_agent, sizeof(float4) * A);
     QS_ALLOC0(st.scn_i, sizeof(int4) * E);
     QS_ALLOC0(st.scn_f, sizeof(float4) * 3 * E);
+    {   // per-block hand-over words (at most one block per env), all "ready"
+        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * E));
+        std::vector<int> ones((size_t)E, 1);
+        QS_CUDA(cudaMemcpy(st.ready, ones.data(), sizeof(int) * E, cudaMemcpyHostToDevice));
+    }
     // rotation = identity so that a never-reset env still holds a valid state
     {
         std::string tmp;
@@ -407,7 +441,7 @@ extern "C" int qs_destroy(QsHandle* h) {
     DevState& st = h->st;
     cudaFree(st.slots); cudaFree(st.env_ctr); cudaFree(st.env_cnt); cudaFree(st.obst); cudaFree(st.next_goal);
     cudaFree(st.next_spawn); cudaFree(st.next_obst); cudaFree(st.stats_env); cudaFree(st.stats_agent);
-    cudaFree(st.scn_i); cudaFree(st.scn_f);
+    cudaFree(st.scn_i); cudaFree(st.scn_f); cudaFree(st.ready);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_rewards); cudaFree(h->d_terms); cudaFree(h->d_dones);
     cudaFree(h->d_mask);
     cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);

@@ -245,6 +245,52 @@ def test_batched_env_mix_on_device_reports_scenario_names():
     env.close()
 
 
+C4 = dict(num_agents=32, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega')
+
+
+@pytest.mark.parametrize('name,kw,E,dev_scn,pdl', [
+    ('c3_handover', C3, 4096, 'o_random', '3'), ('c3_auto', C3, 4096, 'o_random', None), ('c2_split_handover', C2, 1024, 'swap_goals', None),
+    ('c4_multiwave_handover', C4, 2048, 'swarm_vs_swarm', None), ('c3_small', C3, 37, None, '3'), ('c3_wait', C3, 300, None, '2')])
+def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, monkeypatch):
+    """Consecutive step launches overlap on the GPU (programmatic dependent launch with a per-block hand-over instead of a
+    grid-wide wait).  Replaying a CUDA graph of 96 step launches — no host gap between them — must give, bit for bit,
+    what ONE launch that keeps the env block in registers gives, over several replays and across auto-resets."""
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    if pdl is not None:
+        monkeypatch.setenv('QS_PDL', pdl)           # read by each engine at its first step launch
+    T, R = 96, 3
+    N = kw['num_agents']
+    mk = lambda: (QuadSwarmEngine(num_envs=E, seed=9, ep_time=1.0, device_scenario=dev_scn, **kw) if dev_scn else _engine(E, kw, ep_time=1.0)[0])
+    e1, e2 = mk(), mk()
+    a = _actions(T, E, N)
+    st = torch.cuda.Stream()
+    obs = torch.empty((T, E, N, e1.D), device='cuda'); rew = torch.empty((T, E, N), device='cuda')
+    dn = torch.empty((T, E, N), dtype=torch.uint8, device='cuda')
+    with torch.cuda.stream(st):
+        e1.reset()
+        for t in range(3):                                   # warm-up launches before capture (not part of the comparison)
+            e1.step(a[t], obs_out=obs[t], rewards_out=rew[t], dones_out=dn[t])
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for t in range(T):
+                e1.step(a[t], obs_out=obs[t], rewards_out=rew[t], dones_out=dn[t])
+    e2.reset()
+    for t in range(3):
+        e2.step(a[t])
+    for r in range(R):
+        g.replay()
+        torch.cuda.synchronize()
+        o2, r2, d2 = e2.rollout(a)
+        torch.cuda.synchronize()
+        assert torch.equal(obs, o2) and torch.equal(rew, r2) and torch.equal(dn, d2), f'replay {r}'
+        s1, s2 = e1.get_state(), e2.get_state()
+        for k in ('agent_f32', 'agent_u32', 'env_i32'):
+            assert torch.equal(s1[k], s2[k]), (r, k)
+    assert int(dn.sum()) > 0 or T * R < e1.ep_len
+    e1.close(); e2.close()
+
+
 def _ref_style_env(**over):
     from quad_swarm_rl_b200.env import QuadrotorEnvMulti
     kw = dict(num_agents=8, ep_time=4.0, rew_coeff=None, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=6,
