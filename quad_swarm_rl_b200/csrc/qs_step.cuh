@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     } else {
         if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (p.pdl_mode == 4) asm volatile("griddepcontrol.launch_dependents;");      // trigger once the predecessor is done
     }
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp

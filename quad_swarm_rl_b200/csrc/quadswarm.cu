@@ -266,7 +266,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     if (h->pdl_env == -2) {          // read once per handle
         const char* e = getenv("QS_PDL");
         const int m = e ? atoi(e) : -1;
-        h->pdl_env = (m < -1 || m > 3) ? -1 : m;
+        h->pdl_env = (m < -1 || m > 4) ? -1 : m;
     }
     const int pdl_env = h->pdl_env;
     using KernelFn = void (*)(StepParams);
