@@ -49,7 +49,7 @@ extern "C" {
 /* The obstacle-free scenario family, generated and TICKED on the device (formation picks, goal formations, the timed
  * goal switches every 4-6 s, per-tick goal motion; `mix` draws one of the eight per episode; scenarios/base.py:39-150,
  * dynamic_same_goal.py, dynamic_diff_goal.py, swap_goals.py, dynamic_formations.py, ep_lissajous3D.py,
- * swarm_vs_swarm.py, mix.py:37-93).  They need use_obstacles = 0.  The ids 2..9 are contiguous on purpose. */
+ * swarm_vs_swarm.py, mix.py:37-93).  Ids 2..9 need use_obstacles = 0 and are contiguous on purpose. */
 #define QS_SCENARIO_STATIC_SAME_GOAL 2
 #define QS_SCENARIO_STATIC_DIFF_GOAL 3
 #define QS_SCENARIO_DYNAMIC_SAME_GOAL 4
@@ -58,7 +58,10 @@ extern "C" {
 #define QS_SCENARIO_DYNAMIC_FORMATIONS 7
 #define QS_SCENARIO_EP_LISSAJOUS3D 8
 #define QS_SCENARIO_SWARM_VS_SWARM 9
-#define QS_SCENARIO_MIX 10
+#define QS_SCENARIO_MIX 10                  /* use_obstacles = 0: one of 2..9 per episode; = 1: o_random or o_static_same_goal (mix.py:45-57) */
+/* obstacles/o_static_same_goal.py: pillars and spawn cells as o_random, one common goal above the centre of the
+ * largest free square of the pillar grid (o_base.py:123-153), approch_goal_metric 1.0.  Needs use_obstacles. */
+#define QS_SCENARIO_O_STATIC_SAME_GOAL 11
 #define QS_SCENARIO_DEVICE_FAMILY_FIRST QS_SCENARIO_STATIC_SAME_GOAL
 
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a

@@ -58,19 +58,57 @@ def o_random_episode(draws, n_agents, M, L, W):
     return goals, spawn, obst
 
 
+def largest_free_square_cell(mask, L, W):
+    """o_base.py:123-153 on the occupancy bit mask (bit row * W + col); quirks as in the kernels' twin function."""
+    dp = [[0] * W for _ in range(L)]
+    for j in range(W):
+        dp[0][j] = (mask >> j) & 1
+    best = cx = cy = 0
+    for i in range(1, L):
+        dp[i][0] = (mask >> (i * W)) & 1
+        for j in range(1, W):
+            if not (mask >> (i * W + j)) & 1:
+                dp[i][j] = min(dp[i - 1][j], dp[i][j - 1], dp[i - 1][j - 1]) + 1
+                if dp[i][j] > best:
+                    best = dp[i][j]
+                    cx, cy = i - (best - 1) // 2, j - (best - 1) // 2
+    return cx * W + cy
+
+
+O_RANDOM, O_MIX, O_STATIC_SAME_GOAL = 1, 10, 11
+
+
 class DeviceORandomSource:
-    """Episode source for OracleEnv that mirrors QS_SCENARIO_O_RANDOM (needs a PhiloxRng)."""
+    """Episode source for OracleEnv that mirrors the device-side obstacle scenarios (needs a PhiloxRng):
+    QS_SCENARIO_O_RANDOM (default), QS_SCENARIO_O_STATIC_SAME_GOAL, or QS_SCENARIO_MIX over the two."""
 
-    approch_goal_metric = 0.5
-
-    def __init__(self, L=8, W=8):
+    def __init__(self, L=8, W=8, scenario=O_RANDOM):
         self.L, self.W = L, W
+        self.scenario = {'o_random': O_RANDOM, 'mix': O_MIX, 'o_static_same_goal': O_STATIC_SAME_GOAL}.get(scenario, scenario)
+        self.mode = O_RANDOM if self.scenario == O_MIX else self.scenario
+
+    @property
+    def approch_goal_metric(self):
+        return 1.0 if self.mode == O_STATIC_SAME_GOAL else 0.5          # o_base.py:16, o_random.py:10
 
     def name(self):
-        return 'Scenario_o_random'
+        return 'Scenario_o_static_same_goal' if self.mode == O_STATIC_SAME_GOAL else 'Scenario_o_random'
 
     def reset(self, env):
-        return o_random_episode(env.rng.draws, env.num_agents, env.cfg.num_obstacles, self.L, self.W)
+        d = env.rng.draws
+        goals, spawn, obst = o_random_episode(d, env.num_agents, env.cfg.num_obstacles, self.L, self.W)
+        if self.scenario == O_MIX:
+            self.mode = O_RANDOM if _pick(d, 321, 2) == 0 else O_STATIC_SAME_GOAL
+        if self.mode == O_STATIC_SAME_GOAL:
+            mask = 0
+            for xy in obst:                                    # rebuild the occupancy mask from the pillar cells
+                cid = int(round(xy[0] - 0.5 + self.L // 2))
+                rid = self.W - 1 - int(round(xy[1] - 0.5 + self.W // 2))
+                mask |= 1 << (rid * self.W + cid)
+            c = _cell_center(largest_free_square_cell(mask, self.L, self.W), self.L, self.W)
+            z = 1.5 + (3.0 - 1.5) * d.uniform(px.SITE_SCENARIO_U, 0, 0, 320)
+            goals = np.tile(np.array([c[0], c[1], z]), (env.num_agents, 1))
+        return goals, spawn, obst
 
     def step(self, env, tick):
         return None

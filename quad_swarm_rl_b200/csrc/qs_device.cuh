@@ -566,11 +566,33 @@ __device__ __forceinline__ float2 cell_center(int cell, int L, int W) {
     return make_float2((float)cid + 0.5f - (float)(L / 2), (float)(W - 1 - rid) + 0.5f - (float)(W / 2));
 }
 
-struct ORandomEpisode { V3 spawn, goal; };
+struct ORandomEpisode { V3 spawn, goal; int mode; };
+
+// o_base.py:123-153 (max_square_area_center): dynamic programme over the pillar map; returns the map cell (row * W + col)
+// at the centre of the largest free square.  Reference quirks kept: the first row / column of the table hold the MAP
+// values (an occupied border cell counts as a square of size 1), only strictly larger squares replace the best one.
+__device__ __noinline__ int largest_free_square_cell(unsigned long long mask, int L, int W) {
+    unsigned char dp[64];
+    int best = 0, cx = 0, cy = 0;
+    for (int j = 0; j < W; ++j) dp[j] = (unsigned char)((mask >> j) & 1ull);
+    for (int i = 1; i < L; ++i) {
+        dp[i * W] = (unsigned char)((mask >> (i * W)) & 1ull);
+        for (int j = 1; j < W; ++j) {
+            int v = 0;
+            if (!((mask >> (i * W + j)) & 1ull)) {
+                v = min(min((int)dp[(i - 1) * W + j], (int)dp[i * W + j - 1]), (int)dp[(i - 1) * W + j - 1]) + 1;
+                if (v > best) { best = v; cx = i - (best - 1) / 2; cy = j - (best - 1) / 2; }
+            }
+            dp[i * W + j] = (unsigned char)v;
+        }
+    }
+    return cx * W + cy;
+}
 
 // pillar table of the env -> `obst_out[m]` for m = lane, lane + stride, ... ; this lane's spawn / goal returned
-__device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int i, int n_agents, int M, int L, int W, int lane_i, int stride,
-                                                        float2* obst_smem, float2* obst_glob) {
+// `scenario`: QS_SCENARIO_O_RANDOM, QS_SCENARIO_O_STATIC_SAME_GOAL or QS_SCENARIO_MIX (one of the two per episode, slot 321).
+__device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario, int i, int n_agents, int M, int L, int W, int lane_i,
+                                                        int stride, float2* obst_smem, float2* obst_glob) {
     const int cells = L * W;
     unsigned long long mask = 0ull;
 #pragma unroll 1
@@ -585,6 +607,8 @@ __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int i, int n
         }
     }
     ORandomEpisode ep;
+    ep.mode = scenario;
+    if (scenario == QS_SCENARIO_MIX) ep.mode = scenario_pick(key, 321, 2) == 0 ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
     const int free_cells = cells - M;
     unsigned long long ms = mask, mg = mask;
 #pragma unroll 1
@@ -600,6 +624,10 @@ __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int i, int n
             ep.spawn.x = a.x; ep.spawn.y = a.y; ep.spawn.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 128 + k);
             ep.goal.x = b.x; ep.goal.y = b.y; ep.goal.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 256 + k);
         }
+    }
+    if (ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL) {          // one goal for the whole swarm (o_static_same_goal.py:44-52)
+        const float2 c = cell_center(largest_free_square_cell(mask, L, W), L, W);
+        ep.goal.x = c.x; ep.goal.y = c.y; ep.goal.z = 1.5f + (3.0f - 1.5f) * scenario_u(key, 320);
     }
     return ep;
 }

@@ -225,7 +225,7 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
 template <int NP, bool SCN>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
-                                          float nvel[3], int& scn_next) {
+                                          float nvel[3], int& scn_next, float& approach) {
     const DevState& st = p.st;
     if (do_reset && valid) {
         // stale velocity (Appendix D-6): the multi-env's self.vel is only refreshed by step()
@@ -237,12 +237,20 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
         }
         st.slots[SL_STALE_VEL * st.a_pad + a] = make_float4(nvel[0], nvel[1], nvel[2], 0.f);
         V3 spawn;
-        if (p.scenario == QS_SCENARIO_O_RANDOM) {
-            // episode generated on the device; every valid lane also writes its share of the pillar table
-            const ORandomEpisode ep = o_random_episode(key, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, s_obst_env,
+        if (p.use_obst && p.scenario != QS_SCENARIO_HOST_TABLES) {
+            // o_random / o_static_same_goal / their mix: episode generated on the device; every valid lane also writes its
+            // share of the pillar table
+            const ORandomEpisode ep = o_random_episode(key, p.scenario, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, s_obst_env,
                                                        st.obst + (long long)env * p.M);
             s.goal[0] = ep.goal.x; s.goal[1] = ep.goal.y; s.goal[2] = ep.goal.z;
             spawn = ep.spawn;
+            if (p.scenario != QS_SCENARIO_O_RANDOM) {         // per-episode scenario id + its approch_goal_metric (o_base.py:16)
+                approach = ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL ? 1.0f : 0.5f;
+                if (i == 0) {
+                    st.scn_i[env] = make_int4(ep.mode, 0, SCN_NEVER, 0);
+                    st.scn_f[3 * (long long)env + 1] = make_float4(0.f, 0.f, 0.f, approach);
+                }
+            }
         } else if (SCN && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST) {
             // goal formation of the env's scenario, drawn on the device; drones spawn around their goals
             const ScnOut o = scenario_reset(key, p.scenario, p.N, i, st, env);
@@ -259,7 +267,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
         st.slots[SL_DIST_SUMS * st.a_pad + a] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (p.use_obst) {
-        if (do_reset && p.scenario != QS_SCENARIO_O_RANDOM) {
+        if (do_reset && p.scenario == QS_SCENARIO_HOST_TABLES) {
             for (int m = i; m < p.M; m += NP) {
                 const float2 ob = st.next_obst[(long long)env * p.M + m];
                 st.obst[(long long)env * p.M + m] = ob;
@@ -401,6 +409,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     constexpr bool dev_scn = SCN;
     int scn_next = SCN_NEVER;
     if (dev_scn && env_ok && role == 0) scn_next = QS_LD(st.scn_i + env).z;
+    // approch_goal_metric is a property of the episode's scenario where the obstacle scenarios are drawn on the device
+    const bool env_metric = p.use_obst && p.scenario > QS_SCENARIO_O_RANDOM;
+    float approach = p.approach_metric;
+    if (env_metric && env_ok && role == 0) approach = QS_LD(st.scn_f + 3 * (long long)env + 1).w;
     if (SPLIT && role == 1) {
         // ============================ observer warp ============================
         const int gbase = lane & ~(NP - 1);
@@ -687,7 +699,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         // goal-distance log and reached_goal, quadrotor_multi.py:542-546
         {
             const float m5 = (dist + s.ring[0] + s.ring[1] + s.ring[2] + s.ring[3]) * 0.2f;
-            if (ctr.tick >= 5 && m5 < p.approach_metric) s.flags |= QS_FLAG_REACHED_GOAL;
+            if (ctr.tick >= 5 && m5 < approach) s.flags |= QS_FLAG_REACHED_GOAL;
             s.ring[3] = s.ring[2]; s.ring[2] = s.ring[1]; s.ring[1] = s.ring[0]; s.ring[0] = dist;
             const int len = p.ep_len + 1;
             const int w5 = min(len, 500);
@@ -814,9 +826,9 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 int32_t* o = st.stats_env + (long long)env * QS_NUM_ENV_STATS;
                 for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = QS_LD(c + k); c[k] = 0; }
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
-                o[QS_STAT_SCENARIO] = dev_scn ? QS_LD(st.scn_i + env).x : p.scenario;
+                o[QS_STAT_SCENARIO] = (dev_scn || env_metric) ? QS_LD(st.scn_i + env).x : p.scenario;
             }
-            reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next);
+            reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next, approach);
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -914,7 +926,8 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     float nvel[3] = {0.f, 0.f, 0.f};
     // every lane of the warp takes part in the shuffles below; lanes of unmasked envs write nothing
     int scn_next = SCN_NEVER;
-    reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next);
+    float approach = p.approach_metric;
+    reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next, approach);
     if (env_ok && i == 0) {
         int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) c[k] = 0;

@@ -51,7 +51,7 @@ class QuadSwarmEngine:
         cfg.env_id_offset = int(env_id_offset)
         if device_scenario is not None and device_scenario not in L.DEVICE_SCENARIOS:
             raise ValueError(f"no device-side generator for scenario {device_scenario!r} (host tables handle it)")
-        if device_scenario is not None and (device_scenario == 'o_random') != bool(use_obstacles):
+        if device_scenario not in (None, 'mix') and (device_scenario in L.OBSTACLE_SCENARIOS) != bool(use_obstacles):
             raise ValueError(f"device-side scenario {device_scenario!r} does not match use_obstacles={use_obstacles}")
         cfg.scenario = L.DEVICE_SCENARIOS[device_scenario] if device_scenario is not None else L.SCENARIO_HOST_TABLES
         cfg.obst_grid = (C.c_int32 * 2)(int(obst_spawn_area[0]), int(obst_spawn_area[1]))

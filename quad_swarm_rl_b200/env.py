@@ -144,7 +144,10 @@ class _EnvBase:
             obst_size=obst_size, obst_spawn_area=obst_spawn_area, use_downwash=use_downwash, room_dims=room_dims,
             ep_time=ep_time, collision_hitbox_radius=collision_hitbox_radius,
             collision_falloff_radius=collision_falloff_radius, sense_noise=sense_noise, rew_coeff=rew_coeff,
-            seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario)
+            seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario,
+            # scenario.approch_goal_metric (o_base.py:16: 1.0 for the goal-sharing obstacle scenarios, else 0.5); with the
+            # host-side `mix` over obstacle scenarios the value of o_random is used for every episode
+            approch_goal_metric=1.0 if quads_mode == 'o_static_same_goal' else 0.5)
         self.device_scenario = device_scenario
         self.rew_coeff = self.engine.rew_coeff               # the live, mutable dict (reward_shaping.py:55-61 writes it)
         self.ep_len = self.engine.ep_len
@@ -422,7 +425,8 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         # device-side generators (no host work per episode or per tick): o_random with obstacles, the goal-formation
         # family and mix without; every other mode uses host tables
         dev_scn = None
-        if device_scenarios and quads_mode in L.DEVICE_SCENARIOS and (quads_mode == 'o_random') == bool(use_obstacles):
+        if device_scenarios and quads_mode in L.DEVICE_SCENARIOS and \
+                (quads_mode == 'mix' or (quads_mode in L.OBSTACLE_SCENARIOS) == bool(use_obstacles)):
             dev_scn = quads_mode
         super().__init__(num_envs, num_agents, ep_time, rew_coeff, obs_repr, neighbor_visible_num, neighbor_obs_type,
                          collision_hitbox_radius, collision_falloff_radius, use_obstacles, obst_density, obst_size,

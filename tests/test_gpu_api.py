@@ -223,6 +223,25 @@ def test_batched_env_and_dynamic_scenario(device_scenarios):
     env.close()
 
 
+def test_batched_env_obstacle_mix_on_device():
+    """The obstacle baseline's `--quads_mode=mix` with pillars (runs/obstacles/quad_obstacle_baseline.py:12): both obstacle
+    scenarios are drawn and generated on the device, no host work per episode."""
+    from quad_swarm_rl_b200.env import QuadrotorEnvMultiBatched
+    env = QuadrotorEnvMultiBatched(num_envs=48, num_agents=8, ep_time=0.2, neighbor_visible_num=2, quads_mode='mix', seed=9,
+                                   use_obstacles=True, obs_repr='xyz_vxyz_R_omega_floor', use_downwash=True)
+    assert env.device_scenario == 'mix' and env.engine.M == 12
+    env.reset()
+    for t in range(22):
+        obs, rew, term, trunc, _ = env.step(torch.rand((384, 4), device='cuda') * 2 - 1)
+    es, _ = env.engine.episode_stats()
+    assert set(es[:, 12].cpu().numpy().tolist()) == {1, 11}
+    goals = env.engine.get_state()['agent_f32'][..., 30:33].cpu().numpy()
+    same = np.array([np.all(g == g[0]) for g in goals])
+    assert same.any() and not same.all()                         # o_static_same_goal envs share one goal, o_random envs do not
+    assert torch.isfinite(obs).all()
+    env.close()
+
+
 def test_batched_env_mix_on_device_reports_scenario_names():
     """quads_mode='mix' with the device-side generators: every episode draws its scenario on the device; the single-env
     API reports it in the episode statistics' key prefix (reward_shaping.py:95-98 consumes those keys)."""

@@ -195,6 +195,44 @@ def test_device_side_o_random_generator_matches_twin():
     pair.engine.close()
 
 
+@pytest.mark.parametrize('scenario', ['o_static_same_goal', 'mix'])
+def test_device_side_obstacle_scenarios_match_twin(scenario):
+    """QS_SCENARIO_O_STATIC_SAME_GOAL and QS_SCENARIO_MIX with obstacles (o_random / o_static_same_goal drawn per episode,
+    mix.py:45-57): pillars, spawn cells, the common goal above the largest free square and the per-scenario
+    approch_goal_metric come from the kernels and equal the twin; reached-goal flags are compared bit for bit."""
+    from oracle.scenario_gen import DeviceORandomSource
+    from tests import parity_util as pu
+    kw = dict(C3, ep_time=0.5)
+    E = 10
+    pair = pu.DevicePair(E, kw, 8642, scenario, lambda: DeviceORandomSource(scenario=scenario))
+    seen, reached = set(), 0
+
+    def hook(p, t):
+        nonlocal reached
+        if t > 0 and t % 17 == 0:
+            fl = p.device_fields()['flags']
+            for e, o in enumerate(p.oracles):
+                if o.tick >= 6:
+                    assert np.array_equal((fl[e] & pu.L.FLAG_REACHED_GOAL) != 0, np.asarray(o.reached_goal, bool)), (t, e)
+                    reached += int(np.sum(o.reached_goal))
+                seen.add(o.source.mode)
+
+    rep = pu.run_parity(pair, 160, np.random.RandomState(6), resync=20, hook=hook)
+    assert rep['dones'] >= 3 * E
+    st = pair.engine.get_state()
+    obst_dev = st['obst_xy'].cpu().numpy()
+    goals_dev = st['agent_f32'][..., 30:33].cpu().numpy()
+    for e, o in enumerate(pair.oracles):
+        assert np.array_equal(obst_dev[e], o.obst_xy.astype(np.float32))
+        np.testing.assert_allclose(goals_dev[e], np.array([d.goal for d in o.drones]), rtol=1e-6)
+    es, _ = pair.engine.episode_stats()
+    ids = set(es[:, 12].cpu().numpy().tolist())
+    assert ids <= {1, 11} and (scenario == 'mix' or ids == {11})
+    assert seen == ({11} if scenario == 'o_static_same_goal' else {1, 11})
+    print('reached-goal flags compared while set:', reached)
+    pair.engine.close()
+
+
 DEVICE_FAMILY = ['static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals',
                  'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix']
 

@@ -163,3 +163,48 @@ def test_mix_draws_every_available_scenario():
         qo.OracleEnv(cfg1, qo.PhiloxRng(7), src, env_id=env_id).reset()
         single.add(src.s['mode'])
     assert single == {sg.STATIC_SAME_GOAL, sg.STATIC_DIFF_GOAL, sg.EP_LISSAJOUS3D, sg.DYNAMIC_SAME_GOAL}
+
+
+def test_largest_free_square_equals_host_generator():
+    """oracle/scenario_gen.py:largest_free_square_cell (the kernels' twin) against scenarios.py's restatement of
+    o_base.py:123-153, which runs on the reference's obst_map / cell_centers layout (replayed against the reference
+    in test_oracle_vs_reference.py: c3 golden case uses the same layout)."""
+    rs = np.random.RandomState(3)
+    cells = hs.grid_cell_centers(8, 8)
+    for trial in range(300):
+        M = rs.randint(1, 40)
+        occ = rs.choice(64, M, replace=False)
+        obst_map = np.zeros((8, 8))
+        mask = 0
+        for c in occ:
+            obst_map[c // 8, c % 8] = 1
+            mask |= 1 << int(c)
+        sc = hs.OStaticSameGoal(4, rng=np.random.RandomState(0), use_obstacles=True)
+        sc.obstacle_map, sc.cell_centers = obst_map, cells
+        want = sc._largest_free_square_center()[:2]
+        got = sg._cell_center(sg.largest_free_square_cell(mask, 8, 8), 8, 8)
+        assert np.allclose(got, want), (trial, got, want)
+
+
+@pytest.mark.parametrize('scenario', ['o_static_same_goal', 'mix'])
+def test_obstacle_twin_episode_semantics(scenario):
+    kw = dict(num_agents=8, obs_repr='xyz_vxyz_R_omega_floor', neighbor_visible_num=2, use_obstacles=True, ep_time=0.1)
+    cfg = pc.cfg_to_oracle(kw)
+    modes = set()
+    for env_id in range(12):
+        src = sg.DeviceORandomSource(scenario=scenario)
+        env = qo.OracleEnv(cfg, qo.PhiloxRng(11), src, env_id=env_id)
+        env.reset()
+        modes.add(src.mode)
+        goals = np.array([d.goal for d in env.drones])
+        pill = env.obst_xy
+        assert len({tuple(p) for p in pill}) == cfg.num_obstacles                 # distinct pillar cells
+        if src.mode == sg.O_STATIC_SAME_GOAL:
+            assert np.all(goals == goals[0]) and 1.5 <= goals[0, 2] <= 3.0 and src.approch_goal_metric == 1.0
+            assert src.name() == 'Scenario_o_static_same_goal'
+            assert np.abs(pill - goals[0, :2]).max(axis=1).min() >= 1.0 - 1e-9    # the goal cell itself is free
+        else:
+            assert len({tuple(g[:2]) for g in goals}) == 8 and src.approch_goal_metric == 0.5
+        for t in range(12):
+            env.step(np.zeros((8, 4)))
+    assert modes == ({sg.O_STATIC_SAME_GOAL} if scenario == 'o_static_same_goal' else {sg.O_RANDOM, sg.O_STATIC_SAME_GOAL})
