@@ -440,9 +440,12 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         obs = self._reset_all()
         return obs.view(self.num_agents, -1), {}
 
-    def step(self, actions):
+    def step(self, actions, with_terms=False):
+        """with_terms: also fill engine.rew_terms [E,N,QS_NUM_TERMS] (raw reward terms of this step, batched.py)."""
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.engine.device).reshape(self.num_envs, self.num_agents_per_env, 4)
-        obs, rew, done = self.engine.step(a.contiguous())
+        obs, rew, done = self.engine.step(a.contiguous(), with_terms=with_terms)
+        if self.device_scenario is not None:           # nothing to do on the host: episodes and goal events live in the kernels
+            return obs.view(self.num_agents, -1), rew.view(-1), done.view(-1).bool(), self._truncated, {}
         self._tick += 1
         finished = np.nonzero(self._tick > self.ep_len)[0]           # lock-step episodes: known on the host without a sync
         if len(finished):
