@@ -198,9 +198,9 @@ class BatchedExperienceReplay:
     def _ar(self):
         return torch.arange(self.E, device=self.engine.device)
 
-    def step(self, actions):
+    def step(self, actions, with_terms=True):
         env, eng = self.env, self.engine
-        obs, rew, term, trunc, infos = env.step(actions, with_terms=True)
+        obs, rew, term, trunc, infos = env.step(actions, with_terms=True)      # collisions are read from the raw terms
         E, N = self.E, env.num_agents_per_env
         obs3 = obs.view(E, N, -1)
         done = term.view(E, N)[:, 0]

@@ -186,6 +186,37 @@ def make_quadrotor_env_multi(cfg, render_mode=None, **kwargs):
     return QuadEnvCompatibility(env)
 
 
+def make_quadrotor_env_multi_batched(cfg, num_envs, env_id_offset=0):
+    """The same factory for a batched sampler: `num_envs` envs behind one object, CUDA tensors in and out, the wrappers
+    of quad_utils.py:67-110 in their batched form (batched.py).  Episodes, goal events, reward shaping statistics and the
+    collision-event replay all stay on the device."""
+    from .env import QuadrotorEnvMultiBatched
+    from .batched import BatchedRewardShaping, BatchedExperienceReplay
+    env = QuadrotorEnvMultiBatched(
+        num_envs=num_envs, num_agents=cfg.quads_num_agents, ep_time=cfg.quads_episode_duration,
+        rew_coeff=dict(DEFAULT_QUAD_REWARD_SHAPING['quad_rewards']), obs_repr=cfg.quads_obs_repr,
+        neighbor_visible_num=cfg.quads_neighbor_visible_num, neighbor_obs_type=cfg.quads_neighbor_obs_type,
+        collision_hitbox_radius=cfg.quads_collision_hitbox_radius, collision_falloff_radius=cfg.quads_collision_falloff_radius,
+        use_obstacles=cfg.quads_use_obstacles, obst_density=cfg.quads_obst_density, obst_size=cfg.quads_obst_size,
+        obst_spawn_area=cfg.quads_obst_spawn_area, use_downwash=cfg.quads_use_downwash, quads_mode=cfg.quads_mode,
+        room_dims=cfg.quads_room_dims, device=getattr(cfg, 'quads_device', 0), seed=getattr(cfg, 'seed', None),
+        env_id_offset=env_id_offset)
+    if cfg.replay_buffer_sample_prob > 0.0:                # quad_utils.py:67-70
+        env = BatchedExperienceReplay(env, cfg.replay_buffer_sample_prob, seed=getattr(cfg, 'seed', None) or 0)
+    reward_shaping = copy.deepcopy(DEFAULT_QUAD_REWARD_SHAPING)
+    reward_shaping['quad_rewards']['quadcol_bin'] = cfg.quads_collision_reward
+    reward_shaping['quad_rewards']['quadcol_bin_smooth_max'] = cfg.quads_collision_smooth_max_penalty
+    reward_shaping['quad_rewards']['quadcol_bin_obst'] = cfg.quads_obst_collision_reward
+    annealing = None
+    if cfg.anneal_collision_steps > 0:
+        names = {'quadcol_bin': cfg.quads_collision_reward, 'quadcol_bin_smooth_max': cfg.quads_collision_smooth_max_penalty,
+                 'quadcol_bin_obst': cfg.quads_obst_collision_reward}
+        for k in names:
+            reward_shaping['quad_rewards'][k] = 0.0
+        annealing = [AnnealSchedule(k, v, cfg.anneal_collision_steps) for k, v in names.items()]
+    return BatchedRewardShaping(env, reward_shaping_scheme=reward_shaping, annealing=annealing)
+
+
 def make_quadrotor_env(env_name, cfg=None, _env_config=None, render_mode=None, **kwargs):
     """Sample Factory env factory, same signature as swarm_rl/env_wrappers/quad_utils.py:113-117."""
     if env_name == 'quadrotor_multi':

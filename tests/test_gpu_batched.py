@@ -120,3 +120,34 @@ def test_batched_experience_replay_stores_and_replays_collision_events():
         assert seen[e] == 301
     assert 'replay' in infos and infos['replay']['replay/replay_rate'] > 0
     env.close()
+
+
+def test_batched_factory_with_the_obstacle_baseline_flags():
+    """make_quadrotor_env_multi_batched with the flags of swarm_rl/runs/obstacles/quad_obstacle_baseline.py:12-21
+    (mix with pillars, replay on, collision-reward annealing): everything stays on the device and statistics come out."""
+    import types
+    from quad_swarm_rl_b200.wrappers import make_quadrotor_env_multi_batched
+    cfg = types.SimpleNamespace(
+        quads_num_agents=8, quads_episode_duration=0.3, quads_obs_repr='xyz_vxyz_R_omega_floor', quads_neighbor_visible_num=2,
+        quads_neighbor_obs_type='pos_vel', quads_collision_hitbox_radius=2.0, quads_collision_falloff_radius=4.0,
+        quads_use_obstacles=True, quads_obst_density=0.2, quads_obst_size=0.6, quads_obst_spawn_area=[8.0, 8.0],
+        quads_use_downwash=True, quads_mode='mix', quads_room_dims=[10., 10., 10.], replay_buffer_sample_prob=0.75,
+        quads_collision_reward=5.0, quads_collision_smooth_max_penalty=4.0, quads_obst_collision_reward=5.0,
+        anneal_collision_steps=300000000.0, seed=3)
+    env = make_quadrotor_env_multi_batched(cfg, num_envs=64)
+    assert env.device_scenario == 'mix' and env.engine.M == 12 and env.num_agents == 512
+    env.training_info['approx_total_training_steps'] = 150000000
+    obs, _ = env.reset()
+    assert obs.shape == (512, 40)
+    stats = None
+    for t in range(31):
+        obs, rew, term, trunc, infos = env.step(torch.rand((512, 4), device='cuda') * 2 - 1)
+        if 'episode_extra_stats' in infos:
+            stats = infos['episode_extra_stats']
+    assert stats is not None and term.all()
+    assert env.engine.rew_coeff['quadcol_bin'] == pytest.approx(2.5) and env.engine.rew_coeff['quadcol_bin_obst'] == pytest.approx(2.5)
+    assert {'rew_pos', 'rewraw_quadcol_obstacle', 'num_collisions_obst_quad', 'metric/agent_success_rate',
+            'z_anneal_quadcol_bin_smooth_max'} <= set(stats)
+    assert any(k.startswith('Scenario_o_random/') for k in stats) and any(k.startswith('Scenario_o_static_same_goal/') for k in stats)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    env.close()
