@@ -380,6 +380,8 @@ def run_cuda_arm(args):
         launches = sum(e_.launch_count for e_ in engs) - launches0
         if graph is not None:
             launches = args.steps * groups             # replayed launches are not seen by the host-side counter
+        if any(e_.handover_timeouts for e_ in engs):   # overlapping step grids must never have lost a hand-over
+            raise RuntimeError("a per-block hand-over between step grids timed out: results of this run are invalid")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

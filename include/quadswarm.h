@@ -215,6 +215,12 @@ int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stat
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t qs_launch_count(const QsHandle* h);
 
+/* Consecutive qs_step / qs_rollout launches of a handle may overlap on the GPU: a CTA of the later grid waits for the
+ * CTA of the earlier grid that owns the same envs (per-block hand-over).  The wait is bounded (~1 s); this
+ * returns how many waits ran into the bound since qs_create — always 0 unless the device state was corrupted.
+ * Synchronises the device. */
+int64_t qs_handover_timeouts(QsHandle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,7 @@ EXPORTS = {
     'qs_set_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_read_episode_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_launch_count': (C.c_int64, [C.c_void_p]),
+    'qs_handover_timeouts': (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

@@ -78,7 +78,8 @@ struct DevState {
     float2* next_obst;      // [E][M]
     int32_t* stats_env;     // [E][QS_NUM_ENV_STATS]  latched at episode end
     float4* stats_agent;    // [A]                     latched at episode end
-    int* ready;             // [E]     per step-kernel block: 1 = the block's env state is complete in L2 (pdl_mode 3)
+    int* ready;             // [E + 1] per step-kernel block: 1 = the block's env state is complete in L2 (pdl_mode 3);
+                            //         ready[E] counts hand-over waits that timed out
     int4* scn_i;            // [E]     device-side scenario state: scenario, period, next event tick, formation | growing << 8
     float4* scn_f;          // [E][3]  formation size / layer distance / largest size / speed; centre 1; centre 2
 };

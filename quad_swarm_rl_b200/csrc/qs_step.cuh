@@ -301,12 +301,13 @@ __device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { c[k] = QS_LD
 // word block b(t) left for b(t+1).  The writer publishes with barrier + __threadfence + st.release; the reader acquires
 // and reads the state with ld.global.cg (L1 is not coherent across the grids).  Any other kernel / copy on the stream
 // never triggers early, so it still sees, and is seen by, whole step grids.
-__device__ __forceinline__ void handover_acquire(int* ready) {
+__device__ __forceinline__ void handover_acquire(int* ready, int* timeouts) {
     int v = 0, spins = 0;
     do {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
         if (v == 0) __nanosleep(40);
     } while (v == 0 && ++spins < (1 << 24));          // ~1 s: a lost hand-over must not hang the GPU
+    if (v == 0) atomicAdd(timeouts, 1);               // reported by qs_handover_timeouts
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(0) : "memory");
 }
 __device__ __forceinline__ void handover_release(int* ready) {
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     // (mode 2, default: hides ~0.3 us of launch latency per step; triggering at kernel start, mode 1, is 2 us SLOWER
     // because the early grid competes for issue slots while it spins).  Without the launch attribute both are no-ops.
     if (HO) {
-        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x);
+        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
     } else {

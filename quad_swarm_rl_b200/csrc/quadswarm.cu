@@ -394,9 +394,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.scn_i, sizeof(int4) * E);
     QS_ALLOC0(st.scn_f, sizeof(float4) * 3 * E);
     {   // per-block hand-over words (at most one block per env), all "ready"
-        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * E));
-        std::vector<int> ones((size_t)E, 1);
-        QS_CUDA(cudaMemcpy(st.ready, ones.data(), sizeof(int) * E, cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * (E + 1)));
+        std::vector<int> ones((size_t)E + 1, 1);
+        ones[(size_t)E] = 0;                                  // time-out counter
+        QS_CUDA(cudaMemcpy(st.ready, ones.data(), sizeof(int) * (E + 1), cudaMemcpyHostToDevice));
     }
     // rotation = identity so that a never-reset env still holds a valid state
     {
@@ -458,6 +459,14 @@ extern "C" int qs_num_agents(const QsHandle* h) { return h ? h->cfg.num_agents :
 extern "C" int qs_num_obstacles(const QsHandle* h) { return h ? h->M : 0; }
 extern "C" int qs_ep_len(const QsHandle* h) { return h ? h->ep_len : 0; }
 extern "C" int64_t qs_launch_count(const QsHandle* h) { return h ? h->launches : 0; }
+
+extern "C" int64_t qs_handover_timeouts(QsHandle* h) {
+    if (!h) return -1;
+    int v = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, h->st.ready + h->cfg.num_envs, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
 
 extern "C" int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host) {
     if (!h || !coeffs_host) return fail(QS_ERR_INVALID_ARG, "null argument");

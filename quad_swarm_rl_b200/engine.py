@@ -207,6 +207,11 @@ class QuadSwarmEngine:
     def launch_count(self):
         return int(self.lib.qs_launch_count(self.h))
 
+    @property
+    def handover_timeouts(self):
+        """Hand-over waits between overlapping step grids that hit their bound (0 in a healthy run); synchronises."""
+        return int(self.lib.qs_handover_timeouts(self.h))
+
 
 # field offsets inside agent_f32 rows (include/quadswarm.h, qs_get_state)
 STATE_F32_FIELDS = dict(pos=(0, 3), vel=(3, 6), rot=(6, 15), omega=(15, 18), thrust_rot_damp=(18, 22),

@@ -307,6 +307,7 @@ def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, mo
         for k in ('agent_f32', 'agent_u32', 'env_i32'):
             assert torch.equal(s1[k], s2[k]), (r, k)
     assert int(dn.sum()) > 0 or T * R < e1.ep_len
+    assert e1.handover_timeouts == 0 and e2.handover_timeouts == 0
     e1.close(); e2.close()
 
 
