@@ -1,26 +1,43 @@
-"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): both step kernels, resets, contacts."""
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): both step-kernel shapes, both
+launch-chaining modes, resets, contacts, every device-side scenario id, rollout, state and statistics kernels."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from quad_swarm_rl_b200.engine import QuadSwarmEngine
 from tests.parity_util import make_tables
+
+OBST = dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, use_downwash=True)
+WALL = dict(num_agents=5, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega_wall')
+WIDE = dict(num_agents=32, neighbor_visible_num=6)
+
+
+def run(kw, E, scn, steps=14):
+    eng = QuadSwarmEngine(num_envs=E, seed=1, ep_time=0.12, device_scenario=scn, **kw)
+    if scn is None:
+        t = make_tables(np.random.RandomState(2), E, kw['num_agents'], eng.M, kw.get('use_obstacles', False), episodes=1, spread=0.05)[0]
+        t['spawn'] = t['goals'].copy() if not kw.get('use_obstacles') else t['spawn']     # tight clusters -> contacts
+        eng.set_next_episode(t['goals'], t['spawn'], t['obst'])
+    eng.reset()
+    a = torch.rand((steps + 8, E, kw['num_agents'], 4), device='cuda') * 2 - 1
+    for k in range(steps):
+        eng.step(a[k].contiguous(), with_terms=True)
+    eng.rollout(a[steps:].contiguous())
+    st = eng.get_state(); eng.set_state(st); eng.episode_stats()
+    assert eng.handover_timeouts == 0
+    torch.cuda.synchronize()
+    eng.close()
+
+
 for split in ('0', '1'):
     os.environ['QS_SPLIT'] = split
-    for kw, E in ((dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, use_downwash=True), 13),
-                  (dict(num_agents=5, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega_wall'), 7),
-                  (dict(num_agents=32, neighbor_visible_num=6), 3)):
-        for scn in ((None, 'o_random') if kw.get('use_obstacles') else (None,)):
-            eng = QuadSwarmEngine(num_envs=E, seed=1, ep_time=0.12, device_scenario=scn, **kw)
-            if scn is None:
-                t = make_tables(np.random.RandomState(2), E, kw['num_agents'], eng.M, kw.get('use_obstacles', False), episodes=1, spread=0.05)[0]
-                t['spawn'] = t['goals'].copy() if not kw.get('use_obstacles') else t['spawn']     # tight clusters -> contacts
-                eng.set_next_episode(t['goals'], t['spawn'], t['obst'])
-            eng.reset()
-            a = torch.rand((30, E, kw['num_agents'], 4), device='cuda') * 2 - 1
-            for k in range(14):
-                eng.step(a[k].contiguous(), with_terms=True)
-            eng.rollout(a[14:].contiguous())
-            eng.get_state(); eng.episode_stats()
-            torch.cuda.synchronize()
-            eng.close()
+    os.environ['QS_PDL'] = '3'                       # per-block hand-over between step grids
+    for kw, E, scn in ((OBST, 13, None), (OBST, 13, 'mix'), (WALL, 7, None), (WIDE, 3, 'mix')):
+        run(kw, E, scn, steps=10)
+os.environ['QS_SPLIT'] = '0'
+os.environ['QS_PDL'] = '2'                           # grid-wide wait
+run(OBST, 13, 'o_static_same_goal', steps=10)
+os.environ['QS_PDL'] = '3'
+for scn in ('static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals', 'dynamic_formations',
+            'ep_lissajous3D', 'swarm_vs_swarm'):
+    run(dict(num_agents=8, neighbor_visible_num=3), 5, scn, steps=4)
 print('sanitize workload done')
