@@ -151,7 +151,29 @@ def _ref_kwargs(cfg):
                 quads_mode=cfg['mode'], rew_coeff=rew, use_numba=True)
 
 
-def _ref_worker(args):
+def effective_cpus():
+    """Host cores this process may actually use: cpu_count, capped by the affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]                  # cgroup v2
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())                    # cgroup v1
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
+def _ref_worker(args, barrier=None):
     """One process = one reference env (how Sample Factory's rollout workers run it)."""
     cfg_name, n_warm, n_steps, seed = args
     from oracle import ref_harness as rh
@@ -175,10 +197,24 @@ def _ref_worker(args):
         step = lambda: env.step(rs.uniform(-1, 1, (N, 4)))
     for _ in range(n_warm):
         step()
+    if barrier is not None:
+        barrier.wait()                 # every process has imported, JIT-compiled and warmed up before any of them is timed
     t0 = time.perf_counter()
     for _ in range(n_steps):
         step()
     return time.perf_counter() - t0, kind
+
+
+def _ref_proc(args, barrier, q):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    try:
+        q.put(_ref_worker(args, barrier))
+    except Exception as e:             # never leave the others waiting at the barrier
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        q.put((float('nan'), f'error: {e!r}'))
 
 
 def cpu_baseline_single(cfg_name, budget_s=12.0):
@@ -203,12 +239,22 @@ def run_reference_arm(args):
         return
     cfg = CONFIGS[args.config]
     N = cfg['kw']['num_agents']
-    P = os.cpu_count() or 1
+    P = effective_cpus()
     n_proc = int(min(max(args.steps, 100), 2500))
     n_warm = int(min(max(args.warmup, 3), 50))
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMBA_NUM_THREADS'):
+        os.environ.setdefault(k, '1')  # one env per process, one thread per process (inherited by the workers)
     ctx = mp.get_context('spawn')
-    with ctx.Pool(P) as pool:
-        res = pool.map(_ref_worker, [(args.config, n_warm, n_proc, 100 + r) for r in range(P)])
+    barrier, q = ctx.Barrier(P), ctx.Queue()
+    procs = [ctx.Process(target=_ref_proc, args=((args.config, n_warm, n_proc, 100 + r), barrier, q)) for r in range(P)]
+    for pr in procs:
+        pr.start()
+    res = [q.get() for _ in procs]
+    for pr in procs:
+        pr.join()
+    bad = [r for r in res if not (r[0] == r[0])]
+    if bad:
+        raise RuntimeError(f'reference worker failed: {bad[0][1]}')
     wall = max(r[0] for r in res)
     kind = res[0][1]
     value = P * N * n_proc / wall
@@ -217,7 +263,7 @@ def run_reference_arm(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f"{args.config}: {cfg['desc']}",
-                   'note': f'bounded sample: {P} processes x 1 env each x {n_proc} control steps (numba path), spread over the {args.steps} bench steps'},
+                   'note': f'bounded sample: {P} processes (= usable host cores of {os.cpu_count()} logical) x 1 env each x {n_proc} control steps (numba path), timed after all processes warmed up'},
         'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': P, 'kind': kind,
                          'sample': f'{P} processes x 1 env x {n_proc} control steps of workload {args.config}'},
         'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
