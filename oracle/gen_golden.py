@@ -82,6 +82,27 @@ CASES = [
                                               quads_mode='swarm_vs_swarm'), T=500, seed=71, obs_stride=10),
     dict(name='dynamic_formations_8', kw=dict(num_agents=8, neighbor_visible_num=6, ep_time=0.8,
                                               quads_mode='dynamic_formations'), T=180, seed=81, obs_stride=4),
+    # the remaining scenario classes: timed goal events (4-6 s periods need episodes > 6 s), per-tick goal motion,
+    # obstacle scenarios with the largest-free-square goal
+    dict(name='dynamic_same_goal_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3,
+                                             quads_mode='dynamic_same_goal'), T=700, seed=91, obs_stride=20),
+    dict(name='dynamic_diff_goal_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3,
+                                             quads_mode='dynamic_diff_goal'), T=700, seed=92, obs_stride=20),
+    dict(name='swap_goals_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3,
+                                      quads_mode='swap_goals'), T=700, seed=93, obs_stride=20),
+    dict(name='lissajous_3', kw=dict(num_agents=3, neighbor_visible_num=2, ep_time=1.0,
+                                     quads_mode='ep_lissajous3D'), T=160, seed=94, obs_stride=8),
+    dict(name='run_away_5', kw=dict(num_agents=5, neighbor_visible_num=2, ep_time=2.6,
+                                    quads_mode='run_away'), T=300, seed=95, obs_stride=10),
+    dict(name='o_static_same_goal_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=1.0, use_obstacles=True,
+                                              quads_mode='o_static_same_goal', obs_repr='xyz_vxyz_R_omega_floor'),
+         T=230, seed=96, obs_stride=10),
+    dict(name='o_dynamic_same_goal_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3, use_obstacles=True,
+                                               quads_mode='o_dynamic_same_goal', obs_repr='xyz_vxyz_R_omega_floor'),
+         T=700, seed=97, obs_stride=20),
+    dict(name='o_swap_goals_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3, use_obstacles=True,
+                                        quads_mode='o_swap_goals', obs_repr='xyz_vxyz_R_omega_floor'),
+         T=700, seed=98, obs_stride=20),
 ]
 
 

@@ -147,7 +147,7 @@ class _EnvBase:
             seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario,
             # scenario.approch_goal_metric (o_base.py:16: 1.0 for the goal-sharing obstacle scenarios, else 0.5); with the
             # host-side `mix` over obstacle scenarios the value of o_random is used for every episode
-            approch_goal_metric=1.0 if quads_mode == 'o_static_same_goal' else 0.5)
+            approch_goal_metric=1.0 if quads_mode in ('o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals') else 0.5)
         self.device_scenario = device_scenario
         self.rew_coeff = self.engine.rew_coeff               # the live, mutable dict (reward_shaping.py:55-61 writes it)
         self.ep_len = self.engine.ep_len

