@@ -223,3 +223,129 @@ def test_sharding_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('ok') == 2
+
+
+# ---- batched wrappers (batched.py) on CPU tensors with a stand-in engine ----
+class _FakeBatchedEngine:
+    """Counts ticks per env, auto-resets after ep_len steps, reports a collision when told to."""
+
+    def __init__(self, E, N, D, ep_len):
+        import torch
+        self.device = torch.device('cpu')
+        self.E, self.N, self.D, self.ep_len, self.M = E, N, D, ep_len, 0
+        self.af = torch.zeros((E, N, 43)); self.au = torch.zeros((E, N, 4), dtype=torch.int32)
+        self.ei = torch.zeros((E, 36), dtype=torch.int32)
+        self.rew_terms = torch.zeros((E, N, 8))
+        self.rew_coeff = dict(pos=1.0, effort=0.05, crash=1.0, orient=1.0, spin=0.1, quadcol_bin=5.0,
+                              quadcol_bin_smooth_max=4.0, quadcol_bin_obst=5.0)
+        self.collide = torch.zeros(E, dtype=torch.bool)
+        self.stats_env = torch.zeros((E, 13), dtype=torch.int32)
+
+    def get_state(self):
+        import torch
+        return dict(agent_f32=self.af.clone(), agent_u32=self.au.clone(), env_i32=self.ei.clone(),
+                    obst_xy=torch.zeros((self.E, 0, 2)))
+
+    def set_state(self, st, env_mask=None):
+        m = env_mask.bool()
+        self.af[m] = st['agent_f32'][m]; self.au[m] = st['agent_u32'][m]; self.ei[m] = st['env_i32'][m]
+
+    def episode_stats(self):
+        import torch
+        return self.stats_env.clone(), torch.zeros((self.E, self.N, 4))
+
+
+class _FakeBatchedEnv:
+    device_scenario = 'static_same_goal'
+    use_obstacles = False
+    quads_mode = 'static_same_goal'
+
+    def __init__(self, E=6, N=2, D=5, ep_len=300):
+        self.engine = _FakeBatchedEngine(E, N, D, ep_len)
+        self.num_envs, self.num_agents_per_env, self.num_agents = E, N, E * N
+
+    def reset(self, **kw):
+        e = self.engine
+        e.af.zero_(); e.ei.zero_()
+        return e.af[..., :e.D].reshape(self.num_agents, -1).clone(), {}
+
+    def step(self, actions, with_terms=False):
+        import torch
+        e = self.engine
+        e.ei[:, 0] += 1
+        e.ei[:, 1] += 1                                   # RNG step counter: never rewinds
+        e.af += 1.0                                       # the "physics": every state entry counts steps of the episode
+        done = e.ei[:, 0] > e.ep_len
+        e.rew_terms.zero_()
+        e.rew_terms[..., 0] = -0.01
+        e.rew_terms[e.collide, 0, 5] = -1.0
+        e.collide.zero_()
+        if done.any():                                    # auto-reset inside the "kernel"
+            e.stats_env[done, 11] += 1
+            e.stats_env[done, 12] = 2
+            e.af[done] = 0.0
+            e.ei[done, 0] = 0
+            e.ei[done, 3] += 1
+        obs = e.af[..., :e.D].reshape(self.num_agents, -1).clone()
+        rew = e.rew_terms[..., 0].reshape(-1).clone()
+        term = done.repeat_interleave(self.num_agents_per_env)
+        return obs, rew, term, torch.zeros_like(term), {}
+
+
+def test_batched_replay_logic_on_cpu_tensors():
+    """BatchedExperienceReplay (quad_experience_replay.py:66-209 per env, masked): checkpoint every 50 ticks, the
+    checkpoint from 3 checkpoints back is stored on a collision after the grace period, one event per 5 s, replay at the
+    episode end restores that state (tick, state rows, observation) while the RNG step counter keeps running."""
+    import torch
+    from quad_swarm_rl_b200.batched import BatchedExperienceReplay
+    env = _FakeBatchedEnv()
+    rp = BatchedExperienceReplay(env, replay_buffer_sample_prob=1.0, always_active=True, seed=1)
+    rp.reset()
+    E, N = env.num_envs, env.num_agents_per_env
+    a = torch.zeros((E * N, 4))
+    for t in range(1, 302):
+        if t == 120:
+            env.engine.collide[0] = True                  # before the grace period (tick <= 150): ignored
+        if t == 231:
+            env.engine.collide[1] = True                  # checkpoints at 50..200 exist -> stores the one of tick 100
+            env.engine.collide[2] = True
+        if t == 260:
+            env.engine.collide[1] = True                  # same episode again: already saved, ignored
+        obs, rew, term, trunc, infos = rp.step(a)
+    assert term.all() and rp.episode_counter == E
+    assert rp.buf_valid.sum(dim=0).tolist() == [0, 1, 1, 0, 0, 0]
+    assert rp.buf['env_i32'][0, 1, 0] == 100 and torch.all(rp.buf['agent_f32'][0, 1] == 100.0)
+    # envs 1 and 2 were replayed (p = 1): tick 100, state rows of tick 100, the stored observation; others start fresh
+    assert rp.tick.tolist() == [0, 100, 100, 0, 0, 0] and rp.replayed_events == 2
+    assert torch.all(env.engine.af[1] == 100.0) and torch.all(env.engine.af[0] == 0.0)
+    assert torch.all(obs.view(E, N, -1)[2] == 100.0) and torch.all(obs.view(E, N, -1)[3] == 0.0)
+    assert env.engine.ei[1, 1] == 301 and env.engine.ei[1, 0] == 100          # step counter kept, tick restored
+    assert rp.saved.tolist() == [False, True, True, False, False, False]
+    # replayed envs end after ep_len + 1 - 100 more steps, and then (p = 1) replay the same event again
+    for t in range(1, 202):
+        obs, rew, term, trunc, infos = rp.step(a)
+    d = term.view(E, N)[:, 0].tolist()
+    assert d == [False, True, True, False, False, False]
+    assert rp.buf_replayed[0, 1] == 2 and rp.tick.tolist() == [201, 100, 100, 201, 201, 201]
+    assert infos['replay']['replay/replay_rate'] == pytest.approx(4 / 8)
+
+
+def test_batched_reward_shaping_on_cpu_tensors():
+    import torch
+    from quad_swarm_rl_b200.batched import BatchedRewardShaping
+    env = _FakeBatchedEnv(E=3, N=2, ep_len=4)
+    w = BatchedRewardShaping(env, reward_shaping_scheme=dict(quad_rewards=dict(pos=2.0)),
+                             annealing=[wr.AnnealSchedule('quadcol_bin', 5.0, 100)])
+    w.training_info['approx_total_training_steps'] = 50
+    w.reset()
+    infos = {}
+    for t in range(5):
+        env.engine.collide[0] = (t == 2)
+        obs, rew, term, trunc, infos = w.step(torch.full((6, 4), 0.5))
+    st = infos['episode_extra_stats']
+    assert term.all() and env.engine.rew_coeff['quadcol_bin'] == 2.5 and st['z_anneal_quadcol_bin'] == 2.5
+    assert st['rewraw_pos'] == pytest.approx(-0.05) and st['rew_pos'] == pytest.approx(-0.10)       # coefficient 2.0
+    assert st['rewraw_quadcol'] == pytest.approx(-1.0 / 6)                                          # one drone of six, once
+    assert infos['true_reward'][0, 0].item() == pytest.approx(-0.05 - 1000.0)
+    assert st['z_action0_mean'] == pytest.approx(0.5) and st['z_action0_std'] == pytest.approx(0.0, abs=1e-6)
+    assert 'Scenario_static_same_goal/rew_pos' in st
