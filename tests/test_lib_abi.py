@@ -68,3 +68,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith('.py'):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+
+
+def test_integration_doc_binding_matches_the_header():
+    """The ctypes stub shown in INTEGRATION.md must list QsConfig's fields in the header's order (a stale stub would
+    silently shift every field after the change)."""
+    import re
+    from quad_swarm_rl_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, 'INTEGRATION.md')).read()
+    block = md[md.index('class QsConfig(C.Structure)'):]
+    block = block[:block.index(']\n') + 1]
+    doc_fields = re.findall(r'\("(\w+)",', block)
+    assert doc_fields == [f[0] for f in L.QsConfig._fields_]
+    hdr = open(os.path.join(root, 'include', 'quadswarm.h')).read()
+    struct = hdr[hdr.index('typedef struct QsConfig {'):hdr.index('} QsConfig;')]
+    hdr_fields = re.findall(r'^\s+(?:int32_t|float|uint64_t)\s+(\w+)', struct, flags=re.M)
+    assert hdr_fields == doc_fields
