@@ -460,10 +460,21 @@ def run_cuda_arm(args):
         eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same loop with explicit cudaMemcpyAsync H2D / D2H around the kernel instead of zero-copy access (reported beside it)
+    os.environ['QS_ZERO_COPY'] = '0'
+    for k in range(3):
+        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
+    torch.cuda.synchronize()
+    e2e_copy_s = time.perf_counter() - t0
+    os.environ.pop('QS_ZERO_COPY', None)
     if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
+        t = torch.tensor([e2e_s, e2e_copy_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, e2e_copy_s = float(t[0].item()), float(t[1].item())
 
     # ---- extras (rank 0, single GPU): the same kernel (a) T steps per launch (qs_rollout: env block stays in registers,
     #      every observation still written) and (b) at a 4x larger batch, where the GPU has enough warps to fill its
@@ -541,7 +552,11 @@ def run_cuda_arm(args):
             'clocks': clk,
             'e2e': {'value': world * A * n_e2e / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': A * 16,
                     'd2h_bytes_per_step': A * (4 * D + 4 + 1), 'steps': n_e2e,
-                    'note': 'qs_step_host with page-locked numpy buffers: H2D actions, step kernel, D2H obs/rewards/dones, stream sync, every step'},
+                    'explicit_copies_value': world * A * n_e2e / e2e_copy_s,
+                    'note': 'qs_step_host with page-locked numpy buffers, stream sync every step.  value: the kernel reads the '
+                            'actions from and writes obs/rewards/dones to the mapped host buffers itself (zero-copy over PCIe, the '
+                            'bytes listed cross the bus inside the timed region); explicit_copies_value: cudaMemcpyAsync H2D, '
+                            'kernel, cudaMemcpyAsync D2H x3 instead (QS_ZERO_COPY=0)'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': measured_traffic(args.config) if E == cfg['E'] else None, 'peak_source': peak_src, 'alg_bytes_per_agent_step': b_alg,

@@ -50,16 +50,26 @@ def test_rollout_equals_repeated_steps(kw):
         e.close()
 
 
-def test_host_buffer_step_equals_device_step():
+@pytest.mark.parametrize('pinned', [False, True], ids=['pageable_copies', 'pinned_zero_copy'])
+def test_host_buffer_step_equals_device_step(pinned):
+    """qs_step_host == qs_step, bit for bit: pageable numpy buffers go through staging copies, page-locked ones are
+    read / written by the kernel itself (zero-copy over PCIe)."""
     E, kw = 19, C3
     e1, _ = _engine(E, kw); e2, _ = _engine(E, kw)
     e1.reset(); e2.reset()
     a = _actions(12, E, 8)
-    obs_h = np.zeros((E, 8, e1.D), np.float32); rew_h = np.zeros((E, 8), np.float32); dn_h = np.zeros((E, 8), np.uint8)
-    terms_h = np.zeros((E, 8, 8), np.float32)
+
+    def host(shape, dtype):
+        t = torch.zeros(shape, dtype=dtype)
+        return (t.pin_memory() if pinned else t).numpy()
+
+    obs_h, rew_h, dn_h = host((E, 8, e1.D), torch.float32), host((E, 8), torch.float32), host((E, 8), torch.uint8)
+    terms_h = host((E, 8, 8), torch.float32)
+    a_h = host((E, 8, 4), torch.float32)
     for t in range(12):
         o, r, d = e1.step(a[t], with_terms=True)
-        e2.step_host(a[t].cpu().numpy(), obs_h, rew_h, dn_h, terms_h)
+        a_h[...] = a[t].cpu().numpy()
+        e2.step_host(a_h, obs_h, rew_h, dn_h, terms_h)
         assert np.array_equal(o.cpu().numpy(), obs_h) and np.array_equal(r.cpu().numpy(), rew_h)
         assert np.array_equal(d.cpu().numpy(), dn_h) and np.array_equal(e1.rew_terms.cpu().numpy(), terms_h)
     e1.close(); e2.close()
