@@ -538,6 +538,9 @@ extern "C" int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, 
     return launch_step(h, p, (cudaStream_t)stream);
 }
 
+#ifndef QS_ZERO_COPY_DEFAULT
+#define QS_ZERO_COPY_DEFAULT false
+#endif
 // true when the host pointer is page-locked (cudaHostAlloc / cudaHostRegister): DMA can use it directly
 static bool is_pinned(const void* p) {
     cudaPointerAttributes at;
@@ -561,7 +564,7 @@ extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_h
     // outputs straight to, host memory — coalesced 128-bit stores over PCIe overlap the transfer with the step and save
     // the four copy launches (QS_ZERO_COPY=0 falls back to explicit copies).
     const char* zc_env = getenv("QS_ZERO_COPY");          // read per call: bench.py times both paths in one process
-    const bool zero_copy = zc_env ? atoi(zc_env) != 0 : true;
+    const bool zero_copy = zc_env ? atoi(zc_env) != 0 : QS_ZERO_COPY_DEFAULT;
     if (zero_copy && pa && po && pr && pd && (!rew_terms_host || pt)) {
         void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
         bool ok = cudaHostGetDevicePointer(&da, (void*)actions_host, 0) == cudaSuccess &&
