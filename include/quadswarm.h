@@ -167,8 +167,9 @@ int qs_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* reward
 
 /* same step with HOST buffers: H2D of actions, the step kernel, D2H of obs/rewards/dones(/terms), then a
  * stream synchronise — the call a non-batched rollout worker makes.  Pageable buffers go through the handle's
- * page-locked staging; page-locked ones are DMA'd directly.  With QS_ZERO_COPY=1 in the environment and all buffers
- * page-locked and mapped, the kernel reads the actions from and writes its outputs to the host buffers itself. */
+ * page-locked staging.  When every buffer is page-locked and mapped, the kernel reads the actions from and writes its
+ * outputs to the host buffers itself (zero-copy over PCIe, no separate copy launches; QS_ZERO_COPY=0 in the environment
+ * forces explicit cudaMemcpyAsync on the page-locked buffers instead). */
 int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
                  float* rew_terms_host);
 int qs_reset_host(QsHandle* h, const uint8_t* env_mask_host, float* obs_host);

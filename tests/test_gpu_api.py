@@ -51,12 +51,10 @@ def test_rollout_equals_repeated_steps(kw):
 
 
 @pytest.mark.parametrize('pinned', [False, True], ids=['pageable_copies', 'pinned_zero_copy'])
-def test_host_buffer_step_equals_device_step(pinned, monkeypatch):
+def test_host_buffer_step_equals_device_step(pinned):
     """qs_step_host == qs_step, bit for bit: pageable numpy buffers go through staging copies, page-locked ones are
     read / written by the kernel itself (zero-copy over PCIe)."""
     E, kw = 19, C3
-    if pinned:
-        monkeypatch.setenv('QS_ZERO_COPY', '1')
     e1, _ = _engine(E, kw); e2, _ = _engine(E, kw)
     e1.reset(); e2.reset()
     a = _actions(12, E, 8)
