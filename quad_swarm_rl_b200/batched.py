@@ -15,7 +15,6 @@ semantics per env but hold their state as tensors on the GPU and work with masks
 
 PyTorch is used for the bookkeeping tensors only; the env state never leaves the device.
 """
-import numpy as np
 import torch
 
 from . import _lib as L

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import QuadSwarmEngine, DEFAULT_REW_COEFF
+from .engine import QuadSwarmEngine
 from .scenarios import create_scenario, obstacle_map_given_density
 from .spaces import make_observation_space, make_action_space
 

@@ -1,6 +1,5 @@
 """Multi-GPU layout: envs are independent units, so the job shards them in contiguous blocks, one process per GPU,
 with NO step-time collective.  The only cross-rank traffic is an optional metrics reduction."""
-import torch
 import torch.distributed as dist
 
 

@@ -321,7 +321,7 @@ def test_dense_pillars_more_than_32_and_no_sensor_noise():
     kw = dict(num_agents=4, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, obst_density=0.8,
               use_downwash=False, ep_time=0.5, sense_noise=None)
     from tests import parity_util as pu
-    import types
+
 
     def dense_tables(rs, E, N, M, use_obst, episodes=3, spread=1.5):
         cells = pu.qo.get_cell_centers(8, 8)
