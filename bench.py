@@ -228,6 +228,24 @@ def cpu_baseline_single(cfg_name, budget_s=12.0):
                 sample=f'1 env x {n} control steps of workload {cfg_name}, random actions, 1 process (numba path)')
 
 
+def obs_dim_of(cfg):
+    """D = S + 6 K (+ 9 with obstacles), quadrotor_single.py:311-316."""
+    kw = cfg['kw']
+    S = {'xyz_vxyz_R_omega': 18, 'xyz_vxyz_R_omega_floor': 19, 'xyz_vxyz_R_omega_wall': 24}[kw['obs_repr']]
+    K = kw['num_agents'] - 1 if kw['neighbor_visible_num'] == -1 else kw['neighbor_visible_num']
+    return S + 6 * K + (9 if kw.get('use_obstacles', False) else 0)
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line — identical for the CUDA arm and the reference arm (same workload, same keys)."""
+    cfg = CONFIGS[args.config]
+    E = args.envs or cfg['E']
+    N = cfg['kw']['num_agents']
+    return {'workload': f"{args.config}: {cfg['desc']}", 'envs_per_gpu': E, 'drones': N, 'obs_dim': obs_dim_of(cfg),
+            'agents_per_gpu': E * N, 'ep_len': int(args.ep_time / 0.01), 'actions': 'i.i.d. U(-1,1)^4 per agent and step',
+            'parallelism': f'dp{world} (envs sharded, no step-time collective)'}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation on all host cores (one env per process, the way Sample
     Factory's rollout workers run it).  The K bench steps are a BOUNDED SAMPLE of the workload: every process advances
@@ -235,6 +253,7 @@ def run_reference_arm(args):
     the rate, not the step count, is what is compared."""
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
@@ -260,10 +279,14 @@ def run_reference_arm(args):
     value = P * N * n_proc / wall
     line = {
         'impl': 'reference', 'metric': 'env agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f"{args.config}: {cfg['desc']}",
-                   'note': f'bounded sample: {P} processes (= usable host cores of {os.cpu_count()} logical) x 1 env each x {n_proc} control steps (numba path), timed after all processes warmed up'},
+        'steps': args.steps, 'warmup': args.warmup,
+        # one "step" of this arm = every one of the P reference envs advances one control step (P x N agent-steps)
+        'ms_per_step': 1e3 * wall / n_proc, 'sample_steps': n_proc, 'sample_envs': P,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': bench_config(args, world),
+        'sample_note': (f'bounded sample of the workload: {P} processes (= usable host cores of {os.cpu_count()} logical) x 1 reference env '
+                        f'each x {n_proc} control steps (numba path), timed after all processes warmed up; ms_per_step = wall / {n_proc}; '
+                        f'the rate (agent-steps/s) is what compares with the CUDA arm'),
         'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': P, 'kind': kind,
                          'sample': f'{P} processes x 1 env x {n_proc} control steps of workload {args.config}'},
         'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -275,10 +298,198 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------
+L2_BYTES = 140e6          # rings are sized past this (B200 L2 = 126 MB)
+
+
+class StepRunner:
+    """E envs of one workload on one GPU, stepped from CUDA graphs of K consecutive launches (chained step grids).
+
+    Rings: P = NG * K slots of actions / observations / rewards / dones, each ring larger than L2, so consecutive
+    replays never find their inputs or outputs in cache; graph j covers ring slots [j K, (j+1) K)."""
+
+    def __init__(self, torch, cfg, E, args, local_rank, rank, K, graph=True, stagger=True):
+        from quad_swarm_rl_b200.engine import QuadSwarmEngine
+        self.torch = torch
+        kw = cfg['kw']
+        self.E, self.N = E, kw['num_agents']
+        dev = self.dev = torch.device('cuda', local_rank)
+        dev_scn = None if args.host_tables else cfg['mode']
+        self.dev_scn = dev_scn
+        eng = self.eng = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=rank * E, rew_coeff=cfg['rew'],
+                                         ep_time=args.ep_time, device_scenario=dev_scn, **kw)
+        if dev_scn is None:
+            goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank * 64)
+            eng.set_next_episode(goals, spawn, obst)
+        eng.reset()
+        self.stagger = stagger
+        if stagger:
+            # every env starts at its own point of the episode (tick ~ U{0..ep_len}): each control step then carries
+            # E / (ep_len + 1) auto-resets, as in training, where the replay wrapper de-synchronises the envs
+            st = eng.get_state()
+            g = torch.Generator(device=dev)
+            g.manual_seed(1234 + rank)
+            st['env_i32'][:, 0] = torch.randint(0, eng.ep_len + 1, (E,), device=dev, generator=g, dtype=torch.int32)
+            eng.set_state(st)
+        eng.set_chained(True)           # the step grids of a graph follow each other directly on the stream
+        A, D = E * self.N, eng.D
+        self.A, self.D, self.M = A, D, eng.M
+        per_step = A * (16 + 4 * D + 4 + 1)
+        # launches per graph: K itself when it fits, else the largest divisor of K that does (no eager launches inside a
+        # timed block); ring memory bounded to ~8 GB
+        kg_max = int(max(1, min(2048, 8e9 // per_step)))
+        self.Kg = max(d for d in range(1, kg_max + 1) if K % d == 0) if K > kg_max else K
+        if self.Kg < min(64, K):
+            self.Kg = min(K, kg_max)
+        need = int(np.ceil(L2_BYTES / (A * 16)))                            # slots until the ACTION ring alone exceeds L2
+        self.NG = max(1, int(np.ceil(need / self.Kg)))
+        while self.NG > 1 and self.NG * self.Kg * per_step > 8e9:           # bound the ring memory
+            self.NG -= 1
+        self.P = P = self.NG * self.Kg
+        g = torch.Generator(device=dev)
+        g.manual_seed(args.seed * 1000 + rank)
+        self.act = (torch.rand((P, E, self.N, 4), device=dev, generator=g) * 2 - 1).contiguous()
+        self.obs = torch.empty((P, E, self.N, D), device=dev)
+        self.rew = torch.empty((P, E, self.N), device=dev)
+        self.done = torch.empty((P, E, self.N), dtype=torch.uint8, device=dev)
+        self.counter = 0
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graphs = []
+        with torch.cuda.stream(self.stream):
+            for _ in range(3):
+                self._one()
+            self.stream.synchronize()
+            if graph:
+                self.counter = 0
+                for j in range(self.NG):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=self.stream):
+                        for _ in range(self.Kg):
+                            self._one()
+                    self.graphs.append(gr)
+                self.counter = 0
+
+    def _one(self):
+        k = self.counter % self.P
+        self.eng.step(self.act[k], obs_out=self.obs[k], rewards_out=self.rew[k], dones_out=self.done[k])
+        self.counter += 1
+
+    def run(self, n):
+        """n control steps on self.stream (call inside `with torch.cuda.stream(self.stream)`)."""
+        done = 0
+        if self.graphs:
+            while n - done >= self.Kg and self.counter % self.Kg == 0:
+                self.graphs[(self.counter // self.Kg) % self.NG].replay()
+                done += self.Kg
+                self.counter += self.Kg
+        while done < n:
+            self._one()
+            done += 1
+
+    def align(self):
+        if self.graphs and self.counter % self.Kg:
+            self.run(self.Kg - self.counter % self.Kg)
+
+    def close(self):
+        self.graphs = []
+        self.eng.close()
+
+
+def time_blocks(torch, dist, runner, K, R, world, side=None, metrics=None, gather_every=100):
+    """R back-to-back blocks of exactly K control steps, each bracketed by its own pair of CUDA events on the launching
+    stream.  Returns the (start, end) event pairs.  The optional cross-GPU metrics gather (NCCL all-reduce of a small
+    vector every `gather_every` steps) runs on a side stream that only WAITS for the step stream — it is never an edge of
+    the step chain — and is joined after the last block."""
+    st = runner.stream
+    pairs = []
+    since = 0
+    with torch.cuda.stream(st):
+        runner.align()
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for b in range(R):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            runner.run(K)
+            e1.record(st)
+            pairs.append((e0, e1))
+            since += K
+            if side is not None and since >= gather_every:
+                since = 0
+                side.wait_event(e1)
+                with torch.cuda.stream(side):
+                    metrics[0] = runner.rew[(runner.counter - 1) % runner.P].sum()
+                    metrics[1] += 1
+                    dist.all_reduce(metrics[:1], async_op=True)
+            runner.align()                      # K > steps per graph: untimed steps up to the next graph boundary
+        st.synchronize()
+        if side is not None:
+            side.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return pairs
+
+
+def block_times(torch, dist, pairs, world, dev):
+    ms = [a.elapsed_time(b) for a, b in pairs]
+    if world > 1:
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.tolist()
+    return ms
+
+
+def measure_workload(torch, dist, name, args, local_rank, rank, world, K, target_s, clocks=None, side=None, metrics=None):
+    """Device-resident agent-steps/s of one workload: R blocks of K chained step launches, median block."""
+    cfg = CONFIGS[name]
+    E = (args.envs if name == args.config and args.envs else cfg['E'])
+    runner = StepRunner(torch, cfg, E, args, local_rank, rank, K, graph=not args.no_graph, stagger=not args.lockstep)
+    dev = runner.dev
+    with torch.cuda.stream(runner.stream):
+        runner.run(max(3, args.warmup))
+        runner.align()
+        runner.stream.synchronize()
+    # pilot blocks: estimate the block time, warm the graphs
+    evp = time_blocks(torch, dist, runner, K, 2, world)
+    est_ms = max(1e-3, evp[1][0].elapsed_time(evp[1][1]))
+    R = int(min(5000, max(1, np.ceil(target_s * 1e3 / est_ms))))
+    if world > 1:
+        t = torch.tensor([R], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        R = int(t.item())
+    if side is not None:                       # NCCL's lazy channel / connection setup happens here, not in the window
+        with torch.cuda.stream(side):
+            metrics[0] = runner.rew[0].sum()
+            dist.all_reduce(metrics[:1])
+        side.synchronize()
+    launches0 = runner.eng.launch_count
+    if clocks is not None:
+        clocks.start()
+    K_eff = K
+    pairs = time_blocks(torch, dist, runner, K, R, world, side=side, metrics=metrics)
+    clk = clocks.stop() if clocks is not None else None
+    ms = block_times(torch, dist, pairs, world, dev)
+    if runner.eng.handover_timeouts:
+        raise RuntimeError("a per-block hand-over between step grids timed out: results of this run are invalid")
+    med = float(np.median(ms))
+    D, M, N, A = runner.D, runner.M, runner.N, runner.A
+    b_alg = 292 + 4 * D + (8.0 * M / N if M else 0.0)
+    peak, peak_src = hbm_peak()
+    launch_s = med * 1e-3 / K_eff
+    res = dict(runner=runner, med_ms=med, blocks=R, block_ms_min=float(np.min(ms)), block_ms_max=float(np.max(ms)),
+               us_per_step=launch_s * 1e6, value=world * A * K_eff / (med * 1e-3), b_alg=b_alg, D=D, M=M, N=N, A=A, E=E,
+               frac=b_alg * A / launch_s / 1e9 / peak, achieved=b_alg * A / launch_s / 1e9, peak=peak, peak_src=peak_src,
+               clk=clk, launches_host=runner.eng.launch_count - launches0, ring_slots=runner.P,
+               ring_mb=dict(actions=runner.P * A * 16 / 1e6, observations=runner.P * A * D * 4 / 1e6), graphs=runner.NG,
+               steps_per_graph=runner.Kg)
+    return res
+
+
 def run_cuda_arm(args):
     import torch
     import torch.distributed as dist
-    from quad_swarm_rl_b200.engine import QuadSwarmEngine
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -288,161 +499,33 @@ def run_cuda_arm(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-
+    K = max(1, args.steps)
     cfg = CONFIGS[args.config]
-    E = args.envs or cfg['E']
-    kw = cfg['kw']
-    N = kw['num_agents']
-    # Episodes are generated ON THE DEVICE inside the reset path of the kernels (o_random: pillars, spawn and goal cells;
-    # static_same_goal / swarm_vs_swarm: goal formations), and swarm_vs_swarm's goal swaps every 4-6 s happen inside the
-    # step kernel: no host work per episode or per tick.  --host-tables uploads host-generated tables once instead.
-    dev_scn = None if args.host_tables else cfg['mode']
-    # Optional (--groups G > 1): the E envs of this GPU are stepped as G independent blocks, each with its own chain of
-    # kernel launches and no edge between the chains (double-buffered sampling, as Sample Factory runs its rollout
-    # workers).  Every env still advances one control step per bench step; results do not depend on the grouping (global
-    # env ids key the RNG: tests/test_gpu_api.py).  Measured gain on c3: 9.17 -> 8.93 us/step with 2 or 4 groups; the
-    # default stays 1 group = one kernel launch per control step.
-    groups = max(1, args.groups)
-    while E % groups:
-        groups -= 1
-    Eg = E // groups
-    engs = []
-    for gi in range(groups):
-        e_ = QuadSwarmEngine(num_envs=Eg, seed=args.seed, device=local_rank, env_id_offset=rank * E + gi * Eg,
-                             rew_coeff=cfg['rew'], ep_time=args.ep_time, device_scenario=dev_scn, **kw)
-        if dev_scn is None:
-            goals, spawn, obst = make_episode_tables(cfg, Eg, seed=1000 + rank * 64 + gi)
-            e_.set_next_episode(goals, spawn, obst)
-        e_.reset()
-        engs.append(e_)
-    eng = engs[0]
-    A, D, M = E * N, eng.D, eng.M
 
-    # synthetic inputs: i.i.d. U(-1,1)^4 actions, pre-generated ring larger than L2; observation rollout ring
-    pow2 = lambda x: 1 << int(np.ceil(np.log2(max(1, x))))
-    R_act = max(8, min(1024, pow2(140e6 / (A * 16))))
-    R_obs = max(8, min(1024, pow2(140e6 / (A * D * 4))))
-    g = torch.Generator(device=dev)
-    g.manual_seed(args.seed * 1000 + rank)
-    act_ring = (torch.rand((R_act, E, N, 4), device=dev, generator=g) * 2 - 1).contiguous()
-    obs_ring = torch.empty((R_obs, E, N, D), device=dev)
-    rew_ring = torch.empty((R_obs, E, N), device=dev)
-    done_ring = torch.empty((R_obs, E, N), dtype=torch.uint8, device=dev)
-    metrics = torch.zeros(64, device=dev)
-
-    counter = [0]
-    side = [torch.cuda.Stream(device=dev) for _ in range(groups - 1)]
-
-    def one_step():
-        """one control step of every env: one kernel launch per env group, each on its own stream"""
-        k = counter[0]
-        cur = torch.cuda.current_stream(dev)
-        for gi, e_ in enumerate(engs):
-            sl = slice(gi * Eg, (gi + 1) * Eg)
-            with torch.cuda.stream(cur if gi == 0 else side[gi - 1]):
-                e_.step(act_ring[k % R_act, sl], obs_out=obs_ring[k % R_obs, sl], rewards_out=rew_ring[k % R_obs, sl],
-                        dones_out=done_ring[k % R_obs, sl])
-        counter[0] = k + 1
-
-    def fork():
-        cur = torch.cuda.current_stream(dev)
-        for s_ in side:
-            s_.wait_stream(cur)
-
-    def join():
-        cur = torch.cuda.current_stream(dev)
-        for s_ in side:
-            cur.wait_stream(s_)
-
-    # CUDA graph of G consecutive steps (G divides both rings' periods so replays stay consistent)
-    # graph of G consecutive steps; G is a power of two (ring indices baked into the graph stay periodic) and no larger
-    # than the number of timed steps, so that short runs are still graph-replayed
-    G = max(R_act, R_obs)
-    while G > max(1, args.steps):
-        G //= 2
-    stream = torch.cuda.Stream(device=dev)
-    graph = None
-    with torch.cuda.stream(stream):
-        fork()
-        for _ in range(3):
-            one_step()
-        join()
-        stream.synchronize()
-        if not args.no_graph and G >= 4:
-            counter[0] = 0
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                fork()
-                for _ in range(G):
-                    one_step()
-                join()
-            counter[0] = 0
-
-        def run_steps(n):
-            done = 0
-            if graph is not None:
-                while n - done >= G and counter[0] % G == 0:
-                    graph.replay()
-                    done += G
-                    counter[0] += G
-            if done < n:
-                fork()
-                while done < n:
-                    one_step()
-                    done += 1
-                join()
-
-        def sync_all():
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        run_steps(max(3, args.warmup))
-        # realign to a graph boundary so that the timed region is mostly graph replays
-        if graph is not None and counter[0] % G != 0:
-            run_steps(G - counter[0] % G)
-        sync_all()
-        launches0 = sum(e_.launch_count for e_ in engs)
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        n_done = 0
-        chunk = G if graph is not None else 100
-        while n_done < args.steps:
-            n = min(chunk, args.steps - n_done) if world > 1 else args.steps - n_done
-            run_steps(n)
-            n_done += n
-            if world > 1:
-                # optional cross-GPU metrics gather (north star: NCCL only for this): one small all-reduce per chunk
-                metrics[0] = rew_ring[(counter[0] - 1) % R_obs].sum()
-                dist.all_reduce(metrics)
-        ev1.record(stream)
-        sync_all()
-        ms = ev0.elapsed_time(ev1)
-        clk = clocks.stop() if rank == 0 else None
-        launches = sum(e_.launch_count for e_ in engs) - launches0
-        if graph is not None:
-            launches = args.steps * groups             # replayed launches are not seen by the host-side counter
-        if any(e_.handover_timeouts for e_ in engs):   # overlapping step grids must never have lost a hand-over
-            raise RuntimeError("a per-block hand-over between step grids timed out: results of this run are invalid")
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    # optional cross-GPU metrics gather (north star: NCCL only for this): side stream, every 100 steps
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    metrics = torch.zeros(64, device=dev) if world > 1 else None
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    main = measure_workload(torch, dist, args.config, args, local_rank, rank, world, K, args.target_seconds, clocks=clocks,
+                            side=side, metrics=metrics)
+    runner = main['runner']
+    E, N, A, D, M = main['E'], main['N'], main['A'], main['D'], main['M']
+    gathers = int(metrics[1].item()) if metrics is not None else 0
+    runner.close()
+    del runner
+    torch.cuda.empty_cache()
 
     # ---- e2e: reference-facing call with HOST buffers (one engine holding all E envs of this GPU)
-    for e_ in engs:
-        e_.close()
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    kw = cfg['kw']
+    dev_scn = None if args.host_tables else cfg['mode']
     eng = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=rank * E, rew_coeff=cfg['rew'],
                           ep_time=args.ep_time, device_scenario=dev_scn, **kw)
     if dev_scn is None:
         goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank)
         eng.set_next_episode(goals, spawn, obst)
     eng.reset()
-    n_e2e = max(10, min(args.steps, args.e2e_steps))
+    n_e2e = max(10, min(max(args.steps, 100), args.e2e_steps))
     # page-locked host buffers (numpy views of pinned torch tensors): the DMA engine reads / writes them directly
     a_pin = torch.empty((8, E, N, 4), dtype=torch.float32).pin_memory()
     a_pin.copy_(torch.from_numpy(np.random.RandomState(5 + rank).uniform(-1, 1, (8, E, N, 4)).astype(np.float32)))
@@ -450,107 +533,101 @@ def run_cuda_arm(args):
     obs_h = torch.zeros((E, N, D), dtype=torch.float32).pin_memory().numpy()
     rew_h = torch.zeros((E, N), dtype=torch.float32).pin_memory().numpy()
     done_h = torch.zeros((E, N), dtype=torch.uint8).pin_memory().numpy()
-    for k in range(3):
-        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(n_e2e):
-        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+
+    def host_loop(n):
+        for k in range(3):
+            eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(n):
+            eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_s = host_loop(n_e2e)
     # the same loop with explicit cudaMemcpyAsync H2D / D2H around the kernel (QS_ZERO_COPY=0) instead of the default, in
     # which the kernel reads / writes the mapped page-locked host buffers itself; reported beside it
     os.environ['QS_ZERO_COPY'] = '0'
-    for k in range(3):
-        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(n_e2e):
-        eng.step_host(a_host[k % 8], obs_h, rew_h, done_h)
-    torch.cuda.synchronize()
-    e2e_copy_s = time.perf_counter() - t0
+    e2e_copy_s = host_loop(n_e2e)
     os.environ.pop('QS_ZERO_COPY', None)
     if world > 1:
         t = torch.tensor([e2e_s, e2e_copy_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, e2e_copy_s = float(t[0].item()), float(t[1].item())
 
-    # ---- extras (rank 0, single GPU): the same kernel (a) T steps per launch (qs_rollout: env block stays in registers,
-    #      every observation still written) and (b) at a 4x larger batch, where the GPU has enough warps to fill its
-    #      issue slots.  They explain the headline (which is latency-bound at 1.7 warps per SM sub-partition); they are
-    #      not the headline.
+    # ---- extras: they explain the headline, they are not the headline
     extra = {}
-    if rank == 0 and world == 1 and not args.no_extras:
-        def _events(fn, reps):
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); [fn() for _ in range(reps)]; e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) * 1e-3 / reps
-        T = 64
-        acts = act_ring[:T].contiguous()
-        o = torch.empty((T, E, N, D), device=dev); r = torch.empty((T, E, N), device=dev)
-        d_ = torch.empty((T, E, N), dtype=torch.uint8, device=dev)
-        eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_)
-        sec = _events(lambda: eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_), 8)
-        b_alg_ = 292 + 4 * D + (8.0 * M / N if M else 0.0)
-        extra['rollout'] = {'steps_per_launch': T, 'us_per_step': sec / T * 1e6, 'agent_steps_per_s': A * T / sec,
-                            'roofline_frac': b_alg_ * A * T / sec / 1e9 / hbm_peak()[0],
-                            'note': 'qs_rollout: T control steps per launch, all observations written'}
-        del o, r, d_
-        E4 = 4 * E
-        big = QuadSwarmEngine(num_envs=E4, seed=args.seed, device=local_rank, rew_coeff=cfg['rew'], ep_time=args.ep_time,
-                              device_scenario=dev_scn, **kw)
-        if dev_scn is None:
-            g4, s4, o4 = make_episode_tables(cfg, min(E4, 512), seed=77)
-            rep = E4 // min(E4, 512)
-            big.set_next_episode(np.tile(g4, (rep, 1, 1)), np.tile(s4, (rep, 1, 1)), None if o4 is None else np.tile(o4, (rep, 1, 1)))
-        big.reset()
-        Rb = 8
-        ab = (torch.rand((Rb, E4, N, 4), device=dev) * 2 - 1).contiguous()
-        ob = torch.empty((Rb, E4, N, D), device=dev); rb = torch.empty((Rb, E4, N), device=dev)
-        db = torch.empty((Rb, E4, N), dtype=torch.uint8, device=dev)
-        st2 = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(st2):
-            for k in range(Rb):
-                big.step(ab[k], obs_out=ob[k], rewards_out=rb[k], dones_out=db[k])
-            st2.synchronize()
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, stream=st2):
-                for k in range(Rb):
-                    big.step(ab[k], obs_out=ob[k], rewards_out=rb[k], dones_out=db[k])
-            gb.replay(); st2.synchronize()
-            sec = _events(gb.replay, 40) / Rb
-        extra['large_batch'] = {'envs': E4, 'agents': E4 * N, 'us_per_step': sec * 1e6, 'agent_steps_per_s': E4 * N / sec,
-                                'roofline_frac': b_alg_ * E4 * N / sec / 1e9 / hbm_peak()[0],
-                                'note': 'same kernel, one launch per control step, 4x the envs of the headline workload'}
-        big.close()
-        del ab, ob, rb, db
+    if not args.no_extras:
+        if world == 1:
+            def _events(fn, reps):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); [fn() for _ in range(reps)]; e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) * 1e-3 / reps
+            # (a) the same kernel, T steps per launch (qs_rollout: env block stays in registers, every observation written)
+            T = 64
+            g = torch.Generator(device=dev); g.manual_seed(3)
+            acts = (torch.rand((T, E, N, 4), device=dev, generator=g) * 2 - 1).contiguous()
+            o = torch.empty((T, E, N, D), device=dev); r = torch.empty((T, E, N), device=dev)
+            d_ = torch.empty((T, E, N), dtype=torch.uint8, device=dev)
+            eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_)
+            sec = _events(lambda: eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_), 8)
+            extra['rollout'] = {'steps_per_launch': T, 'us_per_step': sec / T * 1e6, 'agent_steps_per_s': A * T / sec,
+                                'roofline_frac': main['b_alg'] * A * T / sec / 1e9 / main['peak'],
+                                'note': 'qs_rollout: T control steps per launch, all observations written'}
+            del o, r, d_, acts
+            # (b) the other BASELINE configs and a 4x batch of the headline workload, same protocol (blocks of K chained launches)
+            per_cfg = {}
+            sub = argparse.Namespace(**vars(args))
+            sub.envs = 0
+            for name in ('c2', 'c4', 'c5'):
+                if name == args.config:
+                    continue
+                m = measure_workload(torch, dist, name, sub, local_rank, rank, world, min(K, 2000), 0.12)
+                per_cfg[name] = {'workload': CONFIGS[name]['desc'], 'us_per_step': m['us_per_step'], 'agent_steps_per_s': m['value'],
+                                 'roofline_frac': m['frac'], 'alg_bytes_per_agent_step': m['b_alg'], 'blocks': m['blocks']}
+                m['runner'].close()
+                torch.cuda.empty_cache()
+            extra['configs'] = per_cfg
+            sub.envs = 4 * E
+            m = measure_workload(torch, dist, args.config, sub, local_rank, rank, world, min(K, 2000), 0.12)
+            extra['large_batch'] = {'envs': 4 * E, 'agents': 4 * A, 'us_per_step': m['us_per_step'], 'agent_steps_per_s': m['value'],
+                                    'roofline_frac': m['frac'],
+                                    'note': 'same kernel, one launch per control step, 4x the envs of the headline workload'}
+            m['runner'].close()
+        else:
+            # BASELINE config c5 (8 drones x 4096 envs per GPU, obstacle-free, K=6) over all ranks, same protocol
+            sub = argparse.Namespace(**vars(args))
+            sub.envs = 0
+            m = measure_workload(torch, dist, 'c5', sub, local_rank, rank, world, min(K, 2000), 0.12, side=side, metrics=metrics)
+            extra['c5'] = {'workload': CONFIGS['c5']['desc'], 'n_gpus': world, 'envs_total': world * CONFIGS['c5']['E'],
+                           'us_per_step': m['us_per_step'], 'agent_steps_per_s': m['value'], 'roofline_frac_per_gpu': m['frac']}
+            m['runner'].close()
 
     if rank == 0:
-        value = world * A * args.steps / (ms * 1e-3)
-        peak, peak_src = hbm_peak()
-        b_alg = 292 + 4 * D + (8.0 * M / N if M else 0.0)
-        per_launch_bytes = b_alg * A
-        launch_s = ms * 1e-3 / args.steps
-        achieved = per_launch_bytes / launch_s / 1e9
         cpu = cpu_baseline_single(args.config) if (world == 1 and not args.no_cpu_baseline) else None
+        conf = bench_config(args, world)
         line = {
-            'metric': 'env agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'metric': 'env agent-steps/sec', 'value': main['value'], 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': main['med_ms'] / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f"{args.config}: {cfg['desc']}", 'envs_per_gpu': E, 'drones': N, 'obs_dim': D,
-                       'agents_per_gpu': A, 'ep_len': eng.ep_len,
-                       'episodes': 'generated on the device at every auto-reset' if dev_scn else 'host-generated tables, uploaded once',
-                       'l2': f'inputs larger than L2: action ring {R_act} x {A * 16 / 1e6:.2f} MB, observation rollout ring '
-                             f'{R_obs} x {A * D * 4 / 1e6:.2f} MB; env state ({A * 192 / 1e6:.1f} MB) is L2-resident by nature',
-                       'launch': (('one kernel per control step' if groups == 1 else
-                                   f'{groups} independent env blocks of {Eg} envs (double-buffered sampling), one kernel per block per control step')
-                                  + (f', CUDA graph of {G} steps' if graph is not None else '')),
-                       'parallelism': f'dp{world} (envs sharded, no step-time collective)'},
-            'clocks': clk,
+            'config': conf,
+            'timing': {'protocol': (f'{main["blocks"]} back-to-back blocks of exactly {K} control steps, each block bracketed by CUDA events on the '
+                                    f'launching stream; value / ms_per_step are the MEDIAN block (max over ranks per block)'),
+                       'blocks': main['blocks'], 'block_ms_median': main['med_ms'], 'block_ms_min': main['block_ms_min'],
+                       'block_ms_max': main['block_ms_max'],
+                       'episodes': ('generated on the device at every auto-reset' if dev_scn else 'host-generated tables, uploaded once'),
+                       'auto_resets': ('envs start at staggered ticks: every control step carries E / (ep_len + 1) auto-resets' if not args.lockstep
+                                       else 'envs in lock-step: all envs reset in the same step every ep_len + 1 steps'),
+                       'l2': (f'inputs and outputs larger than L2: rings of {main["ring_slots"]} slots, actions {main["ring_mb"]["actions"]:.0f} MB, '
+                              f'observations {main["ring_mb"]["observations"]:.0f} MB ({main["graphs"]} CUDA graphs of {main["steps_per_graph"]} launches '
+                              f'walk them in turn); env state ({A * 192 / 1e6:.1f} MB) is L2-resident by nature'),
+                       'launch': 'one kernel per control step, chained step grids replayed from CUDA graphs' if not args.no_graph else 'one kernel per control step, eager launches',
+                       'metrics_gather': (f'NCCL all-reduce of a 64-float vector every 100 steps on a side stream ({gathers} issued)' if world > 1 else 'n/a (1 GPU)')},
+            'clocks': main['clk'],
             'e2e': {'value': world * A * n_e2e / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': A * 16,
                     'd2h_bytes_per_step': A * (4 * D + 4 + 1), 'steps': n_e2e,
                     'explicit_copies_value': world * A * n_e2e / e2e_copy_s,
@@ -558,11 +635,11 @@ def run_cuda_arm(args):
                             'actions from and writes obs/rewards/dones to the mapped host buffers itself (zero-copy: the bytes '
                             'listed cross PCIe inside the timed region, no separate copy launches); explicit_copies_value: '
                             'cudaMemcpyAsync H2D actions, step kernel, cudaMemcpyAsync D2H obs/rewards/dones (QS_ZERO_COPY=0)'},
-            'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': measured_traffic(args.config) if E == cfg['E'] else None, 'peak_source': peak_src, 'alg_bytes_per_agent_step': b_alg,
-                         'alg_bytes_per_launch': per_launch_bytes / groups, 'launch_us': launch_s * 1e6,
-                         'note': f'{groups} concurrent launches of {Eg} envs per control step; achieved = bytes of all of them / step time'},
+            'gpu_launches': int(K),
+            'roofline': {'bound': 'hbm', 'achieved': main['achieved'], 'peak': main['peak'], 'unit': 'GB/s', 'frac': main['frac'],
+                         'traffic': measured_traffic(args.config) if E == cfg['E'] else None, 'peak_source': main['peak_src'],
+                         'alg_bytes_per_agent_step': main['b_alg'], 'alg_bytes_per_launch': main['b_alg'] * A,
+                         'launch_us': main['us_per_step']},
             'cpu_baseline': cpu,
         }
         line.update(extra)
@@ -584,7 +661,9 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=300)
     ap.add_argument('--no-extras', action='store_true', help='skip the rollout / large-batch explanatory measurements')
-    ap.add_argument('--groups', type=int, default=1, help='independent env blocks per GPU, each with its own launch chain')
+    ap.add_argument('--lockstep', action='store_true', help='start all envs at tick 0 (all auto-resets fall into the same step)')
+    ap.add_argument('--target-seconds', type=float, default=0.5,
+                    help='repeat the K-step block until about this much time is measured (the clock sampler needs load)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--host-tables', action='store_true', help='use host-generated episode tables even where a device generator exists')
     ap.add_argument('--no-cpu-baseline', action='store_true')

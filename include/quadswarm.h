@@ -13,7 +13,9 @@
  *   - E = envs on this GPU, N = drones per env (<= 32), A = E*N agents, D = qs_obs_dim(),
  *     M = qs_num_obstacles().  Agent index a = env*N + i everywhere.
  *   - Work is enqueued on the cudaStream_t passed as `stream` (a void*; NULL = default stream);
- *     only the *_host entry points synchronise.
+ *     only the *_host entry points synchronise.  The *_host entry points run on a private stream of the
+ *     handle and order themselves after the most recent asynchronous call of the handle (whatever stream it
+ *     used), so e.g. qs_set_goals(stream) followed by qs_step_host() is race-free.
  *   - Return value: 0 = QS_OK, negative = error; qs_last_error() gives the message (thread-local).
  *   - One handle per GPU; a handle is not thread-safe.
  */
@@ -215,13 +217,24 @@ int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f3
  * env_stats_dev [E,QS_NUM_ENV_STATS] (int32), agent_stats_dev [E,N,QS_NUM_AGENT_STATS] (float) */
 int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stats_dev, void* stream);
 
+/* Launch chaining between consecutive step grids.  Off (default): every qs_step grid waits for the complete stream
+ * predecessor (griddepcontrol.wait) before it touches anything — correct after ANY kernel, e.g. the policy network
+ * that wrote actions_dev.  On: the caller promises that between two consecutive qs_step / qs_rollout calls of this
+ * handle nothing else is enqueued on `stream` (pre-generated action rollouts, benchmarks, CUDA graphs of steps); the
+ * first step after any other call of the handle still does the full wait.  Chained grids prefetch their actions before
+ * the dependency wait and, where a grid needs more than one wave of CTAs (or the split shape is used), hand their envs
+ * over per CTA instead of waiting grid-wide.  Environment QS_CHAINED=1 sets the initial value.
+ * There is no reference counterpart (Sample Factory steps its envs from Python, one at a time). */
+int qs_set_chained(QsHandle* h, int on);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t qs_launch_count(const QsHandle* h);
 
 /* Consecutive qs_step / qs_rollout launches of a handle may overlap on the GPU: a CTA of the later grid waits for the
  * CTA of the earlier grid that owns the same envs (per-block hand-over).  The wait is bounded (~1 s); this
  * returns how many waits ran into the bound since qs_create — always 0 unless the device state was corrupted.
- * Synchronises the device. */
+ * A timed-out wait also latches a sticky error: every later qs_step / qs_rollout / qs_step_host of the handle returns
+ * QS_ERR_CUDA.  Synchronises the device. */
 int64_t qs_handover_timeouts(QsHandle* h);
 
 #ifdef __cplusplus

@@ -45,6 +45,9 @@ SITE_CEIL_U = 12       # (i)    uniforms v0 speed, v1..3 dir, v4 z, v5..7 omega 
 SITE_SPAWN_U = 13      # (i)    uniforms v0..2                         quadrotor_single.py:394
 SITE_RESET_YAW_U = 14  # (i)    uniforms v[k], k = rejection try       quadrotor_single.py:432-434
 SITE_SCENARIO_U = 15   # (slot) uniforms, env-level scenario generators (see scenario_gen.py)
+SITE_HOT = 16          # (i)    compact layout of the two draws every drone makes every step: SITE_OU v0..3 and
+                       #        SITE_SENSOR0 v0..8 are served from TWO blocks of this site, one word per normal pair
+                       #        (hot_normal below); every other site keeps the full-precision layout above
 
 RESET_YAW_MAX_TRIES = 64
 
@@ -74,6 +77,25 @@ def normal_pair(xa, xb):
     return r * math.cos(a), r * math.sin(a)
 
 
+def normal_pair16(x):
+    """Compact pair of one word: u1 = ((x >> 16) + 0.5) 2^-16, u2 = (x & 0xffff) 2^-16 (|n| <= 4.85)."""
+    u1 = ((x >> 16) + 0.5) * (2.0 ** -16)
+    u2 = (x & 0xFFFF) * (2.0 ** -16)
+    r = math.sqrt(-2.0 * math.log(u1))
+    a = 2.0 * math.pi * u2
+    return r * math.cos(a), r * math.sin(a)
+
+
+# (site, v) -> index of the normal inside the SITE_HOT stream: OU 0..3 -> 0..3, SENSOR0 0..8 -> 4..12;
+# stream index n lives in word n // 2 of the two blocks (words 0..3 = block 0, 4..7 = block 1), half n % 2
+def hot_index(site, v):
+    if site == SITE_OU and 0 <= v < 4:
+        return v
+    if site == SITE_SENSOR0 and 0 <= v < 9:
+        return 4 + v
+    return None
+
+
 class KeyedDraws:
     """(env, step_count)-scoped view of the keyed generator with a small block cache."""
 
@@ -97,6 +119,11 @@ class KeyedDraws:
         return u01(self._block(site, i, j, v // 4)[v % 4])
 
     def normal(self, site, i, j, v):
+        n = hot_index(site, v)
+        if n is not None:
+            word = n // 2
+            blk = self._block(SITE_HOT, i, 0, word // 4)
+            return normal_pair16(blk[word % 4])[n % 2]
         blk = self._block(site, i, j, v // 4)
         w = v % 4
         pair = normal_pair(blk[0], blk[1]) if w < 2 else normal_pair(blk[2], blk[3])

@@ -73,6 +73,7 @@ EXPORTS = {
     'qs_get_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_set_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_read_episode_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qs_set_chained': (C.c_int, [C.c_void_p, C.c_int]),
     'qs_launch_count': (C.c_int64, [C.c_void_p]),
     'qs_handover_timeouts': (C.c_int64, [C.c_void_p]),
 }

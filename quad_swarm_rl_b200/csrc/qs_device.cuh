@@ -80,11 +80,13 @@ struct DevState {
     float4* stats_agent;    // [A]                     latched at episode end
     int* ready;             // [E + 1] per step-kernel block: 1 = the block's env state is complete in L2 (pdl_mode 3);
                             //         ready[E] counts hand-over waits that timed out
+    int* err_flag;          // mapped page-locked host word: set to 1 by a step kernel whose hand-over wait timed out (sticky)
     int4* scn_i;            // [E]     device-side scenario state: scenario, period, next event tick, formation | growing << 8
     float4* scn_f;          // [E][3]  formation size / layer distance / largest size / speed; centre 1; centre 2
 };
 
 struct StepParams {
+    alignas(64) unsigned char obs_map[128];     // CUtensorMap of the caller's observation array (obs_bulk == 1), see quadswarm.cu
     DevState st;
     const float4* actions;  // [T][A]
     float* obs;             // [T][A][D] or [A][D]
@@ -103,6 +105,10 @@ struct StepParams {
     int env_id_offset;
     // observation staging (coalesced write-out): vector width V, Q = D / V, padded row stride Dp, magic = ceil(2^20 / Q)
     int obs_stage, obs_v, obs_q, obs_dp, obs_magic, smem_tile_off;
+    int obs_bulk;                       // write-out of the staged tile: 0 vector stores, 1 one TMA tensor store per warp tile
+                                        // (obs_map, D % 4 == 0), 2 one linear cp.async.bulk per warp tile (unpadded rows)
+    int chained;                        // 1: the stream predecessor of this launch is a step grid of the same handle (qs_set_chained):
+                                        //    actions are prefetched before the dependency wait; hand-over kernels skip the grid-wide wait
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
     int pdl_mode;                       // 0 off, 1 trigger dependents at kernel start, 2 trigger before the final stores,
                                         // 3 per-block hand-over: no grid-wide wait at all (see qs_step_kernel)
@@ -539,15 +545,15 @@ __device__ __noinline__ KickVO downwash_kick(RngKey key, int other, int me, floa
 //      192.. goal cells, 256.. goal z.  Cell (rid, cid) sits at (cid + 0.5 - L/2, W - 1 - rid + 0.5 - W/2) like the
 //      reference's get_cell_centers / obst_map indexing.  Twin: oracle/scenario_gen.py.
 __device__ __forceinline__ int nth_free_cell(unsigned long long mask, int r, int cells) {
-    int k = 0;
-#pragma unroll 1
-    for (; k < cells; ++k) {
-        if (!((mask >> k) & 1ull)) {
-            if (r == 0) break;
-            --r;
-        }
-    }
-    return k;
+    // index of the r-th (0-based) clear bit of `mask` among bits [0, cells); `cells` if there is none.
+    // find-n-th-set (fns) on the two 32-bit halves of the free-cell mask instead of a bit-by-bit scan.
+    const unsigned long long lim = cells >= 64 ? ~0ull : ((1ull << cells) - 1ull);
+    const unsigned long long fr = ~mask & lim;
+    const uint32_t lo = (uint32_t)fr, hi = (uint32_t)(fr >> 32);
+    const int nlo = __popc(lo);
+    if (r < nlo) return (int)__fns(lo, 0u, r + 1);
+    if (r - nlo < __popc(hi)) return 32 + (int)__fns(hi, 0u, r - nlo + 1);
+    return cells;
 }
 
 __device__ __forceinline__ float scenario_u(const RngKey& key, int v) {
@@ -568,6 +574,14 @@ __device__ __forceinline__ float2 cell_center(int cell, int L, int W) {
 }
 
 struct ORandomEpisode { V3 spawn, goal; int mode; };
+
+// word w of a uniform block
+__device__ __forceinline__ float u4_word(const float4& u, int w) { return w == 0 ? u.x : (w == 1 ? u.y : (w == 2 ? u.z : u.w)); }
+// floor(u * n) for a uniform already drawn (same integer arithmetic as scenario_pick)
+__device__ __forceinline__ int pick_of(float u, int n) {
+    const uint32_t k = (uint32_t)(u * 16777216.0f);
+    return (int)((k * (uint32_t)n) >> 24);
+}
 
 // o_base.py:123-153 (max_square_area_center): dynamic programme over the pillar map; returns the map cell (row * W + col)
 // at the centre of the largest free square.  Reference quirks kept: the first row / column of the table hold the MAP
@@ -592,13 +606,17 @@ __device__ __noinline__ int largest_free_square_cell(unsigned long long mask, in
 
 // pillar table of the env -> `obst_out[m]` for m = lane, lane + stride, ... ; this lane's spawn / goal returned
 // `scenario`: QS_SCENARIO_O_RANDOM, QS_SCENARIO_O_STATIC_SAME_GOAL or QS_SCENARIO_MIX (one of the two per episode, slot 321).
+// The draws are the keyed values scenario_u(key, v) (one Philox block serves four consecutive v: it is computed once
+// per four picks here, not once per pick).
 __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario, int i, int n_agents, int M, int L, int W, int lane_i,
                                                         int stride, float2* obst_smem, float2* obst_glob) {
     const int cells = L * W;
     unsigned long long mask = 0ull;
+    float4 ub = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int m = 0; m < M; ++m) {
-        const int r = scenario_pick(key, m, cells - m);
+        if ((m & 3) == 0) ub = rng_uniform4(key, SITE_SCENARIO_U, 0, 0, m >> 2);
+        const int r = pick_of(u4_word(ub, m & 3), cells - m);
         const int c = nth_free_cell(mask, r, cells);
         mask |= 1ull << c;
         if ((m % stride) == lane_i) {
@@ -612,19 +630,25 @@ __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario
     if (scenario == QS_SCENARIO_MIX) ep.mode = scenario_pick(key, 321, 2) == 0 ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
     const int free_cells = cells - M;
     unsigned long long ms = mask, mg = mask;
+    float4 us = ub, ug = ub;
+    int cs = 0, cg = 0;
+    const int kend = min(i, n_agents - 1);
 #pragma unroll 1
-    for (int k = 0; k <= i && k < n_agents; ++k) {
-        const int rs = scenario_pick(key, 64 + k, free_cells - k);
-        const int cs = nth_free_cell(ms, rs, cells);
-        ms |= 1ull << cs;
-        const int rg = scenario_pick(key, 192 + k, free_cells - k);
-        const int cg = nth_free_cell(mg, rg, cells);
-        mg |= 1ull << cg;
-        if (k == i) {
-            const float2 a = cell_center(cs, L, W), b = cell_center(cg, L, W);
-            ep.spawn.x = a.x; ep.spawn.y = a.y; ep.spawn.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 128 + k);
-            ep.goal.x = b.x; ep.goal.y = b.y; ep.goal.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 256 + k);
+    for (int k = 0; k <= kend; ++k) {
+        if ((k & 3) == 0) {
+            us = rng_uniform4(key, SITE_SCENARIO_U, 0, 0, (64 + k) >> 2);
+            ug = rng_uniform4(key, SITE_SCENARIO_U, 0, 0, (192 + k) >> 2);
         }
+        cs = nth_free_cell(ms, pick_of(u4_word(us, k & 3), free_cells - k), cells);
+        ms |= 1ull << cs;
+        cg = nth_free_cell(mg, pick_of(u4_word(ug, k & 3), free_cells - k), cells);
+        mg |= 1ull << cg;
+    }
+    {
+        const int k = kend;
+        const float2 a = cell_center(cs, L, W), b = cell_center(cg, L, W);
+        ep.spawn.x = a.x; ep.spawn.y = a.y; ep.spawn.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 128 + k);
+        ep.goal.x = b.x; ep.goal.y = b.y; ep.goal.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 256 + k);
     }
     if (ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL) {          // one goal for the whole swarm (o_static_same_goal.py:44-52)
         const float2 c = cell_center(largest_free_square_cell(mask, L, W), L, W);
@@ -645,10 +669,11 @@ __device__ __noinline__ ResetPose reset_pose(RngKey key, int i, V3 spawn, float 
     const float n = sqrtf(hx * hx + hy * hy);
     if (!(n < 0.00001f)) { hx /= n; hy /= n; }
     float sn = 0.f, cs = 1.f;
+    float4 uy = u;
 #pragma unroll 1
     for (int k = 0; k < RESET_YAW_MAX_TRIES; ++k) {
-        const float4 uy = rng_uniform4(key, SITE_RESET_YAW_U, i, 0, k >> 2);
-        const float uu = (k & 3) == 0 ? uy.x : (k & 3) == 1 ? uy.y : (k & 3) == 2 ? uy.z : uy.w;
+        if ((k & 3) == 0) uy = rng_uniform4(key, SITE_RESET_YAW_U, i, 0, k >> 2);
+        const float uu = u4_word(uy, k & 3);
         sincosf(-PI_F + (PI_F - (-PI_F)) * uu, &sn, &cs);
         if (cs * hx + sn * hy >= 0.5f) break;          // rotation[:, 0] = (cos, sin, 0)
     }

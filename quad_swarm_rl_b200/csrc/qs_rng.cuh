@@ -38,6 +38,7 @@ enum Site : uint32_t {
     SITE_SPAWN_U = 13,      // (i)   uniforms v0..2                              quadrotor_single.py:394
     SITE_RESET_YAW_U = 14,  // (i)   uniforms v[k], k = rejection try            quadrotor_single.py:432-434
     SITE_SCENARIO_U = 15,   // (slot) env-level scenario generators
+    SITE_HOT = 16,          // (i)   the draws every drone needs every step (OU + first sensor draw), compact layout below
 };
 
 constexpr int RESET_YAW_MAX_TRIES = 64;
@@ -92,6 +93,27 @@ __device__ __forceinline__ void philox4x32_10_x4(uint32_t c0, uint32_t c1, const
     for (int q = 0; q < 4; ++q) out[q] = make_uint4(a[q], b[q], c[q], d[q]);
 }
 
+// Two independent blocks in one rolled loop: the hot per-step draws (SITE_HOT, see hot_normals below).
+__device__ __forceinline__ void philox4x32_10_x2(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1, uint4 out[2]) {
+    uint32_t a[2] = {c0, c0}, b[2] = {c1, c1}, c[2] = {c2, c2}, d[2] = {0u, 1u};
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t hi0 = __umulhi(PHILOX_M0, a[q]), lo0 = PHILOX_M0 * a[q];
+            const uint32_t hi1 = __umulhi(PHILOX_M1, c[q]), lo1 = PHILOX_M1 * c[q];
+            a[q] = hi1 ^ b[q] ^ k0;
+            b[q] = lo1;
+            c[q] = hi0 ^ d[q] ^ k1;
+            d[q] = lo0;
+        }
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) out[q] = make_uint4(a[q], b[q], c[q], d[q]);
+}
+
 __device__ __forceinline__ uint32_t rng_c2(uint32_t site, uint32_t i, uint32_t j) { return site | (i << 8) | (j << 16); }
 
 __device__ __forceinline__ uint4 rng_block(const RngKey& k, uint32_t site, uint32_t i, uint32_t j, uint32_t block) {
@@ -116,6 +138,37 @@ __device__ __forceinline__ void normal_pair(uint32_t xa, uint32_t xb, float& n0,
     const float ang = 6.283185307179586f * (u2 - 0.5f);
     n0 = -r * fcos(ang);
     n1 = -r * fsin(ang);
+}
+
+// Compact normal pair of ONE word (hot per-step draws): u1 = ((x >> 16) + 0.5) 2^-16, u2 = (x & 0xffff) 2^-16.
+// |n| <= sqrt(2 ln 2^17) = 4.85; the two draws every drone makes every step (OU thrust noise, sigma 0.01, and the
+// sensor noise, sigma <= 0.01) then need 7 words = 2 Philox blocks instead of 4.  Twin: oracle/philox.py hot_normal.
+__device__ __forceinline__ void normal_pair16(uint32_t x, float& n0, float& n1) {
+    const float u1 = ((float)(x >> 16) + 0.5f) * 1.52587890625e-05f;        // 2^-16, exact
+    const float u2 = (float)(x & 0xffffu) * 1.52587890625e-05f;
+    const float r = fsqrt(-1.3862943611198906f * flg2(u1));
+    const float ang = 6.283185307179586f * (u2 - 0.5f);
+    n0 = -r * fcos(ang);
+    n1 = -r * fsin(ang);
+}
+
+// SITE_HOT layout (drone i, blocks 0 and 1 of counter word 3):
+//   block 0: word 0 -> OU normals 0,1; word 1 -> OU 2,3; word 2 -> sensor 0,1 (pos x, y); word 3 -> sensor 2,3 (pos z, vel x)
+//   block 1: word 0 -> sensor 4,5 (vel y, z); word 1 -> sensor 6,7 (gyro x, y); word 2 -> sensor 8 (gyro z), spare
+struct HotNormals { float ou[4]; float sn[9]; };
+__device__ __forceinline__ HotNormals hot_normals(const RngKey& k, uint32_t i) {
+    uint4 blk[2];
+    philox4x32_10_x2(k.env, k.step, rng_c2(SITE_HOT, i, 0), k.k0, k.k1, blk);
+    HotNormals h;
+    float spare;
+    normal_pair16(blk[0].x, h.ou[0], h.ou[1]);
+    normal_pair16(blk[0].y, h.ou[2], h.ou[3]);
+    normal_pair16(blk[0].z, h.sn[0], h.sn[1]);
+    normal_pair16(blk[0].w, h.sn[2], h.sn[3]);
+    normal_pair16(blk[1].x, h.sn[4], h.sn[5]);
+    normal_pair16(blk[1].y, h.sn[6], h.sn[7]);
+    normal_pair16(blk[1].z, h.sn[8], spare);
+    return h;
 }
 
 // 4 uniforms / 4 normals of one block

@@ -219,6 +219,59 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
     }
 }
 
+// ---- asynchronous write-out of a staged observation tile (bulk-copy / TMA engine, shared -> global) ----
+// A warp's rows are one contiguous span of the [T][A][D] observation array.  Instead of the copy loop above (161 executed
+// instructions per warp and step on c3, plus the LSU round trip), ONE elected lane hands the tile to the copy engine:
+//   obs_bulk 1 (D % 4 == 0): cp.async.bulk.tensor.3d store through a tensor map of the caller's observation array
+//               ([T][A][D] floats, box = [1][rows per tile][Dp]).  The box is as wide as the PADDED shared-memory row
+//               (Dp > D keeps the row writes at the 4-way bank-conflict optimum of 16-byte aligned rows); columns >= D
+//               and rows >= A lie outside the tensor and are clipped by the engine, so ragged last tiles need no code.
+//   obs_bulk 2 (otherwise): rows are staged unpadded (stride D: 2-way conflicts for D = 54) and the tile leaves with one
+//               linear cp.async.bulk when its byte count and global address are multiples of 16; the copy loop covers
+//               the rare remainder.
+// The generic-proxy writes of the lanes are ordered before the async proxy's reads by fence.proxy.async + __syncwarp; the
+// tile may be rewritten (or the CTA may exit) only after cp.async.bulk.wait_group.read 0 — bulk_drain() below.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tensor_s2g_3d(const void* tmap, const void* ssrc, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem_u32(ssrc))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_drain() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// rows [0, n_rows) of `tile` -> row `row0` of step `t` of the observation array (gdst = its address)
+__device__ __forceinline__ void emit_observation_tile(const StepParams& p, const float* tile, float* __restrict__ gdst, int row0, int t,
+                                                      int n_rows, int lane) {
+    if (p.obs_bulk == 1) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tensor_s2g_3d(&p.obs_map, tile, 0, row0, t);
+            bulk_commit();
+        }
+        return;
+    }
+    if (p.obs_bulk == 2) {
+        const uint32_t bytes = (uint32_t)(n_rows * p.D) * 4u;
+        if (((bytes | (uint32_t)(uintptr_t)gdst) & 15u) == 0u) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(gdst, tile, bytes);
+                bulk_commit();
+            }
+            return;
+        }
+    }
+    __syncwarp();
+    flush_observation_tile(p, tile, gdst, n_rows, lane);
+}
+
 // Copy the next-episode tables into the live episode of one env and respawn its drones
 // (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).  Called by ALL lanes of a warp (the branch around it is
 // warp-uniform); `do_reset` is per env.  Sets nvel to the velocity the neighbour block must see.
@@ -301,13 +354,17 @@ __device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { c[k] = QS_LD
 // word block b(t) left for b(t+1).  The writer publishes with barrier + __threadfence + st.release; the reader acquires
 // and reads the state with ld.global.cg (L1 is not coherent across the grids).  Any other kernel / copy on the stream
 // never triggers early, so it still sees, and is seen by, whole step grids.
-__device__ __forceinline__ void handover_acquire(int* ready, int* timeouts) {
+__device__ __forceinline__ void handover_acquire(int* ready, int* timeouts, int* err_flag) {
     int v = 0, spins = 0;
     do {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
         if (v == 0) __nanosleep(40);
     } while (v == 0 && ++spins < (1 << 24));          // ~1 s: a lost hand-over must not hang the GPU
-    if (v == 0) atomicAdd(timeouts, 1);               // reported by qs_handover_timeouts
+    if (v == 0) {                                     // the env block is stepped from state that may be incomplete:
+        atomicAdd(timeouts, 1);                       // counted (qs_handover_timeouts) and latched in the handle's sticky
+        if (err_flag != nullptr) *reinterpret_cast<volatile int*>(err_flag) = 1;      // error word: every later qs_step fails
+        __threadfence_system();
+    }
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(0) : "memory");
 }
 __device__ __forceinline__ void handover_release(int* ready) {
@@ -347,7 +404,7 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 // chosen by the launcher when a step grid does not fit the GPU in one wave or the split shape is used.
 template <int NP, bool SPLIT, bool SCN, bool HO>
 __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
-    extern __shared__ float2 s_obst[];
+    extern __shared__ __align__(128) float2 s_obst[];
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
     const int i = lane & (NP - 1);
@@ -361,12 +418,23 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     const long long a = (long long)env * p.N + i;
     const long long A = (long long)p.E * p.N;
 
+    // The actions of the first step are never written by a step grid, and whatever wrote them completed before the
+    // PREDECESSOR of this grid passed its own wait: they are loaded before the dependency wait (HBM latency hidden
+    // behind the predecessor's tail).
+    // Only for CHAINED launches (qs_set_chained: the stream predecessor is a step grid of this handle); otherwise the
+    // predecessor may be the kernel that produced the actions and the load follows the wait.
+    float4 av0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.chained && valid && role == 0) av0 = __ldg(p.actions + a);
+
     // Programmatic dependent launch: wait here for the PREVIOUS step's grid to complete (and flush) before touching any
     // state; the trigger that lets the NEXT step's grid start launching is issued just before this grid's final stores
     // (mode 2, default: hides ~0.3 us of launch latency per step; triggering at kernel start, mode 1, is 2 us SLOWER
     // because the early grid competes for issue slots while it spins).  Without the launch attribute both are no-ops.
     if (HO) {
-        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E);
+        // not chained: the stream predecessor may be a foreign kernel (it never triggers early, so this grid starts when
+        // it has completed; the wait makes its writes formally visible).  Chained step grids (qs_set_chained) skip it.
+        if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
     } else {
@@ -374,6 +442,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (p.pdl_mode == 4) asm volatile("griddepcontrol.launch_dependents;");      // trigger once the predecessor is done
     }
+
+    if (!p.chained && valid && role == 0) av0 = __ldg(p.actions + a);
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
     float2* s_obst_env = s_obst + env_local * p.M;
@@ -385,13 +455,24 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
     if (valid && role == 0) load_agent<HO>(st, a, s);      // state loads are issued before the pillar staging barrier
-    // stage this block's pillar tables (contiguous [envs_per_block][M] float2) in shared memory
+    // stage the pillar tables in shared memory.  Single-warp shape: every warp stages the tables of ITS envs (a contiguous
+    // [32 / NP][M] float2 span) and only a warp-level barrier follows; split shape: the block's two warps share them.
     if (p.use_obst) {
-        const long long base = (long long)blockIdx.x * envs_per_block * p.M;
-        const long long total = (long long)p.E * p.M;
-        for (int k = threadIdx.x; k < envs_per_block * p.M; k += blockDim.x)
-            if (base + k < total) s_obst[k] = ld_state<HO>(st.obst + base + k);
-        __syncthreads();
+        if (SPLIT) {
+            const long long base = (long long)blockIdx.x * envs_per_block * p.M;
+            const long long total = (long long)p.E * p.M;
+            for (int k = threadIdx.x; k < envs_per_block * p.M; k += blockDim.x)
+                if (base + k < total) s_obst[k] = ld_state<HO>(st.obst + base + k);
+            __syncthreads();
+        } else {
+            const int wenv = (threadIdx.x >> 5) * (32 / NP);                      // first env (block-local) of this warp
+            const long long base = ((long long)blockIdx.x * envs_per_block + wenv) * p.M;
+            const long long total = (long long)p.E * p.M;
+            float2* dst = s_obst + wenv * p.M;
+            for (int k = lane; k < (32 / NP) * p.M; k += 32)
+                if (base + k < total) dst[k] = ld_state<HO>(st.obst + base + k);
+            __syncwarp();
+        }
     }
     if (!valid) {
 #pragma unroll
@@ -428,18 +509,12 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             key.step = (uint32_t)ctr.step_count;
             const bool want = !p.last_obs_only || t == p.T - 1;
             Noise9 nz;
-            {   // first sensor-noise draw (3 Philox blocks, 3-way ILP), overlapped with the physics warp's integration
-                const uint32_t c2[4] = {rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0)};
-                const uint32_t c3[4] = {0u, 1u, 2u, 3u};
-                uint4 blk[4];
-                philox4x32_10_x4(key.env, key.step, c2, c3, key.k0, key.k1, blk);
-                const float4 na = normal4_of(blk[0]), nb = normal4_of(blk[1]);
-                float nc0, nc1;
-                normal_pair(blk[2].x, blk[2].y, nc0, nc1);
+            {   // first sensor-noise draw (SITE_HOT, 2 Philox blocks), overlapped with the physics warp's integration
+                const HotNormals hn = hot_normals(key, i);
                 const float on = p.sense_noise ? 1.f : 0.f;
-                nz.p[0] = on * POS_NOISE_STD * na.x; nz.p[1] = on * POS_NOISE_STD * na.y; nz.p[2] = on * POS_NOISE_STD * na.z;
-                nz.v[0] = on * VEL_NOISE_STD * na.w; nz.v[1] = on * VEL_NOISE_STD * nb.x; nz.v[2] = on * VEL_NOISE_STD * nb.y;
-                nz.w[0] = on * GYRO_NOISE_STD * nb.z; nz.w[1] = on * GYRO_NOISE_STD * nb.w; nz.w[2] = on * GYRO_NOISE_STD * nc0;
+                nz.p[0] = on * POS_NOISE_STD * hn.sn[0]; nz.p[1] = on * POS_NOISE_STD * hn.sn[1]; nz.p[2] = on * POS_NOISE_STD * hn.sn[2];
+                nz.v[0] = on * VEL_NOISE_STD * hn.sn[3]; nz.v[1] = on * VEL_NOISE_STD * hn.sn[4]; nz.v[2] = on * VEL_NOISE_STD * hn.sn[5];
+                nz.w[0] = on * GYRO_NOISE_STD * hn.sn[6]; nz.w[1] = on * GYRO_NOISE_STD * hn.sn[7]; nz.w[2] = on * GYRO_NOISE_STD * hn.sn[8];
             }
             Agent o;
             float nvel[3];
@@ -466,10 +541,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand2, gbase);
             }
             if (want) {
-                __syncwarp();
                 float* gbase_ptr = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
                 if (envs_here > 0)
-                    flush_observation_tile(p, s_tile, gbase_ptr + (long long)env_first * p.N * p.D, envs_here * p.N, lane);
+                    emit_observation_tile(p, s_tile, gbase_ptr + (long long)env_first * p.N * p.D, env_first * p.N,
+                                          p.last_obs_only ? 0 : t, envs_here * p.N, lane);
+                if (p.obs_bulk) bulk_drain();                         // the tile is rewritten in the next step
             }
             ctr.step_count += 1;
             bar_sync(3);                                              // hand-off arrays and tile are free again
@@ -490,32 +566,28 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         key.env = (uint32_t)(p.env_id_offset + env);
         key.step = (uint32_t)ctr.step_count;
 
-        // the draws every drone needs every step: OU thrust noise + first sensor-noise draw (4 Philox blocks, 4-way ILP)
+        // the draws every drone needs every step: OU thrust noise + first sensor-noise draw (SITE_HOT: 2 Philox blocks)
         Noise9 nz;
         float4 ou_z;
         if (SPLIT) {
-            ou_z = rng_normal4(key, SITE_OU, i, 0, 0);
+            const uint4 b0 = rng_block(key, SITE_HOT, i, 0, 0);
+            normal_pair16(b0.x, ou_z.x, ou_z.y);
+            normal_pair16(b0.y, ou_z.z, ou_z.w);
 #pragma unroll
             for (int k = 0; k < 3; ++k) { nz.p[k] = 0.f; nz.v[k] = 0.f; nz.w[k] = 0.f; }
         } else {
-            const uint32_t c2[4] = {rng_c2(SITE_OU, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0), rng_c2(SITE_SENSOR0, i, 0)};
-            const uint32_t c3[4] = {0u, 0u, 1u, 2u};
-            uint4 blk[4];
-            philox4x32_10_x4(key.env, key.step, c2, c3, key.k0, key.k1, blk);
-            ou_z = normal4_of(blk[0]);
-            const float4 na = normal4_of(blk[1]), nb = normal4_of(blk[2]);
-            float nc0, nc1;
-            normal_pair(blk[3].x, blk[3].y, nc0, nc1);
+            const HotNormals hn = hot_normals(key, i);
+            ou_z = make_float4(hn.ou[0], hn.ou[1], hn.ou[2], hn.ou[3]);
             const float on = p.sense_noise ? 1.f : 0.f;
-            nz.p[0] = on * POS_NOISE_STD * na.x; nz.p[1] = on * POS_NOISE_STD * na.y; nz.p[2] = on * POS_NOISE_STD * na.z;
-            nz.v[0] = on * VEL_NOISE_STD * na.w; nz.v[1] = on * VEL_NOISE_STD * nb.x; nz.v[2] = on * VEL_NOISE_STD * nb.y;
-            nz.w[0] = on * GYRO_NOISE_STD * nb.z; nz.w[1] = on * GYRO_NOISE_STD * nb.w; nz.w[2] = on * GYRO_NOISE_STD * nc0;
+            nz.p[0] = on * POS_NOISE_STD * hn.sn[0]; nz.p[1] = on * POS_NOISE_STD * hn.sn[1]; nz.p[2] = on * POS_NOISE_STD * hn.sn[2];
+            nz.v[0] = on * VEL_NOISE_STD * hn.sn[3]; nz.v[1] = on * VEL_NOISE_STD * hn.sn[4]; nz.v[2] = on * VEL_NOISE_STD * hn.sn[5];
+            nz.w[0] = on * GYRO_NOISE_STD * hn.sn[6]; nz.w[1] = on * GYRO_NOISE_STD * hn.sn[7]; nz.w[2] = on * GYRO_NOISE_STD * hn.sn[8];
         }
 
         // ================= per-drone part: QuadrotorSingle._step, quadrotor_single.py:341-357 =================
         float act[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid) {
-            const float4 av = p.actions[(long long)t * A + a];
+            const float4 av = (t == 0) ? av0 : __ldg(p.actions + ((long long)t * A + a));
             act[0] = av.x; act[1] = av.y; act[2] = av.z; act[3] = av.w;
         }
         float cmd[4];
@@ -642,8 +714,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 s.flags &= ~QS_FLAG_NO_COL_OBST;
                 // distance to goal of the FIRST-draw noisy position (quadrotor_multi.py:474)
                 if (SPLIT && p.sense_noise) {
-                    const float4 n0 = rng_normal4(key, SITE_SENSOR0, i, 0, 0);
-                    nz.p[0] = POS_NOISE_STD * n0.x; nz.p[1] = POS_NOISE_STD * n0.y; nz.p[2] = POS_NOISE_STD * n0.z;
+                    const uint4 b0 = rng_block(key, SITE_HOT, i, 0, 0);
+                    float n0, n1, n2, n3;
+                    normal_pair16(b0.z, n0, n1);
+                    normal_pair16(b0.w, n2, n3);
+                    nz.p[0] = POS_NOISE_STD * n0; nz.p[1] = POS_NOISE_STD * n1; nz.p[2] = POS_NOISE_STD * n2;
                 }
                 const float q = norm3((s.pos[0] + nz.p[0]) - s.goal[0], (s.pos[1] + nz.p[1]) - s.goal[1], (s.pos[2] + nz.p[2]) - s.goal[2]);
                 far35 = q > 3.5f; far5 = q > 5.0f;
@@ -854,14 +929,15 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         } else if (!p.last_obs_only || t == p.T - 1) {
             float* gbase = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
             if (p.obs_stage) {
-                // rows go to the warp's shared-memory tile, then out with coalesced vector stores
+                // rows go to the warp's shared-memory tile, then out through the bulk-copy engine (or coalesced vector stores)
                 const int slot = (lane / NP) * p.N + i;               // row of this drone inside the warp's tile
+                if (p.obs_bulk && p.T > 1) bulk_drain();              // the previous step's copy has read the tile
                 write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp);
-                __syncwarp();
                 const int env_first = blockIdx.x * envs_per_block + (threadIdx.x >> 5) * (32 / NP);
                 const int envs_here = min(32 / NP, p.E - env_first);
                 if (envs_here > 0)
-                    flush_observation_tile(p, s_tile, gbase + (long long)env_first * p.N * p.D, envs_here * p.N, lane);
+                    emit_observation_tile(p, s_tile, gbase + (long long)env_first * p.N * p.D, env_first * p.N,
+                                          p.last_obs_only ? 0 : t, envs_here * p.N, lane);
                 __syncwarp();
             } else {
                 write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, gbase + a * p.D);
@@ -882,6 +958,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
 
     if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
     if (valid) store_agent(st, a, s, goal_dirty);
+    if (!SPLIT && p.obs_bulk) bulk_drain();           // shared memory must outlive the bulk copy's reads
     if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
     if (HO) {
         if (SPLIT) bar_sync(4); else __syncthreads();
@@ -892,7 +969,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
 // Explicit reset of the masked envs: QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411.
 template <int NP>
 __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ StepParams p) {
-    extern __shared__ float2 s_obst[];
+    extern __shared__ __align__(128) float2 s_obst[];
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
     const int i = lane & (NP - 1);

@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>          // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
+
 #include "qs_step.cuh"
 
 using namespace qs;
@@ -26,6 +28,13 @@ struct QsHandle {
     int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
     int pdl_env;          // QS_PDL at the first step launch (-2 = not read yet, -1 = unset)
     int handover;         // -1 not decided yet, 0 grid-wide wait between step grids, 1 per-block hand-over (launch_step)
+    int chained;          // qs_set_chained: consecutive qs_step / qs_rollout launches follow each other directly on the stream
+    int last_was_step;    // the last launch this handle enqueued was a step / rollout grid
+    int bulk_mode;        // QS_OBS_BULK: -1 auto, 0 never use the bulk-copy engine for the observation write-out, 2 linear copies only
+    int* err_host;        // mapped page-locked word the step kernels set when a hand-over wait timed out (sticky)
+    cudaEvent_t ev_sync;  // the *_host entry points (own stream) order themselves after the caller-stream work below
+    cudaStream_t last_stream;   // stream of the most recent asynchronous call of this handle
+    bool async_pending;
     // staging for the *_host entry points (pinned host + device mirrors)
     float *d_actions, *d_obs, *d_rewards, *d_terms;
     uint8_t *d_dones, *d_mask;
@@ -88,7 +97,71 @@ static void fill_params(const QsHandle* h, StepParams& p) {
     p.obs_dp = (Q % 2 == 0) ? D + V : D;                 // odd number of V-wide words per row: fewer bank conflicts
     p.obs_magic = ((1 << 20) + Q - 1) / Q;
     p.obs_stage = (D <= 72) ? 1 : 0;
+    p.obs_bulk = 0;
+    p.chained = 0;
     p.scenario = c.scenario; p.grid_l = c.obst_grid[0]; p.grid_w = c.obst_grid[1];
+}
+
+// Observation write-out mode of a step launch (qs_step.cuh, emit_observation_tile): the bulk-copy engine needs a 16-byte
+// aligned destination in device memory; host-mapped (zero-copy) destinations keep the vector-store loop.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+static void choose_obs_writeout(const QsHandle* h, StepParams& p, bool dst_is_device_memory) {
+    static_assert(sizeof(CUtensorMap) == sizeof(p.obs_map), "tensor map size");
+    if (!p.obs_stage || !dst_is_device_memory || h->bulk_mode == 0) return;
+    if (((uintptr_t)p.obs & 15u) != 0) return;
+    if (p.D % 4 == 0 && h->bulk_mode != 2) {
+        // tensor map of the caller's observation array: [T][A][D] floats, box [1][rows of a warp tile][Dp] — the box is as
+        // wide as the padded shared-memory row; the columns >= D (and rows >= A of a ragged last tile) are clipped
+        EncodeTiledFn enc = tensor_map_encoder();
+        if (!enc) return;
+        const cuuint64_t T = p.last_obs_only ? 1 : (cuuint64_t)p.T;
+        const cuuint64_t A = (cuuint64_t)p.E * p.N;
+        const cuuint64_t gdim[3] = {(cuuint64_t)p.D, A, T};
+        const cuuint64_t gstr[2] = {(cuuint64_t)p.D * 4, A * (cuuint64_t)p.D * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)p.obs_dp, (cuuint32_t)((32 / h->NP) * p.N), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc((CUtensorMap*)p.obs_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.obs, gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+        p.obs_bulk = 1;
+    } else {
+        p.obs_bulk = 2;                   // one linear copy per warp tile: rows staged back to back
+        p.obs_dp = p.D;
+    }
+}
+
+// Every asynchronous call remembers its stream; the host-buffer entry points, which run on the handle's own
+// non-blocking stream, order themselves after it (join_caller_stream) so that e.g. a qs_set_goals / qs_set_state issued on
+// the caller's stream is complete before qs_step_host reads the state.  Nothing is recorded on the hot path.
+static void note_async(QsHandle* h, cudaStream_t s, bool is_step) {
+    h->last_was_step = is_step ? 1 : 0;
+    if (s != h->own_stream) { h->last_stream = s; h->async_pending = true; }
+}
+static void join_caller_stream(QsHandle* h) {
+    if (!h->async_pending) return;
+    h->async_pending = false;
+    if (cudaEventRecord(h->ev_sync, h->last_stream) == cudaSuccess && cudaStreamWaitEvent(h->own_stream, h->ev_sync, 0) == cudaSuccess) return;
+    cudaGetLastError();                  // stream gone or being captured: fall back to a full device synchronisation
+    cudaDeviceSynchronize();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -240,12 +313,16 @@ static int dispatch_np(int NP, F&& f) {
     return fail(QS_ERR_UNSUPPORTED, "num_agents > 32 is not supported by this build");
 }
 
-static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
+static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool obs_in_device_memory = true) {
+    if (h->err_host && *(volatile int*)h->err_host != 0)
+        return fail(QS_ERR_CUDA, "a per-block hand-over between step grids timed out earlier: the env state of this handle is "
+                                 "not trustworthy any more (qs_handover_timeouts); destroy the handle");
     // split kernel: physics warp + observer warp per 32 drones (QS_SPLIT=0/1 at qs_create overrides the heuristic)
     // Measured (profiles/r01_notes.md): splitting shortens one warp's dependency chain (32 envs: 6.9 -> 5.8 us per
     // launch, 8 x 1024 envs: 8.05 -> 7.17 us) but adds work, so it only pays while the GPU has idle issue slots, i.e.
     // up to about one physics warp per SM sub-partition (4 x 148 on B200).
     StepParams p = p_in;
+    choose_obs_writeout(h, p, obs_in_device_memory);
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
     const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
     const bool split = want_split && p.obs_stage && h->NP > 1;
@@ -253,7 +330,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     const int envs_per_block = (split ? 32 : kBlock) / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
-    smem = (smem + 15) / 16 * 16;
+    smem = (smem + 127) / 128 * 128;              // TMA sources are 128-byte aligned
     p.smem_tile_off = (int)(smem / sizeof(float));
     if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
     if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
@@ -293,7 +370,11 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
             h->handover = split || (long long)grid > (long long)per_sm * sms;
         }
     }
-    const int pdl_mode = h->handover ? 3 : (pdl_env >= 0 ? pdl_env : 2);
+    // The hand-over kernels pay off only between step grids that follow each other directly; an unchained handle uses
+    // the grid-wide wait (formally safe after any predecessor) and never pre-fetches across the dependency wait.
+    p.chained = (h->chained && h->last_was_step) ? 1 : 0;
+    const bool use_ho = h->handover && h->chained;
+    const int pdl_mode = use_ho ? 3 : ((pdl_env >= 0 && pdl_env != 3) ? pdl_env : 2);
     const bool use_pdl = pdl_mode != 0;
     p.pdl_mode = pdl_mode;
     cudaLaunchConfig_t lc = {};
@@ -302,10 +383,11 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
-    const cudaError_t lerr = cudaLaunchKernelEx(&lc, h->handover ? fn_ho : fn_wait, p);
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, use_ho ? fn_ho : fn_wait, p);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, s, true);
     return QS_OK;
 }
 
@@ -321,6 +403,7 @@ static int launch_reset(QsHandle* h, const StepParams& p, cudaStream_t s) {
     if (rc != QS_OK) return rc;
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, s, false);
     return QS_OK;
 }
 
@@ -369,6 +452,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
         h->split_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
         h->handover = -1;
         h->pdl_env = -2;
+        const char* c = getenv("QS_CHAINED");
+        h->chained = c ? (atoi(c) != 0) : 0;
+        const char* b = getenv("QS_OBS_BULK");
+        h->bulk_mode = b ? atoi(b) : -1;          // 0 vector stores only, 2 linear bulk copies only, else automatic
     }
     h->a_pad = (h->A + 31) / 32 * 32;
     // QuadrotorEnvMulti defaults, quadrotor_multi.py:91-94
@@ -433,6 +520,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_CUDA(cudaMallocHost((void**)&h->h_dones, A));
     QS_CUDA(cudaMallocHost((void**)&h->h_mask, E));
     QS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    QS_CUDA(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+    QS_CUDA(cudaHostAlloc((void**)&h->err_host, sizeof(int), cudaHostAllocMapped));
+    *h->err_host = 0;
+    QS_CUDA(cudaHostGetDevicePointer((void**)&st.err_flag, h->err_host, 0));
     *out = h;
     return QS_OK;
 }
@@ -449,6 +540,8 @@ extern "C" int qs_destroy(QsHandle* h) {
     cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);
     cudaFreeHost(h->h_dones); cudaFreeHost(h->h_mask);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+    if (h->err_host) cudaFreeHost(h->err_host);
     delete h;
     return QS_OK;
 }
@@ -466,6 +559,13 @@ extern "C" int64_t qs_handover_timeouts(QsHandle* h) {
     if (cudaSetDevice(h->device) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, h->st.ready + h->cfg.num_envs, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
+}
+
+extern "C" int qs_set_chained(QsHandle* h, int on) {
+    if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
+    h->chained = on ? 1 : 0;
+    h->last_was_step = 0;
+    return QS_OK;
 }
 
 extern "C" int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host) {
@@ -489,6 +589,7 @@ extern "C" int qs_set_next_episode(QsHandle* h, const uint8_t* env_mask_dev, con
                                                                          env_mask_dev, goals_dev, spawn_dev, obst_xy_dev);
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
     return QS_OK;
 }
 
@@ -499,6 +600,7 @@ extern "C" int qs_set_goals(QsHandle* h, const uint8_t* env_mask_dev, const floa
                                                                      goals_dev);
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
     return QS_OK;
 }
 
@@ -556,6 +658,7 @@ extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_h
     if (!h || !actions_host || !obs_host || !rewards_host || !dones_host) return fail(QS_ERR_INVALID_ARG, "null argument");
     QS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
+    join_caller_stream(h);
     const long long A = h->A;
     // pageable buffers go through the handle's pinned staging; page-locked caller buffers are used as they are
     const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rewards_host), pd = is_pinned(dones_host),
@@ -573,7 +676,11 @@ extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_h
                   cudaHostGetDevicePointer(&dd, dones_host, 0) == cudaSuccess &&
                   (!rew_terms_host || cudaHostGetDevicePointer(&dt, rew_terms_host, 0) == cudaSuccess);
         if (ok) {
-            int rc0 = qs_step(h, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, (float*)dt, s);
+            StepParams p;
+            fill_params(h, p);
+            p.actions = (const float4*)da;
+            p.obs = (float*)dob; p.rewards = (float*)dr; p.dones = (uint8_t*)dd; p.rew_terms = (float*)dt;
+            int rc0 = launch_step(h, p, s, /*obs_in_device_memory=*/false);
             if (rc0 != QS_OK) return rc0;
             QS_CUDA(cudaStreamSynchronize(s));
             return QS_OK;
@@ -602,6 +709,7 @@ extern "C" int qs_reset_host(QsHandle* h, const uint8_t* env_mask_host, float* o
     if (!h || !obs_host) return fail(QS_ERR_INVALID_ARG, "null argument");
     QS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
+    join_caller_stream(h);
     const long long A = h->A;
     if (env_mask_host) {
         memcpy(h->h_mask, env_mask_host, h->cfg.num_envs);
@@ -627,6 +735,7 @@ extern "C" int qs_get_state(QsHandle* h, float* agent_f32_dev, uint32_t* agent_u
                                                                   agent_u32_dev, env_i32_dev, h->M > 0 ? obst_xy_dev : nullptr);
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
     return QS_OK;
 }
 
@@ -640,6 +749,7 @@ extern "C" int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const floa
                                                                   h->M > 0 ? obst_xy_dev : nullptr);
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
     return QS_OK;
 }
 
@@ -651,5 +761,6 @@ extern "C" int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float*
                                                                                    env_stats_dev, agent_stats_dev);
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
     return QS_OK;
 }

@@ -203,6 +203,11 @@ class QuadSwarmEngine:
         L.check(self.lib.qs_read_episode_stats(self.h, _ptr(es), _ptr(ags), self._stream()))
         return es, ags
 
+    def set_chained(self, on=True):
+        """Promise (or retract) that consecutive step() / rollout() calls follow each other directly on the stream
+        (include/quadswarm.h, qs_set_chained): rollouts with pre-generated actions, CUDA graphs of steps."""
+        L.check(self.lib.qs_set_chained(self.h, int(bool(on))))
+
     @property
     def launch_count(self):
         return int(self.lib.qs_launch_count(self.h))

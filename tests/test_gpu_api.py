@@ -277,20 +277,26 @@ def test_batched_env_mix_on_device_reports_scenario_names():
 C4 = dict(num_agents=32, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega')
 
 
-@pytest.mark.parametrize('name,kw,E,dev_scn,pdl', [
-    ('c3_handover', C3, 4096, 'o_random', '3'), ('c3_auto', C3, 4096, 'o_random', None), ('c2_split_handover', C2, 1024, 'swap_goals', None),
-    ('c4_multiwave_handover', C4, 2048, 'swarm_vs_swarm', None), ('c3_small', C3, 37, None, '3'), ('c3_wait', C3, 300, None, '2')])
-def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, monkeypatch):
+@pytest.mark.parametrize('name,kw,E,dev_scn,pdl,chained', [
+    ('c3_handover', C3, 4096, 'o_random', '3', True), ('c3_auto', C3, 4096, 'o_random', None, True),
+    ('c2_split_handover', C2, 1024, 'swap_goals', None, True), ('c4_multiwave_handover', C4, 2048, 'swarm_vs_swarm', None, True),
+    ('c3_small', C3, 37, None, '3', True), ('c3_wait', C3, 300, None, '2', True),
+    ('c3_unchained', C3, 4096, 'o_random', None, False), ('c4_unchained', C4, 2048, 'swarm_vs_swarm', None, False),
+    ('c2_vector_stores', C2, 1024, 'swap_goals', None, True)])
+def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, chained, monkeypatch):
     """Consecutive step launches overlap on the GPU (programmatic dependent launch with a per-block hand-over instead of a
     grid-wide wait).  Replaying a CUDA graph of 96 step launches — no host gap between them — must give, bit for bit,
     what ONE launch that keeps the env block in registers gives, over several replays and across auto-resets."""
     from quad_swarm_rl_b200.engine import QuadSwarmEngine
     if pdl is not None:
         monkeypatch.setenv('QS_PDL', pdl)           # read by each engine at its first step launch
+    if name.endswith('vector_stores'):
+        monkeypatch.setenv('QS_OBS_BULK', '0')      # observation tiles leave with vector stores instead of the copy engine
     T, R = 96, 3
     N = kw['num_agents']
     mk = lambda: (QuadSwarmEngine(num_envs=E, seed=9, ep_time=1.0, device_scenario=dev_scn, **kw) if dev_scn else _engine(E, kw, ep_time=1.0)[0])
     e1, e2 = mk(), mk()
+    e1.set_chained(chained)                         # step grids follow each other directly (qs_set_chained)
     a = _actions(T, E, N)
     st = torch.cuda.Stream()
     obs = torch.empty((T, E, N, e1.D), device='cuda'); rew = torch.empty((T, E, N), device='cuda')
