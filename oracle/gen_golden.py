@@ -103,6 +103,16 @@ CASES = [
     dict(name='o_swap_goals_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.3, use_obstacles=True,
                                         quads_mode='o_swap_goals', obs_repr='xyz_vxyz_R_omega_floor'),
          T=700, seed=98, obs_stride=20),
+    # other physical models: per-drone constants derived by the reference are stored in the fixture
+    dict(name='defaultquad_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=1.0, quads_mode='static_diff_goal',
+                                       dynamics_params='DefaultQuad'), T=130, seed=101, obs_stride=1, plant='room4', plant_at=[30]),
+    dict(name='mediumquad_3', kw=dict(num_agents=3, neighbor_visible_num=2, ep_time=0.8, quads_mode='static_same_goal',
+                                      dynamics_params='MediumQuad'), T=100, seed=102, obs_stride=1),
+    dict(name='randomquad_relsampler_5', kw=dict(num_agents=5, neighbor_visible_num=2, ep_time=0.6, quads_mode='static_diff_goal',
+                                                 dynamics_params='RandomQuad', use_downwash=True,
+                                                 dyn_sampler_1={'class': 'RelativeSampler', 'noise_ratio': 0.05, 'sampler': 'normal'},
+                                                 dynamics_randomize_every=1),
+         T=140, seed=103, obs_stride=1, plant='room4', plant_at=[20, 90], construct_seed=777),
 ]
 
 
@@ -122,6 +132,8 @@ def _plants_obst(env, rs):
 
 def run_reference_case(case):
     kw = dict(case['kw'])
+    if 'construct_seed' in case:
+        np.random.seed(case['construct_seed'])     # RandomQuad / samplers draw from numpy's global stream at construction
     env = rh.make_reference_env(**kw)
     n = kw['num_agents']
     seed = case['seed']
@@ -144,6 +156,10 @@ def run_reference_case(case):
     plants_log = []
     ep_stats = []
     obst_log = []
+    from quad_swarm_rl_b200.quad_models import DYN_FIELDS
+    # constants in force after the first reset() (with dynamics_randomize_every the reset itself resamples them)
+    dyn_log = [(0, np.array([[r[k] for k in DYN_FIELDS] for r in rh.dynamics_rows(env)]))]
+    out['env_arm'] = np.array(float(env.quad_arm))
     if kw.get('use_obstacles'):
         obst_log.append((0, np.array(env.obstacles.pos_arr)[:, :2].copy()))
     for t in range(T):
@@ -152,6 +168,10 @@ def run_reference_case(case):
                 plants = _plants_cluster(n, plant_rs)
             elif case['plant'] == 'room':
                 plants = _plants_room(plant_rs)
+            elif case['plant'] == 'room4':
+                plants = [p for p in _plants_room(plant_rs) if p['i'] in (0, 3, 4, 5)]
+                for k, p in enumerate(plants):
+                    p['i'] = k % n
             else:
                 plants = _plants_obst(env, plant_rs)
             for p in plants:
@@ -176,6 +196,7 @@ def run_reference_case(case):
             states[k].append(snap[k])
         if d[0]:
             ep_stats.append((t, {k: float(v) for k, v in inf[0]['episode_extra_stats'].items()}))
+            dyn_log.append((t + 1, np.array([[r[k] for k in DYN_FIELDS] for r in rh.dynamics_rows(env)])))
             if kw.get('use_obstacles'):
                 obst_log.append((t + 1, np.array(env.obstacles.pos_arr)[:, :2].copy()))
     out.update(actions=actions, rewards=rewards, dones=dones, infos=infos, goals=goals,
@@ -186,6 +207,7 @@ def run_reference_case(case):
                plant_rot=np.array([p[4] for p in plants_log]).reshape(-1, 3, 3),
                plant_omega=np.array([p[5] for p in plants_log]).reshape(-1, 3),
                ep_stats_json=np.array(json.dumps(ep_stats)),
+               dyn_t=np.array([t for t, _ in dyn_log], dtype=int), dyn_rows=np.array([r for _, r in dyn_log]),
                obst_t=np.array([t for t, _ in obst_log], dtype=int),
                obst_xy=np.array([o for _, o in obst_log]),
                case_json=np.array(json.dumps(dict(name=case['name'], kw=kw, T=T, seed=seed,

@@ -43,7 +43,8 @@ def make_reference_env(num_agents=8, ep_time=15.0, obs_repr='xyz_vxyz_R_omega', 
                        neighbor_obs_type='pos_vel', use_obstacles=False, obst_density=0.2, obst_size=0.6,
                        obst_spawn_area=(8.0, 8.0), use_downwash=False, use_numba=True, quads_mode='static_same_goal',
                        room_dims=(10., 10., 10.), rew_coeff=None, collision_hitbox_radius=2.0,
-                       collision_falloff_radius=4.0, sense_noise='default', quiet=True):
+                       collision_falloff_radius=4.0, sense_noise='default', quiet=True, dynamics_params='Crazyflie',
+                       dyn_sampler_1=None, dynamics_change=None, dynamics_randomize_every=None):
     _ensure_path()
     from gym_art.quadrotor_multi.quadrotor_multi import QuadrotorEnvMulti
     if rew_coeff is None:
@@ -58,10 +59,11 @@ def make_reference_env(num_agents=8, ep_time=15.0, obs_repr='xyz_vxyz_R_omega', 
             use_obstacles=use_obstacles, obst_density=obst_density, obst_size=obst_size,
             obst_spawn_area=list(obst_spawn_area), use_downwash=use_downwash, use_numba=use_numba,
             quads_mode=quads_mode, room_dims=list(room_dims), use_replay_buffer=False,
-            quads_view_mode=['topdown'], quads_render=False, dynamics_params='Crazyflie', raw_control=True,
-            raw_control_zero_middle=True, dynamics_randomize_every=None,
-            dynamics_change=dict(noise=dict(thrust_noise_ratio=0.05), damp=dict(vel=0, omega_quadratic=0)),
-            dyn_sampler_1=None, sense_noise=sense_noise, init_random_state=False)
+            quads_view_mode=['topdown'], quads_render=False, dynamics_params=dynamics_params, raw_control=True,
+            raw_control_zero_middle=True, dynamics_randomize_every=dynamics_randomize_every,
+            dynamics_change=(dynamics_change if dynamics_change is not None else
+                             dict(noise=dict(thrust_noise_ratio=0.05), damp=dict(vel=0, omega_quadratic=0))),
+            dyn_sampler_1=dyn_sampler_1, sense_noise=sense_noise, init_random_state=False)
     return env
 
 
@@ -103,3 +105,23 @@ def snapshot(env):
         goal=np.array([e.goal for e in env.envs]),
         tick=np.array([e.tick for e in env.envs]),
     )
+
+
+def dynamics_rows(env):
+    """Per-drone derived constants of the reference env (QuadrotorDynamics.update_model, quadrotor_dynamics.py:104-166) as
+    dicts in the layout of quad_swarm_rl_b200.quad_models.DYN_FIELDS."""
+    rows = []
+    for e in env.envs:
+        d = e.dynamics
+        c = dict(mass=float(d.mass), inv_mass=1.0 / float(d.mass), ixx=float(d.inertia[0]), iyy=float(d.inertia[1]),
+                 izz=float(d.inertia[2]), inv_ixx=1.0 / float(d.inertia[0]), inv_iyy=1.0 / float(d.inertia[1]),
+                 inv_izz=1.0 / float(d.inertia[2]), tau_up=float(d.motor_tau_up), tau_down=float(d.motor_tau_down),
+                 linearity=float(d.motor_linearity), ou_sigma=float(d.thrust_noise.sigma), c_drag=float(d.C_rot_drag),
+                 c_roll=float(d.C_rot_roll), vel_damp=float(d.vel_damp), omega_quadratic=float(d.damp_omega_quadratic),
+                 arm=float(d.arm), reserved0=0., reserved1=0., reserved2=0.)
+        pp = np.asarray(d.model.prop_pos)
+        for m in range(4):
+            c[f'thrust_max{m}'], c[f'torque_max{m}'] = float(d.thrust_max[m]), float(d.torque_max[m])
+            c[f'px{m}'], c[f'py{m}'], c[f'pz{m}'] = float(pp[m, 0]), float(pp[m, 1]), float(pp[m, 2])
+        rows.append(c)
+    return rows

@@ -8,7 +8,7 @@ import json
 
 import numpy as np
 
-from .quadswarm_oracle import EnvConfig, OracleEnv, ReplayRng, ReferenceEpisodeSource
+from .quadswarm_oracle import EnvConfig, OracleEnv, ReplayRng, ReferenceEpisodeSource, quad_params_from_constants
 from .gen_golden import INFO_KEYS
 
 
@@ -33,7 +33,43 @@ def replay_golden(g, make_scenario):
     n = cfg.num_agents
     rng = ReplayRng(seed, seed + 1, [seed + 100 + i for i in range(n)])
     scenario = make_scenario(kw.get('quads_mode', 'static_same_goal'), cfg, rng.py)
-    env = OracleEnv(cfg, rng, ReferenceEpisodeSource(scenario))
+    params, dyn_t = None, None
+    if 'dyn_rows' in g and kw.get('dynamics_params', 'Crazyflie') != 'Crazyflie':
+        from quad_swarm_rl_b200.quad_models import DYN_FIELDS
+        dyn_t = [int(t) for t in g['dyn_t']]
+        to_params = lambda rows: [quad_params_from_constants(dict(zip(DYN_FIELDS, r))) for r in rows]
+        params = to_params(g['dyn_rows'][0])
+    env = OracleEnv(cfg, rng, ReferenceEpisodeSource(scenario), params=params)
+    if params is not None:
+        env.env_arm = float(g['env_arm'])
+        env.collision_threshold = cfg.collision_hitbox_radius * env.env_arm
+        env.collision_falloff_threshold = cfg.collision_falloff_radius * env.env_arm
+        if kw.get('dynamics_randomize_every'):
+            # The reference resamples inside each drone's _reset when (traj_count + 1) % every == 0
+            # (quadrotor_single.py:389-390), drawing from numpy's global stream.  The product's samplers
+            # (quad_swarm_rl_b200/quad_models.py) run here on that same stream, in the same place: they must reproduce the
+            # constants the reference derived (rows of the fixture) AND leave the stream where the reference left it.
+            from quad_swarm_rl_b200.quad_models import DynamicsSource, derive_constants
+            every = int(kw['dynamics_randomize_every'])
+            change = kw.get('dynamics_change') or dict(noise=dict(thrust_noise_ratio=0.05), damp=dict(vel=0, omega_quadratic=0))
+            srcs = [DynamicsSource(kw['dynamics_params'], change, kw.get('dyn_sampler_1'), rs=np.random.RandomState(0)) for _ in range(n)]
+            for s_ in srcs:
+                s_.rs = rng.py
+            resets = [0] * n
+            env.dyn_checked = 0
+
+            def dyn_source(i):
+                k = resets[i]
+                resets[i] += 1
+                if (k + 1) % every != 0:
+                    return None
+                c = derive_constants(srcs[i].sample())
+                ref = dict(zip(DYN_FIELDS, g['dyn_rows'][k][i]))
+                for key in DYN_FIELDS:
+                    np.testing.assert_allclose(c[key], ref[key], rtol=1e-12, atol=1e-300, err_msg=f'resample {k} drone {i} {key}')
+                env.dyn_checked += 1
+                return quad_params_from_constants(c)
+            env.dyn_source = dyn_source
     out = dict(obs0=env.reset())
     rewards = np.zeros((T, n))
     dones = np.zeros((T, n), dtype=bool)

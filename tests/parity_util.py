@@ -210,6 +210,103 @@ class DevicePair(Pair):
         pass
 
 
+class SampledPair(Pair):
+    """Full-size engine (E_total envs, the BASELINE shapes) checked against the oracle on a SAMPLE of its envs: the keyed
+    random draws make env e's trajectory a function of (seed, global env id, actions) only, so `OracleEnv(env_id=e)`
+    reproduces exactly what the engine's env e must do while all the other envs run beside it.  The engine therefore runs
+    the kernel instantiation, grid shape and launch chaining of the benchmark; run_parity() sees only the sampled rows.
+    `device_scenario` / `source_factory` as in DevicePair (no host tables), or host tables when both are None."""
+
+    def __init__(self, E_total, sample, kw, seed, device_scenario=None, source_factory=None, chained=False, table_seed=5,
+                 rew_coeff=None):
+        self.E_total = E_total
+        self.sample = list(sample)
+        self.E, self.kw, self.N = len(self.sample), dict(kw), kw['num_agents']
+        self.engine = QuadSwarmEngine(num_envs=E_total, seed=seed, device_scenario=device_scenario, rew_coeff=rew_coeff, **kw)
+        self.engine.set_chained(chained)
+        self.ocfg = cfg_to_oracle(kw)
+        if rew_coeff:
+            self.ocfg.rew_coeff.update(rew_coeff)
+        self.table_idx = 0
+        self.tables = None
+        if device_scenario is None:
+            rs = np.random.RandomState(table_seed)
+            self.tables = make_tables(rs, E_total, self.N, self.engine.M, kw.get('use_obstacles', False), episodes=3)
+        self.oracles = []
+        for e in self.sample:
+            if device_scenario is None:
+                eps = [dict(goals=t['goals'][e].astype(np.float64), spawn=t['spawn'][e].astype(np.float64),
+                            obst_xy=None if t['obst'] is None else t['obst'][e].astype(np.float64)) for t in self.tables]
+                src = qo.TableEpisodeSource(eps, approch_goal_metric=0.5)
+            else:
+                src = source_factory()
+            self.oracles.append(qo.OracleEnv(self.ocfg, qo.PhiloxRng(seed), src, env_id=e))
+        self._gen = torch.Generator(device=self.engine.device)
+        self._gen.manual_seed(seed + 77)
+        self._idx = torch.as_tensor(self.sample, device=self.engine.device, dtype=torch.long)
+        self._mask = torch.zeros(E_total, dtype=torch.uint8, device=self.engine.device)
+        self._mask[self._idx] = 1
+        if self.tables is not None:
+            self._push_table(0)
+
+    def _push_table(self, k):
+        if self.tables is not None:
+            t = self.tables[min(k, len(self.tables) - 1)]
+            self.engine.set_next_episode(t['goals'], t['spawn'], t['obst'])
+
+    def reset(self):
+        obs_o = np.stack([o.reset() for o in self.oracles])
+        obs_d = self.engine.reset()[self._idx].cpu().numpy().astype(np.float64)
+        self.table_idx = 1
+        self._push_table(1)
+        return obs_d, obs_o
+
+    def step(self, actions):
+        """actions float32 [len(sample),N,4]; every other env gets its own random actions"""
+        dev = self.engine.device
+        a_all = torch.rand((self.E_total, self.N, 4), device=dev, generator=self._gen) * 2 - 1
+        a_all[self._idx] = torch.as_tensor(actions, device=dev)
+        obs, rew, done = self.engine.step(a_all.contiguous(), with_terms=True)
+        ix = self._idx
+        out_d = dict(obs=obs[ix].cpu().numpy().astype(np.float64), rewards=rew[ix].cpu().numpy().astype(np.float64),
+                     dones=done[ix].cpu().numpy().astype(bool), terms=self.engine.rew_terms[ix].cpu().numpy().astype(np.float64))
+        res = [o.step(actions[e].astype(np.float64)) for e, o in enumerate(self.oracles)]
+        out_o = dict(obs=np.stack([r[0] for r in res]), rewards=np.array([[float(x) for x in r[1]] for r in res]),
+                     dones=np.array([r[2] for r in res], dtype=bool), infos=[r[3] for r in res])
+        if out_o['dones'].any():
+            self.table_idx += 1
+            self._push_table(self.table_idx)
+        return out_d, out_o
+
+    def sync_device_from_oracle(self):
+        st = self.oracle_state()                       # rows of the sampled envs
+        cur = self.engine.get_state()
+        ix = self._idx.cpu()
+        st['env_i32'][:, 3] = cur['env_i32'][ix.to(cur['env_i32'].device), 3].cpu()
+        if getattr(self.oracles[0].source, 's', None) is None:
+            base = 4 + L.QS_NUM_ENV_STATS
+            st['env_i32'][:, base:] = cur['env_i32'][ix.to(cur['env_i32'].device), base:].cpu()
+        dev = self.engine.device
+        for k in ('agent_f32', 'agent_u32', 'env_i32'):
+            cur[k][self._idx] = st[k].to(dev)
+        if st.get('obst_xy') is not None and self.engine.M > 0:
+            ob = cur['obst_xy'].clone()
+            ob[self._idx] = st['obst_xy'].to(dev)
+            cur['obst_xy'] = ob
+        self.engine.set_state(cur, env_mask=self._mask)
+
+    def device_fields(self):
+        st = self.engine.get_state()
+        ix = self._idx
+        af = st['agent_f32'][ix].cpu().numpy().astype(np.float64)
+        au = st['agent_u32'][ix].cpu().numpy().view(np.uint32)
+        out = {k: af[..., a:b] for k, (a, b) in STATE_F32_FIELDS.items()}
+        out['flags'] = au[..., 0]
+        out['prev_col'] = au[..., 1]
+        out['env_i32'] = st['env_i32'][ix].cpu().numpy()
+        return out
+
+
 def run_parity(pair, T, rs, resync=20, rtol=1e-4, atol=1e-4, action_scale=1.0, check_state=True, hook=None):
     """Step both sides T times; returns a report dict.  Raises AssertionError on a real mismatch."""
     E, N = pair.E, pair.N

@@ -349,3 +349,31 @@ def test_dense_pillars_more_than_32_and_no_sensor_noise():
 def test_two_drones_one_env_minimal():
     """smallest multi-drone case: E = 1, N = 2, K = 1 (all neighbours)."""
     _run(dict(num_agents=2, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega', ep_time=0.4), E=1, T=60, seed=1400)
+
+
+# ---- full-size sampled parity: the BENCHMARKED grid shapes / kernel instantiations / launch chaining against the oracle ----
+@pytest.mark.parametrize('name,chained', [('c3', False), ('c3', True), ('c2', True), ('c4', True), ('c4', False)])
+def test_full_size_sampled_parity(name, chained):
+    """BASELINE shapes (c2 8x1024, c3 8x4096, c4 32x2048), episodes generated on the device as in bench.py.  The keyed
+    draws make env e a function of (seed, global env id, actions) only, so three oracle envs with ids {0, E/2, E-1} check
+    the engine's rows 0, E/2, E-1 while all the other envs run beside them — i.e. the kernel instantiation, grid shape
+    and (chained = True: prefetch across the dependency wait, per-block hand-over for c2 / c4) launch chaining that the
+    benchmark times, not a 12-env stand-in."""
+    from oracle.scenario_gen import DeviceORandomSource, DeviceScenarioSource
+    from tests import parity_util as pu
+    if name == 'c3':
+        E, kw, scn, fac = 4096, dict(C3, ep_time=0.4), 'o_random', (lambda: DeviceORandomSource())
+        T, rew = 100, dict(quadcol_bin=5.0, quadcol_bin_smooth_max=4.0, quadcol_bin_obst=5.0)
+    elif name == 'c2':
+        E, kw, scn, fac = 1024, dict(C2, ep_time=0.4), 'static_same_goal', (lambda: DeviceScenarioSource('static_same_goal'))
+        T, rew = 100, dict(quadcol_bin=5.0, quadcol_bin_smooth_max=10.0)
+    else:
+        E, kw, scn, fac = 2048, dict(C4, ep_time=0.3), 'swarm_vs_swarm', (lambda: DeviceScenarioSource('swarm_vs_swarm'))
+        T, rew = 45, dict(quadcol_bin=5.0, quadcol_bin_smooth_max=10.0)
+    pair = pu.SampledPair(E, [0, E // 2, E - 1], kw, seed=24680, device_scenario=scn, source_factory=fac, chained=chained,
+                          rew_coeff=rew)
+    rep = pu.run_parity(pair, T, np.random.RandomState(12), resync=20)
+    print(name, chained, rep)
+    assert rep['dones'] >= 3 and rep['compared_env_steps'] >= 0.85 * 3 * T, rep
+    assert pair.engine.handover_timeouts == 0
+    pair.engine.close()
