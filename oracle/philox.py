@@ -50,6 +50,7 @@ SITE_HOT = 16          # (i)    compact layout of the two draws every drone make
                        #        (hot_normal below); every other site keeps the full-precision layout above
 
 RESET_YAW_MAX_TRIES = 64
+EPISODE_KEY_BIT = 0x80000000     # counter word 1 of the episode-defining draws = this bit | episode number (qs_rng.cuh)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

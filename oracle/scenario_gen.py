@@ -95,7 +95,7 @@ class DeviceORandomSource:
         return 'Scenario_o_static_same_goal' if self.mode == O_STATIC_SAME_GOAL else 'Scenario_o_random'
 
     def reset(self, env):
-        d = env.rng.draws
+        d = env.rng.episode_draws
         goals, spawn, obst = o_random_episode(d, env.num_agents, env.cfg.num_obstacles, self.L, self.W)
         if self.scenario == O_MIX:
             self.mode = O_RANDOM if _pick(d, 321, 2) == 0 else O_STATIC_SAME_GOAL
@@ -261,7 +261,7 @@ class DeviceScenarioSource:
         return formation_point(s['f'], N - h, k - h, s['size'], s['c2'], s['layer'], per_layer_of(s['f']))
 
     def reset(self, env):
-        d, N = env.rng.draws, env.num_agents
+        d, N = env.rng.episode_draws, env.num_agents
         mode = self.cfg_mode
         if mode == MIX:
             if N == 1:

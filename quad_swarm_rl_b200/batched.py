@@ -287,6 +287,7 @@ class BatchedExperienceReplay:
         # counters the snapshot must not rewind: the RNG step counter and the episode index stay those of the live env
         new['env_i32'][ridx, 1] = cur['env_i32'][ridx, 1]
         new['env_i32'][ridx, 3] = cur['env_i32'][ridx, 3]
+        new['env_i32'][ridx, 4 + L.QS_NUM_ENV_STATS + 16] = cur['env_i32'][ridx, 4 + L.QS_NUM_ENV_STATS + 16]   # episode number
         mask = torch.zeros(self.E, dtype=torch.uint8, device=eng.device)
         mask[ridx] = 1
         eng.set_state(new, env_mask=mask)

@@ -73,13 +73,19 @@ struct DevState {
     int4* env_ctr;          // [E] tick, step_count, svd_count, episode_idx
     int32_t* env_cnt;       // [E][QS_NUM_ENV_STATS] running episode counters
     float2* obst;           // [E][M]
-    float4* next_goal;      // [A]
-    float4* next_spawn;     // [A]  (w = 1: use it, w = 0: spawn at the goal)
+    float4* next_goal;      // [A]  host tables: goal; device-generated record: goal, w = cos(yaw) of the spawn pose
+    float4* next_spawn;     // [A]  host tables: spawn point (w = 1: use it, w = 0: spawn at the goal); record: final spawn
+                            //      position (jitter applied), w = sin(yaw)
     float2* next_obst;      // [E][M]
     int32_t* stats_env;     // [E][QS_NUM_ENV_STATS]  latched at episode end
     float4* stats_agent;    // [A]                     latched at episode end
     int* ready;             // [E + 1] per step-kernel block: 1 = the block's env state is complete in L2 (pdl_mode 3);
                             //         ready[E] counts hand-over waits that timed out
+    int2* epi;              // [E] x = number of the episode the env is running (every reset, explicit or automatic, starts the
+                            //     next one; keys the episode-generation draws), y = episode number the next-episode RECORD
+                            //     (next_goal / next_spawn / next_obst / next_scn_*) was generated for, 0 = none (qs_pregen_kernel)
+    int4* next_scn_i;       // [E]     scenario state of the pre-generated next episode
+    float4* next_scn_f;     // [E][3]
     int* err_flag;          // mapped page-locked host word: set to 1 by a step kernel whose hand-over wait timed out (sticky)
     int4* scn_i;            // [E]     device-side scenario state: scenario, period, next event tick, formation | growing << 8
     float4* scn_f;          // [E][3]  formation size / layer distance / largest size / speed; centre 1; centre 2
@@ -544,15 +550,30 @@ __device__ __noinline__ KickVO downwash_kick(RngKey key, int other, int me, floa
 //      exchange is needed.  Keyed draws (SITE_SCENARIO_U): value v = 0..M-1 pillar cells, 64.. spawn cells, 128.. spawn z,
 //      192.. goal cells, 256.. goal z.  Cell (rid, cid) sits at (cid + 0.5 - L/2, W - 1 - rid + 0.5 - W/2) like the
 //      reference's get_cell_centers / obst_map indexing.  Twin: oracle/scenario_gen.py.
+// position of the r-th (0-based) set bit of x; r < popc(x).  Binary search on popcounts (~25 instructions; the fns
+// instruction is emulated by a loop over the bits).
+__device__ __forceinline__ int nth_set_bit32(uint32_t x, int r) {
+    int pos = 0;
+    int c = __popc(x & 0xffffu);
+    if (r >= c) { r -= c; pos += 16; x >>= 16; }
+    c = __popc(x & 0xffu);
+    if (r >= c) { r -= c; pos += 8; x >>= 8; }
+    c = __popc(x & 0xfu);
+    if (r >= c) { r -= c; pos += 4; x >>= 4; }
+    c = __popc(x & 0x3u);
+    if (r >= c) { r -= c; pos += 2; x >>= 2; }
+    if (r >= (int)(x & 1u)) pos += 1;
+    return pos;
+}
+
 __device__ __forceinline__ int nth_free_cell(unsigned long long mask, int r, int cells) {
-    // index of the r-th (0-based) clear bit of `mask` among bits [0, cells); `cells` if there is none.
-    // find-n-th-set (fns) on the two 32-bit halves of the free-cell mask instead of a bit-by-bit scan.
+    // index of the r-th (0-based) clear bit of `mask` among bits [0, cells); `cells` if there is none
     const unsigned long long lim = cells >= 64 ? ~0ull : ((1ull << cells) - 1ull);
     const unsigned long long fr = ~mask & lim;
     const uint32_t lo = (uint32_t)fr, hi = (uint32_t)(fr >> 32);
     const int nlo = __popc(lo);
-    if (r < nlo) return (int)__fns(lo, 0u, r + 1);
-    if (r - nlo < __popc(hi)) return 32 + (int)__fns(hi, 0u, r - nlo + 1);
+    if (r < nlo) return nth_set_bit32(lo, r);
+    if (r - nlo < __popc(hi)) return 32 + nth_set_bit32(hi, r - nlo);
     return cells;
 }
 

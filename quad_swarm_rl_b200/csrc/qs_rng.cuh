@@ -49,6 +49,12 @@ struct RngKey {
     uint32_t step;        // per-env step counter
 };
 
+// Draws that define an EPISODE (pillar / spawn / goal generation, formation picks, spawn jitter, reset yaw) are keyed by the
+// env's episode number, not by its step counter: counter word 1 = EPISODE_KEY_BIT | episode number.  An episode is then a
+// function of (seed, env id, episode number) only, whenever and wherever it is generated — inside the reset path of the
+// step kernel, or ahead of time by qs_pregen_kernel.  Sites: SITE_SCENARIO_U streams 0 / 1, SITE_SPAWN_U, SITE_RESET_YAW_U.
+constexpr uint32_t EPISODE_KEY_BIT = 0x80000000u;
+
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
 // One block.  The round loop stays rolled: the kernel is instruction-fetch bound, not issue bound.

@@ -176,11 +176,14 @@ __device__ int shuffle_rank(const RngKey& key, int stream, int i, int g0, int g1
     return r;
 }
 
+__device__ __forceinline__ void scn_store_to(int4* si, float4* sf, const ScnState& s) {
+    si[0] = make_int4(s.mode, s.period, s.next, s.f | (s.growing << 8));
+    sf[0] = make_float4(s.size, s.layer, s.hi, s.speed);
+    sf[1] = make_float4(s.c1.x, s.c1.y, s.c1.z, 0.f);
+    sf[2] = make_float4(s.c2.x, s.c2.y, s.c2.z, 0.f);
+}
 __device__ __forceinline__ void scn_store(const DevState& st, int env, const ScnState& s) {
-    st.scn_i[env] = make_int4(s.mode, s.period, s.next, s.f | (s.growing << 8));
-    st.scn_f[3 * (long long)env + 0] = make_float4(s.size, s.layer, s.hi, s.speed);
-    st.scn_f[3 * (long long)env + 1] = make_float4(s.c1.x, s.c1.y, s.c1.z, 0.f);
-    st.scn_f[3 * (long long)env + 2] = make_float4(s.c2.x, s.c2.y, s.c2.z, 0.f);
+    scn_store_to(st.scn_i + env, st.scn_f + 3 * (long long)env, s);
 }
 __device__ __forceinline__ ScnState scn_load(const DevState& st, int env) {
     ScnState s;
@@ -225,8 +228,8 @@ __device__ V3 svs_goal(const ScnState& s, int N, int k) {
 }
 
 // scenario.reset() of the env's mode (for `mix`: of the scenario drawn for this episode).  Every lane of the env computes
-// the same scenario state; lane 0 stores it.
-__device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, int i, DevState st, int env) {
+// the same scenario state; lane 0 stores it to (si, sf): the env's live scenario state, or its next-episode record.
+__device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, int i, int4* si, float4* sf) {
     ScnState s;
     s.mode = cfg_mode;
     if (cfg_mode == QS_SCENARIO_MIX) {
@@ -267,7 +270,7 @@ __device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, i
         o.goal = formation_point(s.f, N, k, s.size, s.c1, s.layer, fm.per_layer);
     }
     o.next = s.next;
-    if (i == 0) scn_store(st, env, s);
+    if (i == 0) scn_store_to(si, sf, s);
     return o;
 }
 

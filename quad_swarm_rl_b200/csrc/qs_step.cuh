@@ -272,9 +272,67 @@ __device__ __forceinline__ void emit_observation_tile(const StepParams& p, const
     flush_observation_tile(p, tile, gdst, n_rows, lane);
 }
 
-// Copy the next-episode tables into the live episode of one env and respawn its drones
-// (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).  Called by ALL lanes of a warp (the branch around it is
-// warp-uniform); `do_reset` is per env.  Sets nvel to the velocity the neighbour block must see.
+// ---- episodes ----
+// An episode (pillar table, goals, spawn poses, scenario state) is a function of (seed, env id, episode number): its draws
+// are keyed by the episode number (qs_rng.cuh, EPISODE_KEY_BIT).  generate_episode() is therefore the same whether it runs
+// inside the reset path of a step / reset kernel or ahead of time in qs_pregen_kernel, which fills the env's NEXT-episode
+// record (next_goal / next_spawn / next_obst / next_scn_*) off the step's critical path; an (auto-)reset that finds the
+// record of its episode only copies it.  (Envs that reset in different steps, as in training with collision-event replay,
+// would otherwise put one ~20 k-instruction generator on the critical path of EVERY step.)
+struct EpisodeLane { V3 goal; ResetPose pose; int scn_next; float approach; };
+
+__device__ __forceinline__ RngKey episode_key(const StepParams& p, int env, int episode) {
+    RngKey k;
+    k.k0 = p.seed_lo; k.k1 = p.seed_hi;
+    k.env = (uint32_t)(p.env_id_offset + env);
+    k.step = EPISODE_KEY_BIT | (uint32_t)episode;
+    return k;
+}
+
+// true when the kernels generate the episodes (no host tables)
+template <bool SCN>
+__device__ __forceinline__ bool device_generated(const StepParams& p) {
+    return (p.use_obst && p.scenario != QS_SCENARIO_HOST_TABLES) || (SCN && !p.use_obst && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST);
+}
+
+// this lane's share of the env's next episode; the env-level parts go to (obst_smem,) obst_dst, scn_i_dst, scn_f_dst
+template <bool SCN>
+__device__ __forceinline__ EpisodeLane generate_episode(const StepParams& p, const RngKey& ekey, int i, float2* obst_smem,
+                                                        float2* obst_dst, int4* scn_i_dst, float4* scn_f_dst) {
+    EpisodeLane e;
+    e.scn_next = SCN_NEVER;
+    e.approach = p.approach_metric;
+    V3 spawn;
+    if (p.use_obst) {
+        // o_random / o_static_same_goal / their mix; every lane also writes its share of the pillar table
+        const ORandomEpisode ep = o_random_episode(ekey, p.scenario, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, obst_smem, obst_dst);
+        e.goal = ep.goal;
+        spawn = ep.spawn;
+        if (p.scenario != QS_SCENARIO_O_RANDOM)           // per-episode scenario id + its approch_goal_metric (o_base.py:16)
+            e.approach = ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL ? 1.0f : 0.5f;
+        if (i == 0) {
+            scn_i_dst[0] = make_int4(ep.mode, 0, SCN_NEVER, 0);
+            scn_f_dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            scn_f_dst[1] = make_float4(0.f, 0.f, 0.f, e.approach);
+            scn_f_dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else if (SCN) {
+        // goal formation of the env's scenario; drones spawn around their goals
+        const ScnOut o = scenario_reset(ekey, p.scenario, p.N, i, scn_i_dst, scn_f_dst);
+        e.goal = o.goal;
+        spawn = o.goal;
+        e.scn_next = o.next;
+    } else {
+        e.goal.x = 0.f; e.goal.y = 0.f; e.goal.z = 2.f;      // not reached: device_generated<SCN>() is false
+        spawn = e.goal;
+    }
+    e.pose = reset_pose(ekey, i, spawn, p.use_obst ? 0.1f : 2.0f);      // box: quadrotor_single.py:215-218
+    return e;
+}
+
+// Start the next episode of one env and respawn its drones (QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411).
+// Called by ALL lanes of a warp (the branch around it is warp-uniform); `do_reset` is per env.  Sets nvel to the velocity
+// the neighbour block must see.
 template <int NP, bool SCN>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
@@ -289,33 +347,50 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
             nvel[0] = sv.x; nvel[1] = sv.y; nvel[2] = sv.z;
         }
         st.slots[SL_STALE_VEL * st.a_pad + a] = make_float4(nvel[0], nvel[1], nvel[2], 0.f);
-        V3 spawn;
-        if (p.use_obst && p.scenario != QS_SCENARIO_HOST_TABLES) {
-            // o_random / o_static_same_goal / their mix: episode generated on the device; every valid lane also writes its
-            // share of the pillar table
-            const ORandomEpisode ep = o_random_episode(key, p.scenario, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, s_obst_env,
-                                                       st.obst + (long long)env * p.M);
-            s.goal[0] = ep.goal.x; s.goal[1] = ep.goal.y; s.goal[2] = ep.goal.z;
-            spawn = ep.spawn;
-            if (p.scenario != QS_SCENARIO_O_RANDOM) {         // per-episode scenario id + its approch_goal_metric (o_base.py:16)
-                approach = ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL ? 1.0f : 0.5f;
-                if (i == 0) {
-                    st.scn_i[env] = make_int4(ep.mode, 0, SCN_NEVER, 0);
-                    st.scn_f[3 * (long long)env + 1] = make_float4(0.f, 0.f, 0.f, approach);
+        const int2 ep = QS_LD(st.epi + env);
+        const int g = ep.x + 1;                                   // number of the episode that starts now
+        ResetPose rp;
+        if (device_generated<SCN>(p)) {
+            const long long e3 = 3 * (long long)env;
+            if (ep.y == g) {
+                // the episode was generated ahead of time: copy its record
+                const float4 ng = QS_LD(st.next_goal + a), ns = QS_LD(st.next_spawn + a);
+                s.goal[0] = ng.x; s.goal[1] = ng.y; s.goal[2] = ng.z;
+                rp.pos.x = ns.x; rp.pos.y = ns.y; rp.pos.z = ns.z; rp.cs = ng.w; rp.sn = ns.w;
+                if (p.use_obst) {
+                    for (int m = i; m < p.M; m += p.N) {
+                        const float2 ob = QS_LD(st.next_obst + (long long)env * p.M + m);
+                        st.obst[(long long)env * p.M + m] = ob;
+                        if (s_obst_env != nullptr) s_obst_env[m] = ob;
+                    }
                 }
+                const int4 nsi = QS_LD(st.next_scn_i + env);
+                const float4 f1 = QS_LD(st.next_scn_f + e3 + 1);
+                scn_next = nsi.z;
+                if (p.use_obst && p.scenario != QS_SCENARIO_O_RANDOM) approach = f1.w;
+                if (i == 0) {
+                    st.scn_i[env] = nsi;
+                    st.scn_f[e3] = QS_LD(st.next_scn_f + e3);
+                    st.scn_f[e3 + 1] = f1;
+                    st.scn_f[e3 + 2] = QS_LD(st.next_scn_f + e3 + 2);
+                }
+            } else {
+                const EpisodeLane e = generate_episode<SCN>(p, episode_key(p, env, g), i, s_obst_env, st.obst + (long long)env * p.M,
+                                                            st.scn_i + env, st.scn_f + e3);
+                s.goal[0] = e.goal.x; s.goal[1] = e.goal.y; s.goal[2] = e.goal.z;
+                rp = e.pose;
+                scn_next = e.scn_next;
+                if (p.use_obst && p.scenario != QS_SCENARIO_O_RANDOM) approach = e.approach;
             }
-        } else if (SCN && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST) {
-            // goal formation of the env's scenario, drawn on the device; drones spawn around their goals
-            const ScnOut o = scenario_reset(key, p.scenario, p.N, i, st, env);
-            s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
-            spawn = o.goal;
-            scn_next = o.next;
         } else {
-            const float4 g = st.next_goal[a], sp = st.next_spawn[a];
-            s.goal[0] = g.x; s.goal[1] = g.y; s.goal[2] = g.z;
-            spawn.x = sp.w != 0.f ? sp.x : g.x; spawn.y = sp.w != 0.f ? sp.y : g.y; spawn.z = sp.w != 0.f ? sp.z : g.z;
+            // host tables (qs_set_next_episode); the spawn jitter / yaw draws are episode-keyed like everywhere
+            const float4 gq = st.next_goal[a], sp = st.next_spawn[a];
+            s.goal[0] = gq.x; s.goal[1] = gq.y; s.goal[2] = gq.z;
+            V3 spawn;
+            spawn.x = sp.w != 0.f ? sp.x : gq.x; spawn.y = sp.w != 0.f ? sp.y : gq.y; spawn.z = sp.w != 0.f ? sp.z : gq.z;
+            rp = reset_pose(episode_key(p, env, g), i, spawn, p.use_obst ? 0.1f : 2.0f);
         }
-        const ResetPose rp = reset_pose(key, i, spawn, p.use_obst ? 0.1f : 2.0f);      // box: quadrotor_single.py:215-218
+        if (i == 0) st.epi[env] = make_int2(g, ep.y);
         apply_reset(s, rp);
         st.slots[SL_DIST_SUMS * st.a_pad + a] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -1018,6 +1093,32 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, p.use_obst ? min_pillar_dist2(p, s, s_obst_env) : 1e4f,
                           p.obs + a * p.D);
     if (valid) store_agent(st, a, s, true);
+}
+
+// Generates, for every env that does not hold one yet, the record of its NEXT episode (see generate_episode above).  Launched
+// by the library every few hundred steps between two step launches, and after every explicit reset: an env's record is
+// consumed at most once per episode, so the (expensive, latency-bound) generators never run inside a step.
+template <int NP>
+__global__ void __launch_bounds__(128) qs_pregen_kernel(const __grid_constant__ StepParams p) {
+    const DevState& st = p.st;
+    const int lane = threadIdx.x & 31;
+    const int i = lane & (NP - 1);
+    const int env = blockIdx.x * (blockDim.x / NP) + threadIdx.x / NP;
+    const bool valid = env < p.E && i < p.N;
+    const long long a = (long long)env * p.N + i;
+    int2 ep = make_int2(0, 0);
+    if (valid) ep = st.epi[env];
+    const int g = ep.x + 1;
+    const bool work = valid && ep.y != g;
+    if (work) {
+        const long long e3 = 3 * (long long)env;
+        const EpisodeLane e = generate_episode<true>(p, episode_key(p, env, g), i, nullptr, st.next_obst + (long long)env * p.M,
+                                                     st.next_scn_i + env, st.next_scn_f + e3);
+        st.next_goal[a] = make_float4(e.goal.x, e.goal.y, e.goal.z, e.pose.cs);
+        st.next_spawn[a] = make_float4(e.pose.pos.x, e.pose.pos.y, e.pose.pos.z, e.pose.sn);
+    }
+    __syncwarp();
+    if (work && i == 0) st.epi[env] = make_int2(ep.x, g);
 }
 
 }  // namespace qs

@@ -28,6 +28,8 @@ struct QsHandle {
     int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
     int pdl_env;          // QS_PDL at the first step launch (-2 = not read yet, -1 = unset)
     int handover;         // -1 not decided yet, 0 grid-wide wait between step grids, 1 per-block hand-over (launch_step)
+    int pregen_every;     // step launches between two launches of the next-episode generator (0 = never), QS_PREGEN overrides
+    int since_pregen;
     int chained;          // qs_set_chained: consecutive qs_step / qs_rollout launches follow each other directly on the stream
     int last_was_step;    // the last launch this handle enqueued was a step / rollout grid
     int bulk_mode;        // QS_OBS_BULK: -1 auto, 0 never use the bulk-copy engine for the observation write-out, 2 linear copies only
@@ -193,7 +195,7 @@ __global__ void k_set_goals(DevState st, int E, int N, const uint8_t* mask, cons
         st.slots[SL_GOAL * st.a_pad + t] = make_float4(goals[3 * t], goals[3 * t + 1], goals[3 * t + 2], 0.f);
 }
 
-static_assert(QS_STATE_ENV_I32 >= 4 + QS_NUM_ENV_STATS + 16, "env state row too short");
+static_assert(QS_STATE_ENV_I32 >= 4 + QS_NUM_ENV_STATS + 17, "env state row too short");
 __global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_t* au, int32_t* ei, float* obst) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long A = (long long)E * N;
@@ -230,7 +232,8 @@ __global__ void k_get_state(DevState st, int E, int N, int M, float* af, uint32_
             sc[4 + 4 * q] = __float_as_int(f.x); sc[5 + 4 * q] = __float_as_int(f.y);
             sc[6 + 4 * q] = __float_as_int(f.z); sc[7 + 4 * q] = __float_as_int(f.w);
         }
-        for (int k = 4 + QS_NUM_ENV_STATS + 16; k < QS_STATE_ENV_I32; ++k) e[k] = 0;      // reserved
+        e[4 + QS_NUM_ENV_STATS + 16] = st.epi[t].x;                                        // episode number (keys the episode draws)
+        for (int k = 4 + QS_NUM_ENV_STATS + 17; k < QS_STATE_ENV_I32; ++k) e[k] = 0;      // reserved
     }
     if (obst != nullptr && t < (long long)E * M) {
         const float2 ob = st.obst[t];
@@ -271,6 +274,7 @@ __global__ void k_set_state(DevState st, int E, int N, int M, const uint8_t* mas
         for (int q = 0; q < 3; ++q)
             st.scn_f[3 * t + q] = make_float4(__int_as_float(sc[4 + 4 * q]), __int_as_float(sc[5 + 4 * q]),
                                               __int_as_float(sc[6 + 4 * q]), __int_as_float(sc[7 + 4 * q]));
+        st.epi[t] = make_int2(e[4 + QS_NUM_ENV_STATS + 16], 0);          // a pre-generated next-episode record no longer applies
     }
     if (obst != nullptr && t < (long long)E * M && (mask == nullptr || mask[t / M]))
         st.obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
@@ -313,6 +317,8 @@ static int dispatch_np(int NP, F&& f) {
     return fail(QS_ERR_UNSUPPORTED, "num_agents > 32 is not supported by this build");
 }
 
+static int launch_pregen(QsHandle* h, cudaStream_t s);
+
 static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool obs_in_device_memory = true) {
     if (h->err_host && *(volatile int*)h->err_host != 0)
         return fail(QS_ERR_CUDA, "a per-block hand-over between step grids timed out earlier: the env state of this handle is "
@@ -321,6 +327,10 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // Measured (profiles/r01_notes.md): splitting shortens one warp's dependency chain (32 envs: 6.9 -> 5.8 us per
     // launch, 8 x 1024 envs: 8.05 -> 7.17 us) but adds work, so it only pays while the GPU has idle issue slots, i.e.
     // up to about one physics warp per SM sub-partition (4 x 148 on B200).
+    if (h->pregen_every > 0 && (h->since_pregen += p_in.T) >= h->pregen_every) {
+        int rcp = launch_pregen(h, s);          // next-episode records for the envs that consumed theirs (qs_pregen_kernel)
+        if (rcp != QS_OK) return rcp;
+    }
     StepParams p = p_in;
     choose_obs_writeout(h, p, obs_in_device_memory);
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
@@ -391,6 +401,24 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     return QS_OK;
 }
 
+static int launch_pregen(QsHandle* h, cudaStream_t s) {
+    StepParams p;
+    fill_params(h, p);
+    const int kBlock = 128;
+    const int envs_per_block = kBlock / h->NP;
+    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    int rc = dispatch_np(h->NP, [&](auto np) {
+        qs_pregen_kernel<decltype(np)::value><<<grid, kBlock, 0, s>>>(p);
+        return QS_OK;
+    });
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    h->since_pregen = 0;
+    note_async(h, s, false);
+    return QS_OK;
+}
+
 static int launch_reset(QsHandle* h, const StepParams& p, cudaStream_t s) {
     const int kBlock = block_size();
     const int envs_per_block = kBlock / h->NP;
@@ -452,6 +480,12 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
         h->split_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
         h->handover = -1;
         h->pdl_env = -2;
+        // next-episode generator cadence: an env consumes its record once per episode, so a quarter of an episode is ample
+        const char* pg = getenv("QS_PREGEN");
+        const bool dev_gen = cfg->scenario != QS_SCENARIO_HOST_TABLES;
+        h->pregen_every = pg ? atoi(pg) : (dev_gen ? (h->ep_len / 4 < 16 ? 16 : (h->ep_len / 4 > 256 ? 256 : h->ep_len / 4)) : 0);
+        if (!dev_gen) h->pregen_every = 0;
+        h->since_pregen = 0;
         const char* c = getenv("QS_CHAINED");
         h->chained = c ? (atoi(c) != 0) : 0;
         const char* b = getenv("QS_OBS_BULK");
@@ -480,6 +514,9 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.stats_agent, sizeof(float4) * A);
     QS_ALLOC0(st.scn_i, sizeof(int4) * E);
     QS_ALLOC0(st.scn_f, sizeof(float4) * 3 * E);
+    QS_ALLOC0(st.next_scn_i, sizeof(int4) * E);
+    QS_ALLOC0(st.next_scn_f, sizeof(float4) * 3 * E);
+    QS_ALLOC0(st.epi, sizeof(int2) * E);
     {   // per-block hand-over words (at most one block per env), all "ready"
         QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * (E + 1)));
         std::vector<int> ones((size_t)E + 1, 1);
@@ -534,7 +571,7 @@ extern "C" int qs_destroy(QsHandle* h) {
     DevState& st = h->st;
     cudaFree(st.slots); cudaFree(st.env_ctr); cudaFree(st.env_cnt); cudaFree(st.obst); cudaFree(st.next_goal);
     cudaFree(st.next_spawn); cudaFree(st.next_obst); cudaFree(st.stats_env); cudaFree(st.stats_agent);
-    cudaFree(st.scn_i); cudaFree(st.scn_f); cudaFree(st.ready);
+    cudaFree(st.scn_i); cudaFree(st.scn_f); cudaFree(st.ready); cudaFree(st.next_scn_i); cudaFree(st.next_scn_f); cudaFree(st.epi);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_rewards); cudaFree(h->d_terms); cudaFree(h->d_dones);
     cudaFree(h->d_mask);
     cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);
@@ -611,7 +648,9 @@ extern "C" int qs_reset(QsHandle* h, const uint8_t* env_mask_dev, float* obs_dev
     fill_params(h, p);
     p.obs = obs_dev;
     p.env_mask = env_mask_dev;
-    return launch_reset(h, p, (cudaStream_t)stream);
+    int rc = launch_reset(h, p, (cudaStream_t)stream);
+    if (rc == QS_OK && h->pregen_every > 0) rc = launch_pregen(h, (cudaStream_t)stream);
+    return rc;
 }
 
 extern "C" int qs_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev,

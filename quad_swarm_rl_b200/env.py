@@ -398,6 +398,11 @@ class QuadrotorEnvMulti(_EnvBase):
         if zero_collision_counters:          # quad_experience_replay.py:188-190: accurate per-replay statistics
             for k in (0, 1, 7, 8):           # QS_STAT_NUM_COLLISIONS, _AFTER_SETTLE, _OBST, _OBST_AFTER_SETTLE
                 dev['env_i32'][:, 4 + k] = 0
+        # counters a replayed snapshot must not rewind: the RNG step counter (a replay would re-draw the noise it drew the
+        # first time), the episode index and the episode number that keys the episode-generation draws
+        live = self.engine.get_state()['env_i32']
+        for col in (1, 3, 4 + L.QS_NUM_ENV_STATS + 16):
+            dev['env_i32'][:, col] = live[:, col]
         self.engine.set_state(dev)
         self._scenarios, self._next_scenarios = copy.deepcopy(snap['scenarios'])
         for sc in self._scenarios + self._next_scenarios:

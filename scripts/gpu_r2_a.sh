@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, run A: GPU tests, the driver's bench invocation, A/B of the new launch / write-out paths
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2a_pytest.txt
+python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r2a_pytest.txt
 cat gpurun_out/r2a_pytest.txt
 B="--no-extras --no-cpu-baseline --e2e-steps 10"
 run() { name=$1; shift; echo "== $name: $*" | tee -a gpurun_out/r2a_ab.txt; timeout 300 env "$@" 2>&1 | tail -1 | python -c "

@@ -148,6 +148,7 @@ class Pair:
                 au[e, i, 1] = prev
             svd = int(round(o.drones[0].since_last_svd / o.P.dt))
             ei[e, :4] = [o.tick, o.step_count, svd, 0]
+            ei[e, 4 + L.QS_NUM_ENV_STATS + 16] = o.epi              # episode number (keys the episode-generation draws)
             ei[e, 4:4 + 11] = [o.collisions_per_episode, o.collisions_after_settle, o.collisions_final_5s,
                                o.collisions_room_per_episode, o.collisions_floor_per_episode,
                                o.collisions_wall_per_episode, o.collisions_ceiling_per_episode,

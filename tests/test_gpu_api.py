@@ -297,6 +297,8 @@ def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, ch
     mk = lambda: (QuadSwarmEngine(num_envs=E, seed=9, ep_time=1.0, device_scenario=dev_scn, **kw) if dev_scn else _engine(E, kw, ep_time=1.0)[0])
     e1, e2 = mk(), mk()
     e1.set_chained(chained)                         # step grids follow each other directly (qs_set_chained)
+    e2.set_chained(chained)                         # same kernel instantiation on both sides (hand-over / wait variants are
+                                                    # separate template instances: identical source, but only equal builds are bit-equal)
     a = _actions(T, E, N)
     st = torch.cuda.Stream()
     obs = torch.empty((T, E, N, e1.D), device='cuda'); rew = torch.empty((T, E, N), device='cuda')
