@@ -128,6 +128,9 @@ typedef struct QsConfig {
     int32_t scenario;                /* QS_SCENARIO_*: who generates the episodes consumed by (auto-)resets */
     int32_t obst_grid[2];            /* pillar grid cells along x / y = int(obst_spawn_area) (quadrotor_multi.py:305) */
     uint64_t seed;
+    float quad_arm;                  /* QuadrotorEnvMulti.quad_arm = envs[0].dynamics.arm at construction (quadrotor_multi.py:81);
+                                        0 = Crazyflie (0.04596194 m).  Scales the collision / proximity / pillar radii. */
+    int32_t reserved_[3];
 } QsConfig;
 
 typedef struct QsHandle QsHandle;
@@ -196,6 +199,23 @@ int qs_get_state(QsHandle* h, float* agent_f32_dev, uint32_t* agent_u32_dev, int
                  float* obst_xy_dev, void* stream);
 int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f32_dev, const uint32_t* agent_u32_dev,
                  const int32_t* env_i32_dev, const float* obst_xy_dev, void* stream);
+
+/* Per-drone physical constants — replaces QuadrotorSingle.update_dynamics / resample_dynamics (quadrotor_single.py:249-258,
+ * 359-385) and QuadrotorDynamics.update_model (quadrotor_dynamics.py:104-166).  rows_dev [E,N,QS_DYN_ROW] floats, one row per
+ * drone with the constants the integrator reads (host side: quad_swarm_rl_b200/quad_models.py derives them from a parameter
+ * set / the dynamics-randomisation samplers):
+ *   0 mass, 1 1/mass, 2-4 inertia diagonal, 5-7 its inverse, 8-11 thrust_max per motor, 12-15 torque_max per motor,
+ *   16-23 propeller (x, y) per motor, 24-27 propeller z per motor (relative to the centre of mass), 28 motor_tau_up,
+ *   29 motor_tau_down, 30 motor linearity, 31 OU sigma (0.2 * thrust_noise_ratio), 32 C_drag, 33 C_roll (rotor drag /
+ *   rolling moment: numpy path of the reference only, quadrotor_dynamics.py:256-289), 34 vel_damp, 35 omega_quadratic,
+ *   36 arm (= floor threshold, :378), 37-39 reserved.
+ * at_next_reset = 0: the rows take effect now (construction); != 0: every masked env latches them at its next (auto-)reset,
+ * where its OU state and SVD counter restart like those of the reference's fresh QuadrotorDynamics object.
+ * Until the first call every drone uses the Crazyflie constants compiled into the kernels.  The env-level collision radii
+ * (collision_hitbox_radius * arm etc.) stay those of QsConfig.quad_arm, as the reference fixes them at construction
+ * (quadrotor_multi.py:81,154-155). */
+#define QS_DYN_ROW 40
+int qs_set_dynamics(QsHandle* h, const uint8_t* env_mask_dev, const float* rows_dev, int at_next_reset, void* stream);
 
 /* flag bits in agent_u32[.,0] */
 #define QS_FLAG_ON_FLOOR (1u << 0)

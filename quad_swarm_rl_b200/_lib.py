@@ -18,6 +18,7 @@ QS_STATE_F32 = 43
 QS_STATE_U32 = 4
 QS_STATE_ENV_I32 = 36
 QS_MAX_AGENTS = 32
+QS_DYN_ROW = 40
 SCENARIO_HOST_TABLES, SCENARIO_O_RANDOM = 0, 1
 # scenarios with a device-side generator (QS_SCENARIO_* of include/quadswarm.h), by their reference names
 DEVICE_SCENARIOS = {'o_random': 1, 'static_same_goal': 2, 'static_diff_goal': 3, 'dynamic_same_goal': 4,
@@ -49,6 +50,7 @@ class QsConfig(C.Structure):
         ('room_dims', C.c_float * 3), ('ep_time', C.c_float), ('collision_hitbox_radius', C.c_float),
         ('collision_falloff_radius', C.c_float), ('approch_goal_metric', C.c_float),
         ('env_id_offset', C.c_int32), ('scenario', C.c_int32), ('obst_grid', C.c_int32 * 2), ('seed', C.c_uint64),
+        ('quad_arm', C.c_float), ('reserved_', C.c_int32 * 3),
     ]
 
 
@@ -74,6 +76,7 @@ EXPORTS = {
     'qs_set_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_read_episode_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_set_chained': (C.c_int, [C.c_void_p, C.c_int]),
+    'qs_set_dynamics': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'qs_launch_count': (C.c_int64, [C.c_void_p]),
     'qs_handover_timeouts': (C.c_int64, [C.c_void_p]),
 }

@@ -477,7 +477,9 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 // not carry that code (instruction-cache footprint of the hot loop: +1.3 % step time on c3 when it was compiled in).
 // HO = true: per-block hand-over between consecutive step grids instead of the grid-wide wait (handover_acquire above);
 // chosen by the launcher when a step grid does not fit the GPU in one wave or the split shape is used.
-template <int NP, bool SPLIT, bool SCN, bool HO>
+// DYN = true: per-drone physical constants (qs_set_dynamics) instead of the compile-time Crazyflie set — only
+// instantiated for the single-warp shape with the grid-wide wait.
+template <int NP, bool SPLIT, bool SCN, bool HO, bool DYN = false>
 __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) float2 s_obst[];
     const DevState& st = p.st;
@@ -530,6 +532,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
     if (valid && role == 0) load_agent<HO>(st, a, s);      // state loads are issued before the pillar staging barrier
+    Phys ph;
+    if (DYN) load_phys(st.dyn, valid ? a : 0, ph);
     // stage the pillar tables in shared memory.  Single-warp shape: every warp stages the tables of ITS envs (a contiguous
     // [32 / NP][M] float2 span) and only a warp-level barrier follows; split shape: the block's two warps share them.
     if (p.use_obst) {
@@ -669,10 +673,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
 #pragma unroll
         for (int m = 0; m < 4; ++m) cmd[m] = 0.5f * (clampf(act[m], -1.f, 1.f) + 1.f);    // RawControl.step, quadrotor_control.py:53-57
         // OU thrust noise, once per control step (numba_utils.py:101-105, quadrotor_dynamics.py:209)
-        s.ou[0] += OU_THETA * (0.f - s.ou[0]) + OU_SIGMA * ou_z.x;
-        s.ou[1] += OU_THETA * (0.f - s.ou[1]) + OU_SIGMA * ou_z.y;
-        s.ou[2] += OU_THETA * (0.f - s.ou[2]) + OU_SIGMA * ou_z.z;
-        s.ou[3] += OU_THETA * (0.f - s.ou[3]) + OU_SIGMA * ou_z.w;
+        const float ou_sigma = DYN ? ph.ou_sigma : OU_SIGMA;
+        s.ou[0] += OU_THETA * (0.f - s.ou[0]) + ou_sigma * ou_z.x;
+        s.ou[1] += OU_THETA * (0.f - s.ou[1]) + ou_sigma * ou_z.y;
+        s.ou[2] += OU_THETA * (0.f - s.ou[2]) + ou_sigma * ou_z.z;
+        s.ou[3] += OU_THETA * (0.f - s.ou[3]) + ou_sigma * ou_z.w;
 #ifdef QS_UNROLL_SUB
 #pragma unroll
 #else
@@ -682,7 +687,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             ctr.svd_count += 1;
             const bool do_svd = ctr.svd_count >= SVD_PERIOD;
             if (do_svd) ctr.svd_count = 0;
-            dynamics_substep(s, cmd, do_svd, p, key, i, sub);
+            if (DYN) dynamics_substep_dyn(s, cmd, do_svd, p, key, i, sub, ph);
+            else dynamics_substep(s, cmd, do_svd, p, key, i, sub);
         }
         if (SPLIT) {                                                   // positions are final from here on
             hand_store(s_hand, lane, s, s.vel);
@@ -980,6 +986,23 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 o[QS_STAT_SCENARIO] = (dev_scn || env_metric) ? QS_LD(st.scn_i + env).x : p.scenario;
             }
             reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next, approach);
+            if (DYN) {
+                // resample_dynamics inside _reset (quadrotor_single.py:387-390): constants uploaded with at_next_reset are
+                // latched now; update_dynamics builds a fresh QuadrotorDynamics, so OU state and SVD counter restart
+                const int pend = do_reset ? QS_LD(st.dyn_pending + env) : 0;
+                if (pend != 0) {
+                    if (valid) {
+                        for (int q = 0; q < QS_DYN_ROW / 4; ++q)
+                            st.dyn[a * (QS_DYN_ROW / 4) + q] = QS_LD(st.next_dyn + a * (QS_DYN_ROW / 4) + q);
+                        load_phys(st.next_dyn, a, ph);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) s.ou[k] = 0.f;
+                    }
+                    ctr.svd_count = 0;
+                }
+                __syncwarp();
+                if (pend != 0 && i == 0) st.dyn_pending[env] = 0;
+            }
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -1081,6 +1104,20 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     int scn_next = SCN_NEVER;
     float approach = p.approach_metric;
     reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next, approach);
+    if (st.dyn != nullptr) {          // pending physical constants are latched by explicit resets too
+        const int pend = env_ok ? QS_LD(st.dyn_pending + env) : 0;
+        if (pend != 0) {
+            if (valid) {
+                for (int q = 0; q < QS_DYN_ROW / 4; ++q)
+                    st.dyn[a * (QS_DYN_ROW / 4) + q] = QS_LD(st.next_dyn + a * (QS_DYN_ROW / 4) + q);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s.ou[k] = 0.f;
+            }
+            ctr.svd_count = 0;
+        }
+        __syncwarp();
+        if (pend != 0 && i == 0) st.dyn_pending[env] = 0;
+    }
     if (env_ok && i == 0) {
         int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
         for (int k = 0; k < QS_NUM_ENV_STATS; ++k) c[k] = 0;

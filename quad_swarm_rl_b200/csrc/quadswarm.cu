@@ -61,6 +61,8 @@ static int fail(int code, const std::string& msg) {
 
 extern "C" const char* qs_last_error(void) { return g_err.c_str(); }
 
+static inline int blocks_for(long long n) { return (int)((n + 255) / 256); }
+
 static int next_pow2(int n) {
     int p = 1;
     while (p < n) p <<= 1;
@@ -78,7 +80,7 @@ static void fill_params(const QsHandle* h, StepParams& p) {
     // room_box, quadrotor_single.py:146-147
     p.room_lo[0] = -c.room_dims[0] / 2.f; p.room_lo[1] = -c.room_dims[1] / 2.f; p.room_lo[2] = 0.f;
     p.room_hi[0] = c.room_dims[0] / 2.f; p.room_hi[1] = c.room_dims[1] / 2.f; p.room_hi[2] = c.room_dims[2];
-    const double arm = 0.04596194077712559;
+    const double arm = c.quad_arm > 0.f ? (double)c.quad_arm : 0.04596194077712559;      // quadrotor_multi.py:81
     p.col_thr = (float)(c.collision_hitbox_radius * arm);        // quadrotor_multi.py:154
     p.falloff_thr = (float)(c.collision_falloff_radius * arm);   // quadrotor_multi.py:155
     p.obst_radius = (float)(c.obst_size / 2.0);
@@ -280,6 +282,17 @@ __global__ void k_set_state(DevState st, int E, int N, int M, const uint8_t* mas
         st.obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
 }
 
+// qs_set_dynamics: rows [A][QS_DYN_ROW] -> the live table (now) or the table latched at the env's next reset
+__global__ void k_set_dynamics(DevState st, int E, int N, const uint8_t* mask, const float4* rows, int at_next_reset) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)E * N * (QS_DYN_ROW / 4);
+    if (t < total) {
+        const int env = (int)(t / ((long long)N * (QS_DYN_ROW / 4)));
+        if (mask == nullptr || mask[env]) (at_next_reset ? st.next_dyn : st.dyn)[t] = rows[t];
+    }
+    if (at_next_reset && t < E && (mask == nullptr || mask[t])) st.dyn_pending[t] = 1;
+}
+
 __global__ void k_read_stats(DevState st, int E, int N, int32_t* env_stats, float* agent_stats) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < (long long)E * N && agent_stats) {
@@ -335,7 +348,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     choose_obs_writeout(h, p, obs_in_device_memory);
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
     const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
-    const bool split = want_split && p.obs_stage && h->NP > 1;
+    const bool split = want_split && p.obs_stage && h->NP > 1 && h->st.dyn == nullptr;
     const int kBlock = split ? 64 : block_size();
     const int envs_per_block = (split ? 32 : kBlock) / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
@@ -371,6 +384,14 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
         return QS_OK;
     });
     if (rc != QS_OK) return rc;
+    KernelFn fn_dyn = nullptr;
+    if (h->st.dyn != nullptr) {           // per-drone physical constants: single-warp shape, grid-wide wait
+        dispatch_np(h->NP, [&](auto np) {
+            constexpr int NPv = decltype(np)::value;
+            fn_dyn = scn ? (KernelFn)qs_step_kernel<NPv, false, true, false, true> : (KernelFn)qs_step_kernel<NPv, false, false, false, true>;
+            return QS_OK;
+        });
+    }
     if (h->handover < 0) {
         if (pdl_env >= 0) h->handover = pdl_env == 3;
         else {
@@ -383,7 +404,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // The hand-over kernels pay off only between step grids that follow each other directly; an unchained handle uses
     // the grid-wide wait (formally safe after any predecessor) and never pre-fetches across the dependency wait.
     p.chained = (h->chained && h->last_was_step) ? 1 : 0;
-    const bool use_ho = h->handover && h->chained;
+    const bool use_ho = h->handover && h->chained && fn_dyn == nullptr;
     const int pdl_mode = use_ho ? 3 : ((pdl_env >= 0 && pdl_env != 3) ? pdl_env : 2);
     const bool use_pdl = pdl_mode != 0;
     p.pdl_mode = pdl_mode;
@@ -393,7 +414,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
-    const cudaError_t lerr = cudaLaunchKernelEx(&lc, use_ho ? fn_ho : fn_wait, p);
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn_dyn ? fn_dyn : (use_ho ? fn_ho : fn_wait), p);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -571,6 +592,7 @@ extern "C" int qs_destroy(QsHandle* h) {
     DevState& st = h->st;
     cudaFree(st.slots); cudaFree(st.env_ctr); cudaFree(st.env_cnt); cudaFree(st.obst); cudaFree(st.next_goal);
     cudaFree(st.next_spawn); cudaFree(st.next_obst); cudaFree(st.stats_env); cudaFree(st.stats_agent);
+    cudaFree(st.dyn); cudaFree(st.next_dyn); cudaFree(st.dyn_pending);
     cudaFree(st.scn_i); cudaFree(st.scn_f); cudaFree(st.ready); cudaFree(st.next_scn_i); cudaFree(st.next_scn_f); cudaFree(st.epi);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_rewards); cudaFree(h->d_terms); cudaFree(h->d_dones);
     cudaFree(h->d_mask);
@@ -605,6 +627,41 @@ extern "C" int qs_set_chained(QsHandle* h, int on) {
     return QS_OK;
 }
 
+extern "C" int qs_set_dynamics(QsHandle* h, const uint8_t* env_mask_dev, const float* rows_dev, int at_next_reset, void* stream) {
+    if (!h || !rows_dev) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (((uintptr_t)rows_dev & 15u) != 0) return fail(QS_ERR_INVALID_ARG, "rows must be 16-byte aligned");
+    QS_CUDA(cudaSetDevice(h->device));
+    DevState& st = h->st;
+    const long long A = h->A, E = h->cfg.num_envs;
+    if (st.dyn == nullptr) {
+        // first use: both tables start as Crazyflie rows (the constants compiled into the other kernels), so that envs
+        // outside a mask keep flying the default model
+        std::vector<float> row(QS_DYN_ROW, 0.f);
+        const float cf[QS_DYN_ROW] = {MASS, INV_MASS, IXX, IYY, IZZ, INV_IXX, INV_IYY, INV_IZZ, THRUST_MAX, THRUST_MAX, THRUST_MAX, THRUST_MAX,
+                                      TORQUE_MAX, TORQUE_MAX, TORQUE_MAX, TORQUE_MAX, PROP_ARM_XY, -PROP_ARM_XY, -PROP_ARM_XY, -PROP_ARM_XY,
+                                      -PROP_ARM_XY, PROP_ARM_XY, PROP_ARM_XY, PROP_ARM_XY, 0.f, 0.f, 0.f, 0.f, MOTOR_TAU_UP, MOTOR_TAU_DOWN,
+                                      1.0f, OU_SIGMA, 0.f, 0.f, 0.f, 0.f, ARM, 0.f, 0.f, 0.f};
+        std::vector<float> all((size_t)A * QS_DYN_ROW);
+        for (long long a = 0; a < A; ++a) memcpy(&all[(size_t)a * QS_DYN_ROW], cf, sizeof(cf));
+        float4 *d0 = nullptr, *d1 = nullptr;
+        int* pend = nullptr;
+        QS_CUDA(cudaMalloc((void**)&d0, sizeof(float) * QS_DYN_ROW * A));
+        QS_CUDA(cudaMalloc((void**)&d1, sizeof(float) * QS_DYN_ROW * A));
+        QS_CUDA(cudaMalloc((void**)&pend, sizeof(int) * E));
+        QS_CUDA(cudaMemcpy(d0, all.data(), sizeof(float) * QS_DYN_ROW * A, cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMemcpy(d1, all.data(), sizeof(float) * QS_DYN_ROW * A, cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMemset(pend, 0, sizeof(int) * E));
+        st.dyn = d0; st.next_dyn = d1; st.dyn_pending = pend;
+    }
+    const long long n = A * (QS_DYN_ROW / 4);
+    k_set_dynamics<<<blocks_for(n > E ? n : E), 256, 0, (cudaStream_t)stream>>>(st, h->cfg.num_envs, h->cfg.num_agents, env_mask_dev,
+                                                                               (const float4*)rows_dev, at_next_reset ? 1 : 0);
+    QS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
+    return QS_OK;
+}
+
 extern "C" int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host) {
     if (!h || !coeffs_host) return fail(QS_ERR_INVALID_ARG, "null argument");
     for (int k = 0; k < QS_NUM_REW_COEFF; ++k) {
@@ -614,7 +671,6 @@ extern "C" int qs_set_reward_coeffs(QsHandle* h, const float* coeffs_host) {
     return QS_OK;
 }
 
-static inline int blocks_for(long long n) { return (int)((n + 255) / 256); }
 
 extern "C" int qs_set_next_episode(QsHandle* h, const uint8_t* env_mask_dev, const float* goals_dev, const float* spawn_dev,
                                    const float* obst_xy_dev, void* stream) {

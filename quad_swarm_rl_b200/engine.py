@@ -25,7 +25,7 @@ class QuadSwarmEngine:
                  obst_spawn_area=(8.0, 8.0), use_downwash=False, room_dims=(10., 10., 10.), ep_time=15.0,
                  collision_hitbox_radius=2.0, collision_falloff_radius=4.0, sense_noise='default',
                  approch_goal_metric=0.5, rew_coeff=None, seed=0, device=0, env_id_offset=0,
-                 device_scenario=None):
+                 device_scenario=None, quad_arm=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("QuadSwarmEngine needs a CUDA device (the env step has no CPU path)")
         self.lib = L.load()
@@ -56,6 +56,7 @@ class QuadSwarmEngine:
         cfg.scenario = L.DEVICE_SCENARIOS[device_scenario] if device_scenario is not None else L.SCENARIO_HOST_TABLES
         cfg.obst_grid = (C.c_int32 * 2)(int(obst_spawn_area[0]), int(obst_spawn_area[1]))
         cfg.seed = int(seed)
+        cfg.quad_arm = float(quad_arm)          # 0 = Crazyflie; envs[0].dynamics.arm of the model in use otherwise (quadrotor_multi.py:81)
         self.device_scenario = device_scenario
         self.cfg = cfg
         h = C.c_void_p()
@@ -202,6 +203,14 @@ class QuadSwarmEngine:
         ags = torch.empty((self.E, self.N, L.QS_NUM_AGENT_STATS), dtype=torch.float32, device=dev)
         L.check(self.lib.qs_read_episode_stats(self.h, _ptr(es), _ptr(ags), self._stream()))
         return es, ags
+
+    def set_dynamics(self, rows, env_mask=None, at_next_reset=False):
+        """Per-drone physical constants (include/quadswarm.h, qs_set_dynamics): rows [E,N,QS_DYN_ROW] float32, the layout
+        of quad_models.DYN_FIELDS.  at_next_reset: latched by each masked env's next (auto-)reset, like the reference's
+        resample_dynamics inside _reset."""
+        r = self._dev_f32(rows, (self.E, self.N, L.QS_DYN_ROW))
+        m = self._dev_mask(env_mask)
+        L.check(self.lib.qs_set_dynamics(self.h, _ptr(m), _ptr(r), int(bool(at_next_reset)), self._stream()))
 
     def set_chained(self, on=True):
         """Promise (or retract) that consecutive step() / rollout() calls follow each other directly on the stream

@@ -393,16 +393,21 @@ class QuadrotorEnvMulti(_EnvBase):
                     obst_density=self.obst_density, saved_in_replay_buffer=True,
                     activate_replay_buffer=self.activate_replay_buffer)
 
-    def restore(self, snap, zero_collision_counters=False):
+    def restore(self, snap, zero_collision_counters=False, keep_rng_counters=True):
+        """keep_rng_counters (default, what the replay wrapper needs): the RNG step counter, the episode index and the
+        episode number stay those of the LIVE env — the reference's deepcopy does not rewind numpy's global generators
+        either, so a replayed event sees fresh noise.  False restores them too: the continuation is then bit-identical to
+        what followed the snapshot."""
         dev = {k: (v.clone() if v is not None else None) for k, v in snap['device'].items()}
         if zero_collision_counters:          # quad_experience_replay.py:188-190: accurate per-replay statistics
             for k in (0, 1, 7, 8):           # QS_STAT_NUM_COLLISIONS, _AFTER_SETTLE, _OBST, _OBST_AFTER_SETTLE
                 dev['env_i32'][:, 4 + k] = 0
         # counters a replayed snapshot must not rewind: the RNG step counter (a replay would re-draw the noise it drew the
         # first time), the episode index and the episode number that keys the episode-generation draws
-        live = self.engine.get_state()['env_i32']
-        for col in (1, 3, 4 + L.QS_NUM_ENV_STATS + 16):
-            dev['env_i32'][:, col] = live[:, col]
+        if keep_rng_counters:
+            live = self.engine.get_state()['env_i32']
+            for col in (1, 3, 4 + L.QS_NUM_ENV_STATS + 16):
+                dev['env_i32'][:, col] = live[:, col]
         self.engine.set_state(dev)
         self._scenarios, self._next_scenarios = copy.deepcopy(snap['scenarios'])
         for sc in self._scenarios + self._next_scenarios:

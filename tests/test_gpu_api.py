@@ -354,10 +354,15 @@ def test_env_snapshot_restore_and_replay_wrapper():
         env.step(acts[t])
     snap = env.snapshot()
     first = [env.step(acts[t])[0].copy() for t in range(10, 40)]
-    env.restore(snap)
+    env.restore(snap, keep_rng_counters=False)         # everything rewound, the keyed RNG counters included
     assert env.envs[0].tick == 10
     for t, ref in zip(range(10, 40), first):
         assert np.array_equal(env.step(acts[t])[0], ref)
+    # default (what the replay wrapper uses): state rewound, RNG counters live -> same physics, fresh noise
+    env.restore(snap)
+    assert env.envs[0].tick == 10
+    o = env.step(acts[10])[0]
+    assert not np.array_equal(o, first[0]) and np.abs(o - first[0]).max() < 0.1
     env.close()
 
     env = _ref_style_env(ep_time=4.0)
