@@ -120,6 +120,10 @@ class KeyedDraws:
         return u01(self._block(site, i, j, v // 4)[v % 4])
 
     def normal(self, site, i, j, v):
+        if site in (SITE_SENSOR1, SITE_SENSOR_RESET) and 0 <= v < 9:
+            # re-drawn sensor noise: the same compact layout inside the site's own blocks 0 / 1 (qs_device.cuh, sensor_noise)
+            word = v // 2
+            return normal_pair16(self._block(site, i, 0, word // 4)[word % 4])[v % 2]
         n = hot_index(site, v)
         if n is not None:
             word = n // 2

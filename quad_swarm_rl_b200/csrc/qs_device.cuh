@@ -116,6 +116,10 @@ struct StepParams {
     int obs_stage, obs_v, obs_q, obs_dp, obs_magic, smem_tile_off;
     int obs_bulk;                       // write-out of the staged tile: 0 vector stores, 1 one TMA tensor store per warp tile
                                         // (obs_map, D % 4 == 0), 2 one linear cp.async.bulk per warp tile (unpadded rows)
+#ifdef QS_TIMELINE
+    unsigned long long* tl;             // debug build only: [64 slots][4096 blocks][8] %globaltimer stamps of warp 0 of every block
+    int tl_slot;
+#endif
     int chained;                        // 1: the stream predecessor of this launch is a step grid of the same handle (qs_set_chained):
                                         //    actions are prefetched before the dependency wait; hand-over kernels skip the grid-wide wait
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
@@ -565,14 +569,22 @@ __device__ __forceinline__ void observed_rotation(const float R[9], float out[9]
     out[6] = xz - wy; out[7] = yz + wx; out[8] = 1.0f - xx - yy;
 }
 
-// fresh sensor-noise draw for a non-default site (after a contact response / a reset)
+// fresh sensor-noise draw for a non-default site (after a contact response / a reset): the compact layout of the hot
+// draws (qs_rng.cuh, normal_pair16) — normal n of the site lives in half n % 2 of word n / 2 of its blocks 0 and 1
 __device__ __noinline__ Noise9 sensor_noise(RngKey key, uint32_t site, int i) {
-    const float4 a = rng_normal4(key, site, i, 0, 0), b = rng_normal4(key, site, i, 0, 1), c = rng_normal4(key, site, i, 0, 2);
-    Noise9 n;
-    n.p[0] = POS_NOISE_STD * a.x; n.p[1] = POS_NOISE_STD * a.y; n.p[2] = POS_NOISE_STD * a.z;
-    n.v[0] = VEL_NOISE_STD * a.w; n.v[1] = VEL_NOISE_STD * b.x; n.v[2] = VEL_NOISE_STD * b.y;
-    n.w[0] = GYRO_NOISE_STD * b.z; n.w[1] = GYRO_NOISE_STD * b.w; n.w[2] = GYRO_NOISE_STD * c.x;
-    return n;
+    uint4 blk[2];
+    philox4x32_10_x2(key.env, key.step, rng_c2(site, i, 0), key.k0, key.k1, blk);
+    float n[10];
+    normal_pair16(blk[0].x, n[0], n[1]);
+    normal_pair16(blk[0].y, n[2], n[3]);
+    normal_pair16(blk[0].z, n[4], n[5]);
+    normal_pair16(blk[0].w, n[6], n[7]);
+    normal_pair16(blk[1].x, n[8], n[9]);
+    Noise9 o;
+    o.p[0] = POS_NOISE_STD * n[0]; o.p[1] = POS_NOISE_STD * n[1]; o.p[2] = POS_NOISE_STD * n[2];
+    o.v[0] = VEL_NOISE_STD * n[3]; o.v[1] = VEL_NOISE_STD * n[4]; o.v[2] = VEL_NOISE_STD * n[5];
+    o.w[0] = GYRO_NOISE_STD * n[6]; o.w[1] = GYRO_NOISE_STD * n[7]; o.w[2] = GYRO_NOISE_STD * n[8];
+    return o;
 }
 
 // compute_new_vel, collisions/utils.py:8-18

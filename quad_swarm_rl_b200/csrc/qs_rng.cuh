@@ -101,6 +101,7 @@ __device__ __forceinline__ void philox4x32_10_x4(uint32_t c0, uint32_t c1, const
 
 // Two independent blocks in one rolled loop: the hot per-step draws (SITE_HOT, see hot_normals below).
 __device__ __forceinline__ void philox4x32_10_x2(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1, uint4 out[2]) {
+    // blocks 0 and 1 of counter word 3
     uint32_t a[2] = {c0, c0}, b[2] = {c1, c1}, c[2] = {c2, c2}, d[2] = {0u, 1u};
 #pragma unroll 1
     for (int r = 0; r < 10; ++r) {

@@ -17,6 +17,14 @@
 
 namespace qs {
 
+#ifdef QS_TIMELINE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define QS_TL(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) { p.tl[((long long)p.tl_slot * 4096 + blockIdx.x) * 16 + (k)] = gtime(); \
+    if ((k) == 0) { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); p.tl[((long long)p.tl_slot * 4096 + blockIdx.x) * 16 + 8] = sm; } } } while (0)
+#else
+#define QS_TL(k) do { } while (0)
+#endif
+
 struct EnvCtr {
     int tick, step_count, svd_count, episode_idx;
 };
@@ -200,21 +208,21 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
         for (int c = lane; c < total; c += 32) {
             const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
             const int q = c - r * Q;
-            *reinterpret_cast<float4*>(gdst + 4 * c) = *reinterpret_cast<const float4*>(tile + r * Dp + 4 * q);
+            __stcs(reinterpret_cast<float4*>(gdst + 4 * c), *reinterpret_cast<const float4*>(tile + r * Dp + 4 * q));
         }
     } else if (V == 2) {
 #pragma unroll 2
         for (int c = lane; c < total; c += 32) {
             const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
             const int q = c - r * Q;
-            *reinterpret_cast<float2*>(gdst + 2 * c) = *reinterpret_cast<const float2*>(tile + r * Dp + 2 * q);
+            __stcs(reinterpret_cast<float2*>(gdst + 2 * c), *reinterpret_cast<const float2*>(tile + r * Dp + 2 * q));
         }
     } else {
 #pragma unroll 2
         for (int c = lane; c < total; c += 32) {
             const int r = (int)(((unsigned)c * (unsigned)p.obs_magic) >> 20);
             const int q = c - r * Q;
-            gdst[c] = tile[r * Dp + q];
+            __stcs(gdst + c, tile[r * Dp + q]);
         }
     }
 }
@@ -231,13 +239,23 @@ __device__ __forceinline__ void flush_observation_tile(const StepParams& p, cons
 //               the rare remainder.
 // The generic-proxy writes of the lanes are ordered before the async proxy's reads by fence.proxy.async + __syncwarp; the
 // tile may be rewritten (or the CTA may exit) only after cp.async.bulk.wait_group.read 0 — bulk_drain() below.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the observation stream is written once and read by another kernel much later: L2 evict-first, so that it does not push
+// the env state (re-read every step) out of the cache
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes), "l"(l2_evict_first_policy())
+                 : "memory");
 }
 __device__ __forceinline__ void tensor_s2g_3d(const void* tmap, const void* ssrc, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
-                 "r"(c2), "r"(smem_u32(ssrc))
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(tmap),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(ssrc)), "l"(l2_evict_first_policy())
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -407,7 +425,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
 }
 
 #ifndef QS_LB
-#define QS_LB 128
+#define QS_LB 256
 #endif
 // named barriers of the split kernel (physics warp <-> observer warp, 64 threads).  Both warps use bar.sync: the
 // observer reaches barrier 1 first, the physics warp reaches barrier 2 first and has only its stores left to do.
@@ -418,8 +436,9 @@ __device__ __noinline__ void bar_sync(int id) {
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
-// running episode counter += v (L2 read: see load_agent)
-__device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { c[k] = QS_LD(c + k) + v; }
+// running episode counter += v.  A reduction (RED.ADD, no return value): a load + store pair per counter put one L2
+// round trip per counter on the critical path of every warp with a discrete event (the debug-build timeline showed +3 us).
+__device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { if (v != 0) atomicAdd(c + k, v); }
 
 // ---- per-block hand-over between consecutive step grids (pdl_mode 3) ----
 // Envs are independent, so block b of step t+1 only needs block b of step t.  Every step launch carries the programmatic
@@ -480,7 +499,7 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 // DYN = true: per-drone physical constants (qs_set_dynamics) instead of the compile-time Crazyflie set — only
 // instantiated for the single-warp shape with the grid-wide wait.
 template <int NP, bool SPLIT, bool SCN, bool HO, bool DYN = false>
-__global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) float2 s_obst[];
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
@@ -500,8 +519,9 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     // behind the predecessor's tail).
     // Only for CHAINED launches (qs_set_chained: the stream predecessor is a step grid of this handle); otherwise the
     // predecessor may be the kernel that produced the actions and the load follows the wait.
+    QS_TL(0);
     float4 av0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.chained && valid && role == 0) av0 = __ldg(p.actions + a);
+    if (p.chained && valid && role == 0) av0 = __ldcs(p.actions + a);          // streaming: read once
 
     // Programmatic dependent launch: wait here for the PREVIOUS step's grid to complete (and flush) before touching any
     // state; the trigger that lets the NEXT step's grid start launching is issued just before this grid's final stores
@@ -520,7 +540,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         if (p.pdl_mode == 4) asm volatile("griddepcontrol.launch_dependents;");      // trigger once the predecessor is done
     }
 
-    if (!p.chained && valid && role == 0) av0 = __ldg(p.actions + a);
+    QS_TL(1);
+    if (!p.chained && valid && role == 0) av0 = __ldcs(p.actions + a);
 
     // shared memory: [envs_per_block][M] pillar table, then one observation staging tile per warp
     float2* s_obst_env = s_obst + env_local * p.M;
@@ -534,6 +555,34 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     if (valid && role == 0) load_agent<HO>(st, a, s);      // state loads are issued before the pillar staging barrier
     Phys ph;
     if (DYN) load_phys(st.dyn, valid ? a : 0, ph);
+    // env-level words: issued together with the state loads, BEFORE the pillar staging below waits for its own loads (one
+    // L2 round trip for everything; the timeline of the debug build showed two serialized ones, 1.3 us of a 9.6 us step)
+    int4 ctr_raw = make_int4(0, 0, 0, 0);
+    if (env_ok) ctr_raw = ld_state<HO>(st.env_ctr + env);
+    // An env whose episode ends in this step (known from the tick just loaded) will need its next-episode record and its
+    // running statistics at the END of the step: their lines are pulled into L2 now (they were written long ago and have
+    // usually been evicted by the observation stream), behind the whole step's arithmetic.
+    if (env_ok && role == 0 && ctr_raw.x + p.T > p.ep_len && valid) {
+        prefetch_l2(st.epi + env);
+        prefetch_l2(st.next_goal + a);
+        prefetch_l2(st.next_spawn + a);
+        prefetch_l2(st.slots + SL_DIST_SUMS * st.a_pad + a);
+        prefetch_l2(st.slots + SL_STALE_VEL * st.a_pad + a);
+        if (i == 0) {
+            prefetch_l2(st.env_cnt + (long long)env * QS_NUM_ENV_STATS);
+            prefetch_l2(st.next_scn_i + env);
+            prefetch_l2(st.next_scn_f + 3 * (long long)env);
+            if (p.use_obst) prefetch_l2(st.next_obst + (long long)env * p.M);
+        }
+    }
+    // device-side scenarios: the tick of the env's next goal event (qs_scenario.cuh); never for the other scenarios
+    constexpr bool dev_scn = SCN;
+    int scn_next = SCN_NEVER;
+    if (dev_scn && env_ok && role == 0) scn_next = QS_LD(st.scn_i + env).z;
+    // approch_goal_metric is a property of the episode's scenario where the obstacle scenarios are drawn on the device
+    const bool env_metric = p.use_obst && p.scenario > QS_SCENARIO_O_RANDOM;
+    float approach = p.approach_metric;
+    if (env_metric && env_ok && role == 0) approach = QS_LD(st.scn_f + 3 * (long long)env + 1).w;
     // stage the pillar tables in shared memory.  Single-warp shape: every warp stages the tables of ITS envs (a contiguous
     // [32 / NP][M] float2 span) and only a warp-level barrier follows; split shape: the block's two warps share them.
     if (p.use_obst) {
@@ -562,18 +611,11 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         for (int k = 0; k < 4; ++k) { s.rd[k] = 0.f; s.cd[k] = 0.f; s.ou[k] = 0.f; s.ring[k] = 0.f; }
         s.flags = 0u; s.prev_col = 0u;
     }
-    if (env_ok) {
-        const int4 c = ld_state<HO>(st.env_ctr + env);
-        ctr.tick = c.x; ctr.step_count = c.y; ctr.svd_count = c.z; ctr.episode_idx = c.w;
-    }
-    // device-side scenarios: the tick of the env's next goal event (qs_scenario.cuh); never for the other scenarios
-    constexpr bool dev_scn = SCN;
-    int scn_next = SCN_NEVER;
-    if (dev_scn && env_ok && role == 0) scn_next = QS_LD(st.scn_i + env).z;
-    // approch_goal_metric is a property of the episode's scenario where the obstacle scenarios are drawn on the device
-    const bool env_metric = p.use_obst && p.scenario > QS_SCENARIO_O_RANDOM;
-    float approach = p.approach_metric;
-    if (env_metric && env_ok && role == 0) approach = QS_LD(st.scn_f + 3 * (long long)env + 1).w;
+    ctr.tick = ctr_raw.x; ctr.step_count = ctr_raw.y; ctr.svd_count = ctr_raw.z; ctr.episode_idx = ctr_raw.w;
+#ifdef QS_TIMELINE
+    if (ctr.tick + __float_as_int(s.pos[0]) == 0x7fffffff) QS_TL(7);      // depends on the loaded state: stamp 2 follows the loads
+    QS_TL(2);
+#endif
     if (SPLIT && role == 1) {
         // ============================ observer warp ============================
         const int gbase = lane & ~(NP - 1);
@@ -666,7 +708,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         // ================= per-drone part: QuadrotorSingle._step, quadrotor_single.py:341-357 =================
         float act[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid) {
-            const float4 av = (t == 0) ? av0 : __ldg(p.actions + ((long long)t * A + a));
+            const float4 av = (t == 0) ? av0 : __ldcs(p.actions + ((long long)t * A + a));
             act[0] = av.x; act[1] = av.y; act[2] = av.z; act[3] = av.w;
         }
         float cmd[4];
@@ -694,6 +736,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             hand_store(s_hand, lane, s, s.vel);
             bar_sync(1);
         }
+#ifdef QS_TIMELINE
+        if (__float_as_int(s.pos[0]) == 0x7fffffff) QS_TL(7);
+        QS_TL(3);
+#endif
         // compute_reward_weighted, quadrotor_single.py:34-92 (dt = SIM dt, raw unclipped action)
         const bool on_floor = (s.flags & QS_FLAG_ON_FLOOR) != 0u;
         const float dist = norm3(s.goal[0] - s.pos[0], s.goal[1] - s.pos[1], s.goal[2] - s.pos[2]);
@@ -847,6 +893,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             }
         }
 
+#ifdef QS_TIMELINE
+        if (__float_as_int(prox) == 0x7fffffff) QS_TL(7);
+        QS_TL(4);
+#endif
         // rewards, quadrotor_multi.py:499-540
         const float rew_prox = -1.0f * (CONTROL_DT * prox);
         reward += p.rew[QS_REW_QUADCOL_BIN] * raw_quadcol;
@@ -951,8 +1001,8 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         // ================= outputs of this step =================
         const long long ta = (long long)t * A + a;
         if (valid) {
-            p.rewards[ta] = reward;
-            p.dones[ta] = done ? 1 : 0;
+            __stcs(p.rewards + ta, reward);
+            __stcs(p.dones + ta, (uint8_t)(done ? 1 : 0));
             if (p.rew_terms) {
                 float* tr = p.rew_terms + ta * QS_NUM_TERMS;
                 tr[QS_TERM_RAW_POS] = SIM_DT * -dist;
@@ -970,6 +1020,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         float nvel[3] = {s.vel[0], s.vel[1], s.vel[2]};
         const bool do_reset = done && env_ok;
         if (__any_sync(0xffffffffu, do_reset)) {          // warp-uniform branch
+            QS_TL(9);
             if (do_reset && valid) {
                 const float4 sums = QS_LD(st.slots + SL_DIST_SUMS * st.a_pad + a);
                 const int len = p.ep_len + 1;
@@ -981,7 +1032,12 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
             if (do_reset && i == 0) {
                 int32_t* c = st.env_cnt + (long long)env * QS_NUM_ENV_STATS;
                 int32_t* o = st.stats_env + (long long)env * QS_NUM_ENV_STATS;
-                for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = QS_LD(c + k); c[k] = 0; }
+                // all loads first, then the stores: a load behind a store to the same line waits for the store's round trip
+                int32_t v[QS_NUM_ENV_STATS];
+#pragma unroll
+                for (int k = 0; k < QS_NUM_ENV_STATS; ++k) v[k] = QS_LD(c + k);
+#pragma unroll
+                for (int k = 0; k < QS_NUM_ENV_STATS; ++k) { o[k] = v[k]; c[k] = 0; }
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
                 o[QS_STAT_SCENARIO] = (dev_scn || env_metric) ? QS_LD(st.scn_i + env).x : p.scenario;
             }
@@ -1003,6 +1059,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 __syncwarp();
                 if (pend != 0 && i == 0) st.dyn_pending[env] = 0;
             }
+#ifdef QS_TIMELINE
+            if (__float_as_int(s.pos[0]) == 0x7fffffff) QS_TL(7);
+            QS_TL(10);
+#endif
             if (do_reset) {
                 ctr.tick = 0;
                 ctr.episode_idx += 1;
@@ -1012,6 +1072,10 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                     dmin2 = min_pillar_dist2(p, s, s_obst_env);          // new pose, new pillar table
                 }
             }
+#ifdef QS_TIMELINE
+            if (__float_as_int(nz.p[0] + dmin2) == 0x7fffffff) QS_TL(7);
+            QS_TL(11);
+#endif
         }
         if (SPLIT) {
             // hand-off 2: final velocities / rates (and the whole state after a reset) + per-env flags
@@ -1031,6 +1095,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
                 const int slot = (lane / NP) * p.N + i;               // row of this drone inside the warp's tile
                 if (p.obs_bulk && p.T > 1) bulk_drain();              // the previous step's copy has read the tile
                 write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp);
+                QS_TL(5);
                 const int env_first = blockIdx.x * envs_per_block + (threadIdx.x >> 5) * (32 / NP);
                 const int envs_here = min(32 / NP, p.E - env_first);
                 if (envs_here > 0)
@@ -1055,6 +1120,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
     }
 
     if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
+    QS_TL(6);
     if (valid) store_agent(st, a, s, goal_dirty);
     if (!SPLIT && p.obs_bulk) bulk_drain();           // shared memory must outlive the bulk copy's reads
     if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
@@ -1062,6 +1128,7 @@ __global__ void __launch_bounds__(QS_LB) qs_step_kernel(const __grid_constant__ 
         if (SPLIT) bar_sync(4); else __syncthreads();
         if (threadIdx.x == 0) handover_release(st.ready + blockIdx.x);
     }
+    QS_TL(7);
 }
 
 // Explicit reset of the masked envs: QuadrotorEnvMulti.reset, quadrotor_multi.py:339-411.

@@ -35,6 +35,10 @@ struct QsHandle {
     int bulk_mode;        // QS_OBS_BULK: -1 auto, 0 never use the bulk-copy engine for the observation write-out, 2 linear copies only
     int* err_host;        // mapped page-locked word the step kernels set when a hand-over wait timed out (sticky)
     cudaEvent_t ev_sync;  // the *_host entry points (own stream) order themselves after the caller-stream work below
+#ifdef QS_TIMELINE
+    unsigned long long* tl;
+    int tl_next;
+#endif
     cudaStream_t last_stream;   // stream of the most recent asynchronous call of this handle
     bool async_pending;
     // staging for the *_host entry points (pinned host + device mirrors)
@@ -276,7 +280,9 @@ __global__ void k_set_state(DevState st, int E, int N, int M, const uint8_t* mas
         for (int q = 0; q < 3; ++q)
             st.scn_f[3 * t + q] = make_float4(__int_as_float(sc[4 + 4 * q]), __int_as_float(sc[5 + 4 * q]),
                                               __int_as_float(sc[6 + 4 * q]), __int_as_float(sc[7 + 4 * q]));
-        st.epi[t] = make_int2(e[4 + QS_NUM_ENV_STATS + 16], 0);          // a pre-generated next-episode record no longer applies
+        // the pre-generated next-episode record stays: it is a function of (seed, env, episode number) only and is used
+        // only if its number still matches (reset_env)
+        st.epi[t] = make_int2(e[4 + QS_NUM_ENV_STATS + 16], st.epi[t].y);
     }
     if (obst != nullptr && t < (long long)E * M && (mask == nullptr || mask[t / M]))
         st.obst[t] = make_float2(obst[2 * t], obst[2 * t + 1]);
@@ -312,7 +318,7 @@ static int block_size() {
     if (b == 0) {
         const char* e = getenv("QS_BLOCK");
         b = e ? atoi(e) : 64;
-        if (b < 32 || b > 128 || (b % 32) != 0) b = 64;
+        if (b < 32 || b > QS_LB || (b % 32) != 0) b = 64;
     }
     return b;
 }
@@ -349,7 +355,21 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
     const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
     const bool split = want_split && p.obs_stage && h->NP > 1 && h->st.dyn == nullptr;
-    const int kBlock = split ? 64 : block_size();
+    // QS_BALANCE=1 (experiment): one CTA per SM, ceil(warps / SMs) warps each — every SM then holds the same number of warps
+    // whatever the CTA scheduler does while two step grids overlap (the timeline of the debug build showed SMs with 6 CTAs
+    // of 2 warps next to SMs with 2, and the step ends with the slowest block)
+    static int balance = -1;
+    if (balance < 0) { const char* e = getenv("QS_BALANCE"); balance = e ? atoi(e) : 1; }
+    int kBlock = split ? 64 : block_size();
+    if (h->NP >= 16 && kBlock > 128) kBlock = 128;          // launch bounds of the NP >= 16 instantiations
+    bool balanced = false;
+    if (balance && !split && h->NP < 16) {
+        int sms = 0;
+        QS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const int wpc = (int)((phys_warps + sms - 1) / sms);
+        // measured: c5 (8 x 4096, K = 6, staggered resets) 13.7 -> 10.0 us per step, c3 unchanged
+        if (wpc >= 2 && wpc * 32 <= QS_LB && ((wpc * 32) % h->NP) == 0) { kBlock = wpc * 32; balanced = true; }
+    }
     const int envs_per_block = (split ? 32 : kBlock) / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
@@ -357,6 +377,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     p.smem_tile_off = (int)(smem / sizeof(float));
     if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
     if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
+    if (balanced && smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;       // only one CTA fits an SM
     // Programmatic dependent launch between consecutive step grids (QS_PDL overrides; default -1 = choose per handle):
     //   0 off; 1 grid-wide wait, trigger at kernel start (measured 2 us slower); 2 grid-wide wait, trigger before the final
     //   stores (0.2-0.4 us faster per step than 0); 3 per-block hand-over, no grid-wide wait (qs_step.cuh).
@@ -404,6 +425,10 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // The hand-over kernels pay off only between step grids that follow each other directly; an unchained handle uses
     // the grid-wide wait (formally safe after any predecessor) and never pre-fetches across the dependency wait.
     p.chained = (h->chained && h->last_was_step) ? 1 : 0;
+#ifdef QS_TIMELINE
+    if (!h->tl) { QS_CUDA(cudaMalloc((void**)&h->tl, sizeof(unsigned long long) * 64 * 4096 * 16)); QS_CUDA(cudaMemset(h->tl, 0, sizeof(unsigned long long) * 64 * 4096 * 16)); }
+    p.tl = h->tl; p.tl_slot = h->tl_next; h->tl_next = (h->tl_next + 1) % 64;
+#endif
     const bool use_ho = h->handover && h->chained && fn_dyn == nullptr;
     const int pdl_mode = use_ho ? 3 : ((pdl_env >= 0 && pdl_env != 3) ? pdl_env : 2);
     const bool use_pdl = pdl_mode != 0;
@@ -414,7 +439,9 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
-    const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn_dyn ? fn_dyn : (use_ho ? fn_ho : fn_wait), p);
+    KernelFn fn = fn_dyn ? fn_dyn : (use_ho ? fn_ho : fn_wait);
+    if (smem > 48 * 1024) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn, p);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
     QS_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -441,7 +468,7 @@ static int launch_pregen(QsHandle* h, cudaStream_t s) {
 }
 
 static int launch_reset(QsHandle* h, const StepParams& p, cudaStream_t s) {
-    const int kBlock = block_size();
+    const int kBlock = block_size() > 128 ? 128 : block_size();
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     const size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
@@ -619,6 +646,16 @@ extern "C" int64_t qs_handover_timeouts(QsHandle* h) {
     if (cudaMemcpy(&v, h->st.ready + h->cfg.num_envs, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
 }
+
+#ifdef QS_TIMELINE
+// debug build: copies the [64][4096][8] stamp buffer to the host (synchronises)
+extern "C" int qs_debug_timeline(QsHandle* h, unsigned long long* out_host) {
+    if (!h || !h->tl) return fail(QS_ERR_INVALID_ARG, "no timeline");
+    QS_CUDA(cudaMemcpy(out_host, h->tl, sizeof(unsigned long long) * 64 * 4096 * 16, cudaMemcpyDeviceToHost));
+    return QS_OK;
+}
+extern "C" int qs_debug_timeline_rewind(QsHandle* h) { if (h) h->tl_next = 0; return QS_OK; }
+#endif
 
 extern "C" int qs_set_chained(QsHandle* h, int on) {
     if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");

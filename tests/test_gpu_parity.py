@@ -380,22 +380,26 @@ def test_full_size_sampled_parity(name, chained):
 
 
 # ---- per-drone physical constants (other models, dynamics randomisation, rotor drag) ----
-def _dyn_rows(E, N, seed):
-    """A zoo of airframes: the named models, RandomQuad draws, a Crazyflie with rotor drag / rolling moment, non-unit motor
-    linearity and velocity / body-rate damping — one row per drone (quad_models.constants_row)."""
+DYN_KINDS = ('defaultquad', 'mediumquad', 'randomquad', 'rotor_drag', 'relative', 'zoo')
+
+
+def _dyn_rows(E, N, seed, kind='zoo'):
+    """Airframes: the named models, RandomQuad draws, a Crazyflie with rotor drag / rolling moment, non-unit motor
+    linearity and velocity / body-rate damping, perturbed Crazyflies — one row per drone (quad_models.constants_row);
+    'zoo' mixes all of them inside every env."""
     from quad_swarm_rl_b200 import quad_models as qm
     rs = np.random.RandomState(seed)
     rows = np.zeros((E, N, qm.DYN_ROW), np.float32)
     for e in range(E):
         for i in range(N):
-            kind = (e * N + i) % 5
-            if kind == 0:
+            k = DYN_KINDS[(e * N + i) % 5] if kind == 'zoo' else kind
+            if k == 'defaultquad':
                 p = qm.defaultquad_params()
-            elif kind == 1:
+            elif k == 'mediumquad':
                 p = qm.mediumquad_params()
-            elif kind == 2:
+            elif k == 'randomquad':
                 p = qm.RandomQuad().sample(rs=rs)
-            elif kind == 3:
+            elif k == 'rotor_drag':
                 p = qm.crazyflie_params()
                 p['motor'].update(C_drag=0.0028 * rs.uniform(0.5, 20), C_roll=0.003 * rs.uniform(0.5, 5), linearity=0.6)
                 p['damp'].update(vel=0.001, omega_quadratic=0.01)
@@ -412,38 +416,44 @@ def _params_of(rows):
     return [[qo.quad_params_from_constants(dict(zip(DYN_FIELDS, r.astype(np.float64)))) for r in env_rows] for env_rows in rows]
 
 
+@pytest.mark.parametrize('kind', DYN_KINDS)
 @pytest.mark.parametrize('kw_name', ['free', 'obstacles'])
-def test_per_drone_dynamics_models_match_oracle(kw_name):
+def test_per_drone_dynamics_models_match_oracle(kw_name, kind):
     """qs_set_dynamics: every drone flies its own airframe (DefaultQuad, MediumQuad, RandomQuad draws, perturbed Crazyflies,
-    rotor drag + rolling moment, linearity 0.6, velocity / body-rate damping).  Half-way the constants of every env are
-    replaced with at_next_reset = True: the kernel latches them at the env's auto-reset (OU state and SVD counter restart),
-    the oracle does the same through its dyn_source hook (quadrotor_single.py:387-390)."""
+    rotor drag + rolling moment with linearity 0.6 and velocity / body-rate damping; 'zoo' = all of them in one env).
+    Half-way the constants of every env are replaced with at_next_reset = True: the kernel latches them at the env's
+    auto-reset (OU state and SVD counter restart), the oracle does the same through its dyn_source hook
+    (quadrotor_single.py:387-390)."""
     from tests import parity_util as pu
     if kw_name == 'free':
         kw = dict(num_agents=5, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_wall', ep_time=0.6, use_downwash=True)
     else:
         kw = dict(C3, ep_time=0.5, num_agents=4)
     E, N = 6, kw['num_agents']
-    rows0, rows1 = _dyn_rows(E, N, 1), _dyn_rows(E, N, 2)
+    rows0, rows1 = _dyn_rows(E, N, 1, kind), _dyn_rows(E, N, 2, kind)
     pair = pu.Pair(E, kw, seed=777, table_seed=778)
     pair.engine.set_dynamics(rows0)
     P0, P1 = _params_of(rows0), _params_of(rows1)
-    state = dict(pending=False)
+    pending = [[False] * N for _ in range(E)]
     for e, o in enumerate(pair.oracles):
         o.Ps = list(P0[e])
         o.P = o.Ps[0]
 
         def src(i, e=e):
-            return P1[e][i] if state['pending'] else None
+            if pending[e][i]:
+                pending[e][i] = False              # latched once, like the kernel's dyn_pending word
+                return P1[e][i]
+            return None
         o.dyn_source = src
 
     def hook(p, t):
         if t == 40:                                 # uploaded mid-episode: nothing changes before the next reset
             p.engine.set_dynamics(rows1, at_next_reset=True)
-            state['pending'] = True
+            for e in range(E):
+                pending[e] = [True] * N
     rep = pu.run_parity(pair, 150, np.random.RandomState(3), resync=20, hook=hook)
-    print(rep)
-    assert rep['dones'] >= 2 * E and rep['floor'] > 0
+    print(kind, rep)
+    assert rep['dones'] >= 2 * E
     frac = rep['skipped_env_steps'] / max(1, rep['skipped_env_steps'] + rep['compared_env_steps'])
     assert frac < 0.10, rep
     pair.engine.close()
