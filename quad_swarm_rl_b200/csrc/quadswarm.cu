@@ -419,7 +419,10 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
             int per_sm = 0, sms = 0;
             QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_ho, kBlock, smem));
             QS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-            h->handover = split || (long long)grid > (long long)per_sm * sms;
+            // measured on c3 with envs resetting in different steps (round 2, profiles/r02_*): the reset of an env with a
+            // pillar table makes its block ~2 us late; with the grid-wide wait every step pays that (11.2 us), with the
+            // hand-over only the block's own chain does (10.2 us).  Lock-step envs: 9.2 vs 10.0 us (QS_PDL=2 selects it).
+            h->handover = split || (long long)grid > (long long)per_sm * sms || h->cfg.use_obstacles != 0;
         }
     }
     // The hand-over kernels pay off only between step grids that follow each other directly; an unchained handle uses
