@@ -307,7 +307,7 @@ class StepRunner:
     Rings: P = NG * K slots of actions / observations / rewards / dones, each ring larger than L2, so consecutive
     replays never find their inputs or outputs in cache; graph j covers ring slots [j K, (j+1) K)."""
 
-    def __init__(self, torch, cfg, E, args, local_rank, rank, K, graph=True, stagger=True):
+    def __init__(self, torch, cfg, E, args, local_rank, rank, K, graph=True, stagger=True, wrapped=False):
         from quad_swarm_rl_b200.engine import QuadSwarmEngine
         self.torch = torch
         kw = cfg['kw']
@@ -315,7 +315,11 @@ class StepRunner:
         dev = self.dev = torch.device('cuda', local_rank)
         dev_scn = None if args.host_tables else cfg['mode']
         self.dev_scn = dev_scn
-        eng = self.eng = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=rank * E, rew_coeff=cfg['rew'],
+        from quad_swarm_rl_b200.sharding import shard_range
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        lo, hi = shard_range(world * E, world, rank)                 # contiguous block of global env ids of this rank
+        assert hi - lo == E
+        eng = self.eng = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=lo, rew_coeff=cfg['rew'],
                                          ep_time=args.ep_time, device_scenario=dev_scn, **kw)
         if dev_scn is None:
             goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank * 64)
@@ -330,6 +334,11 @@ class StepRunner:
             g.manual_seed(1234 + rank)
             st['env_i32'][:, 0] = torch.randint(0, eng.ep_len + 1, (E,), device=dev, generator=g, dtype=torch.int32)
             eng.set_state(st)
+        self.wrapped = wrapped
+        if wrapped:
+            # the reference's default training stack (replay p = 0.75 + reward shaping) as the kernel behind every step;
+            # the can_drones_fly gate is bypassed: random actions never learn to fly, and the point is to time the full path
+            eng.wrap_enable(use_replay=os.environ.get('QS_WRAP_REPLAY', '1') != '0', replay_buffer_size=20, replay_prob=0.75, replay_always_active=True)
         eng.set_chained(True)           # the step grids of a graph follow each other directly on the stream
         A, D = E * self.N, eng.D
         self.A, self.D, self.M = A, D, eng.M
@@ -370,7 +379,10 @@ class StepRunner:
 
     def _one(self):
         k = self.counter % self.P
-        self.eng.step(self.act[k], obs_out=self.obs[k], rewards_out=self.rew[k], dones_out=self.done[k])
+        if self.wrapped:
+            self.eng.wrap_step(self.act[k], obs_out=self.obs[k], rewards_out=self.rew[k], dones_out=self.done[k])
+        else:
+            self.eng.step(self.act[k], obs_out=self.obs[k], rewards_out=self.rew[k], dones_out=self.done[k])
         self.counter += 1
 
     def run(self, n):
@@ -433,19 +445,18 @@ def time_blocks(torch, dist, runner, K, R, world, side=None, metrics=None, gathe
 
 
 def block_times(torch, dist, pairs, world, dev):
+    from quad_swarm_rl_b200.sharding import reduce_metrics
     ms = [a.elapsed_time(b) for a, b in pairs]
     if world > 1:
-        t = torch.tensor(ms, device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.tolist()
+        ms = reduce_metrics(torch.tensor(ms, device=dev, dtype=torch.float64), op='max').tolist()      # max over ranks per block
     return ms
 
 
-def measure_workload(torch, dist, name, args, local_rank, rank, world, K, target_s, clocks=None, side=None, metrics=None):
+def measure_workload(torch, dist, name, args, local_rank, rank, world, K, target_s, clocks=None, side=None, metrics=None, wrapped=False):
     """Device-resident agent-steps/s of one workload: R blocks of K chained step launches, median block."""
     cfg = CONFIGS[name]
     E = (args.envs if name == args.config and args.envs else cfg['E'])
-    runner = StepRunner(torch, cfg, E, args, local_rank, rank, K, graph=not args.no_graph, stagger=not args.lockstep)
+    runner = StepRunner(torch, cfg, E, args, local_rank, rank, K, graph=not args.no_graph, stagger=not args.lockstep, wrapped=wrapped)
     dev = runner.dev
     with torch.cuda.stream(runner.stream):
         runner.run(max(3, args.warmup))
@@ -579,6 +590,19 @@ def run_cuda_arm(args):
                                 'roofline_frac': main['b_alg'] * A * T / sec / 1e9 / main['peak'],
                                 'note': 'qs_rollout: T control steps per launch, all observations written'}
             del o, r, d_, acts
+            # (a') the headline workload with the reference's default wrapper stack behind every step (csrc/qs_wrap.cuh)
+            sub = argparse.Namespace(**vars(args))
+            m = measure_workload(torch, dist, args.config, sub, local_rank, rank, world, min(K, 2000), 0.15, wrapped=True)
+            agg = m['runner'].eng.wrap_read(reset=False)
+            from quad_swarm_rl_b200 import _lib as L_
+            extra['wrapped'] = {'us_per_step': m['us_per_step'], 'agent_steps_per_s': m['value'], 'vs_bare_step': m['us_per_step'] / main['us_per_step'],
+                                'launches_per_step': 2, 'episodes_finished': float(agg[L_.WA['EPISODES_TOTAL']]),
+                                'checkpoints': float(agg[L_.WA['CHECKPOINTS']]), 'events_stored': float(agg[L_.WA['EVENTS_STORED']]),
+                                'events_replayed': float(agg[L_.WA['REPLAYED_EVENTS']]),
+                                'note': 'qs_wrap_step: step kernel + the wrapper kernel (reward-shaping accumulators and episode statistics, '
+                                        'checkpoint every 0.5 s, collision events, replay p = 0.75 with the can_drones_fly gate open); no host sync'}
+            m['runner'].close()
+            torch.cuda.empty_cache()
             # (b) the other BASELINE configs and a 4x batch of the headline workload, same protocol (blocks of K chained launches)
             per_cfg = {}
             sub = argparse.Namespace(**vars(args))

@@ -247,6 +247,40 @@ int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stat
  * There is no reference counterpart (Sample Factory steps its envs from Python, one at a time). */
 int qs_set_chained(QsHandle* h, int on);
 
+/* ---- the training wrappers as kernels -------------------------------------------------------------
+ * Replaces QuadsRewardShapingWrapper.step (swarm_rl/env_wrappers/reward_shaping.py:52-123: cumulative reward terms, action
+ * statistics, true_reward, episode_extra_stats) and ExperienceReplayWrapper.step / new_episode
+ * (gym_art/quadrotor_multi/quad_experience_replay.py:66-209: checkpoint every 0.5 s, the checkpoint from 1.5 s before a
+ * collision goes into the env's event buffer, finished envs replay a buffered event with probability p once the drones can
+ * fly, quadrotor_multi.py:281-287,356-359).  qs_wrap_step = the step kernel + ONE epilogue kernel; no host
+ * synchronisation: statistics of finished episodes are accumulated on the device and fetched with qs_wrap_read whenever
+ * the trainer logs.  The env "deep copy" of the reference is a copy of the env's state rows (what qs_get_state exports). */
+typedef struct QsWrapConfig {
+    int32_t use_replay;              /* cfg.replay_buffer_sample_prob > 0 (swarm_rl/env_wrappers/quad_utils.py:67-70) */
+    int32_t replay_buffer_size;      /* events per env; the reference keeps 20 per wrapped env (quad_experience_replay.py:16-21) */
+    float replay_prob;               /* replay_buffer_sample_prob */
+    int32_t replay_always_active;    /* 1: skip the can_drones_fly gate (tests) */
+    int32_t reserved_[4];
+} QsWrapConfig;
+int qs_wrap_enable(QsHandle* h, const QsWrapConfig* cfg);
+/* one control step of the wrapped envs: qs_step, then the wrappers' bookkeeping for this step (rows of obs_dev of envs that
+ * restart from a replayed event are overwritten with the event's observation, as ExperienceReplayWrapper.step returns it) */
+int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev, void* stream);
+/* sums over the episodes finished since the last read with reset != 0, layout QS_WA_* below; synchronises `stream`.
+ * A mean statistic = its sum / the matching episode count (QS_WA_AGENT_EPISODES or QS_WA_ENV_EPISODES). */
+#define QS_WRAP_AGG 149
+enum {
+    QS_WA_AGENT_EPISODES = 0, QS_WA_TRUE_REWARD = 1, QS_WA_RAW0 = 2, QS_WA_REW0 = 10, QS_WA_ACT_MEAN0 = 18, QS_WA_ACT_STD0 = 22,
+    QS_WA_ENV_EPISODES = 26, QS_WA_ENV_STAT0 = 27, QS_WA_DIST0 = 38, QS_WA_SUCCESS = 41, QS_WA_DEADLOCK = 42, QS_WA_COL = 43,
+    QS_WA_NEIGHBOR_COL = 44, QS_WA_OBST_COL = 45, QS_WA_REPLAY_ENV_EPISODES = 46, QS_WA_REPLAY_COLLISIONS = 47,
+    QS_WA_REPLAY_COLLISIONS_OBST = 48, QS_WA_EPISODES_TOTAL = 49, QS_WA_REPLAYED_EVENTS = 50, QS_WA_EVENTS_STORED = 51,
+    QS_WA_CHECKPOINTS = 52, QS_WA_SCN0 = 53           /* + 6 * scenario id: agent-episodes, rew_pos, rew_crash, env-episodes,
+                                                         num_collisions_after_settle, distance_to_goal_1s */
+};
+int qs_wrap_read(QsHandle* h, float* agg_host, int reset, void* stream);
+/* infos['true_reward'] of the most recently finished episode of every agent, [E,N] floats (device -> device copy) */
+int qs_wrap_true_reward(QsHandle* h, float* out_dev, void* stream);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t qs_launch_count(const QsHandle* h);
 

@@ -54,6 +54,16 @@ class QsConfig(C.Structure):
     ]
 
 
+class QsWrapConfig(C.Structure):
+    _fields_ = [('use_replay', C.c_int32), ('replay_buffer_size', C.c_int32), ('replay_prob', C.c_float),
+                ('replay_always_active', C.c_int32), ('reserved_', C.c_int32 * 4)]
+
+
+QS_WRAP_AGG = 149
+WA = dict(AGENT_EPISODES=0, TRUE_REWARD=1, RAW0=2, REW0=10, ACT_MEAN0=18, ACT_STD0=22, ENV_EPISODES=26, ENV_STAT0=27, DIST0=38,
+          SUCCESS=41, DEADLOCK=42, COL=43, NEIGHBOR_COL=44, OBST_COL=45, REPLAY_ENV_EPISODES=46, REPLAY_COLLISIONS=47,
+          REPLAY_COLLISIONS_OBST=48, EPISODES_TOTAL=49, REPLAYED_EVENTS=50, EVENTS_STORED=51, CHECKPOINTS=52, SCN0=53)
+
 EXPORTS = {
     # name: (restype, argtypes)
     'qs_create': (C.c_int, [C.POINTER(QsConfig), C.c_int, C.POINTER(C.c_void_p)]),
@@ -77,6 +87,10 @@ EXPORTS = {
     'qs_read_episode_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_set_chained': (C.c_int, [C.c_void_p, C.c_int]),
     'qs_set_dynamics': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'qs_wrap_enable': (C.c_int, [C.c_void_p, C.POINTER(QsWrapConfig)]),
+    'qs_wrap_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qs_wrap_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'qs_wrap_true_reward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_launch_count': (C.c_int64, [C.c_void_p]),
     'qs_handover_timeouts': (C.c_int64, [C.c_void_p]),
 }

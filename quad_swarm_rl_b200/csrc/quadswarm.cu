@@ -10,6 +10,7 @@
 #include <cuda.h>          // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
 
 #include "qs_step.cuh"
+#include "qs_wrap.cuh"
 
 using namespace qs;
 
@@ -28,6 +29,9 @@ struct QsHandle {
     int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
     int pdl_env;          // QS_PDL at the first step launch (-2 = not read yet, -1 = unset)
     int handover;         // -1 not decided yet, 0 grid-wide wait between step grids, 1 per-block hand-over (launch_step)
+    bool wrap_on;
+    WrapState wrap;
+    float* wrap_agg_host; // pinned
     int pregen_every;     // step launches between two launches of the next-episode generator (0 = never), QS_PREGEN overrides
     int since_pregen;
     int chained;          // qs_set_chained: consecutive qs_step / qs_rollout launches follow each other directly on the stream
@@ -628,6 +632,12 @@ extern "C" int qs_destroy(QsHandle* h) {
     cudaFree(h->d_mask);
     cudaFreeHost(h->h_actions); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_terms);
     cudaFreeHost(h->h_dones); cudaFreeHost(h->h_mask);
+    if (h->wrap_on) {
+        WrapState& w = h->wrap;
+        cudaFree(w.acc); cudaFree(w.ep_steps); cudaFree(w.true_reward); cudaFree(w.agg); cudaFree(w.snap_slots); cudaFree(w.snap_obs);
+        cudaFree(w.snap_env); cudaFree(w.snap_obst); cudaFree(w.rp); cudaFree(w.rq); cudaFree(w.crash_now); cudaFree(w.crash_hist);
+        cudaFree(w.ev_state); cudaFreeHost(h->wrap_agg_host);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->err_host) cudaFreeHost(h->err_host);
@@ -659,6 +669,105 @@ extern "C" int qs_debug_timeline(QsHandle* h, unsigned long long* out_host) {
 }
 extern "C" int qs_debug_timeline_rewind(QsHandle* h) { if (h) h->tl_next = 0; return QS_OK; }
 #endif
+
+// ------------------------------------------------------------------------------------------
+// training wrappers (qs_wrap.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" int qs_wrap_enable(QsHandle* h, const QsWrapConfig* cfg) {
+    if (!h || !cfg) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (h->wrap_on) return fail(QS_ERR_INVALID_ARG, "wrappers already enabled");
+    if (cfg->use_replay && h->cfg.scenario == QS_SCENARIO_HOST_TABLES)
+        return fail(QS_ERR_UNSUPPORTED, "collision-event replay on the device needs device-side scenarios (host scenario objects are not part of a snapshot)");
+    if (cfg->use_replay && (cfg->replay_buffer_size < 1 || cfg->replay_buffer_size > 64)) return fail(QS_ERR_INVALID_ARG, "replay_buffer_size must be 1..64");
+    QS_CUDA(cudaSetDevice(h->device));
+    WrapState& w = h->wrap;
+    memset(&w, 0, sizeof(w));
+    const long long A = h->A, E = h->cfg.num_envs, N = h->cfg.num_agents, M = h->M > 0 ? h->M : 1;
+    QS_ALLOC0(w.acc, sizeof(float4) * 6 * A);
+    QS_ALLOC0(w.ep_steps, sizeof(int) * E);
+    QS_ALLOC0(w.true_reward, sizeof(float) * A);
+    QS_ALLOC0(w.agg, sizeof(float) * QS_WRAP_AGG);
+    QS_CUDA(cudaMallocHost((void**)&h->wrap_agg_host, sizeof(float) * QS_WRAP_AGG));
+    w.replay_on = cfg->use_replay ? 1 : 0;
+    w.replay_prob = cfg->replay_prob;
+    w.always_active = cfg->replay_always_active ? 1 : 0;
+    if (w.replay_on) {
+        w.buffer = cfg->replay_buffer_size;
+        w.slots = RP_KEEP + w.buffer;
+        QS_ALLOC0(w.snap_slots, sizeof(float4) * E * w.slots * NUM_SLOTS * N);
+        QS_ALLOC0(w.snap_obs, sizeof(float) * E * w.slots * N * h->D);
+        QS_ALLOC0(w.snap_env, sizeof(int32_t) * E * w.slots * SNAP_ENV_I32);
+        QS_ALLOC0(w.snap_obst, sizeof(float2) * E * w.slots * M);
+        QS_ALLOC0(w.rp, sizeof(int4) * E);
+        QS_ALLOC0(w.rq, sizeof(int4) * E);
+        QS_ALLOC0(w.crash_now, sizeof(float) * E);
+        QS_ALLOC0(w.crash_hist, sizeof(float) * E * 100);
+        QS_CUDA(cudaMalloc((void**)&w.ev_state, sizeof(int32_t) * E * w.buffer));
+        QS_CUDA(cudaMemset(w.ev_state, 0xff, sizeof(int32_t) * E * w.buffer));          // -1: empty
+        std::vector<int4> rp((size_t)E, make_int4(0, 0, 0, -(1 << 30)));
+        QS_CUDA(cudaMemcpy(w.rp, rp.data(), sizeof(int4) * E, cudaMemcpyHostToDevice));
+        if (w.always_active) {
+            std::vector<int4> rq((size_t)E, make_int4(0, 1, 0, 0));
+            QS_CUDA(cudaMemcpy(w.rq, rq.data(), sizeof(int4) * E, cudaMemcpyHostToDevice));
+        }
+    }
+    h->wrap_on = true;
+    return QS_OK;
+}
+
+extern "C" int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev, void* stream) {
+    if (!h || !h->wrap_on) return fail(QS_ERR_INVALID_ARG, "qs_wrap_enable first");
+    int rc = qs_step(h, actions_dev, obs_dev, rewards_dev, dones_dev, h->d_terms, stream);
+    if (rc != QS_OK) return rc;
+    static int probe = -1;                 // QS_WRAP_PROBE (tuning): 1 = skip the wrapper kernel, 2 = launch it without PDL
+    if (probe < 0) { const char* e = getenv("QS_WRAP_PROBE"); probe = e ? atoi(e) : 0; }
+    if (probe == 1) return QS_OK;
+    WrapParams q;
+    fill_params(h, q.sp);
+    q.w = h->wrap;
+    q.actions = (const float4*)actions_dev;
+    q.terms = h->d_terms;
+    q.dones = dones_dev;
+    q.obs = obs_dev;
+    const int kBlock = 128;
+    const int envs_per_block = kBlock / h->NP;
+    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = 0; lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // launched behind the step grid's late trigger
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = probe == 2 ? 0 : 1;
+    using WrapFn = void (*)(WrapParams);
+    WrapFn fn = nullptr;
+    rc = dispatch_np(h->NP, [&](auto np) { fn = (WrapFn)qs_wrap_kernel<decltype(np)::value>; return QS_OK; });
+    if (rc != QS_OK) return rc;
+    const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn, q);
+    if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx(wrap): ") + cudaGetErrorString(lerr));
+    h->launches += 1;
+    note_async(h, (cudaStream_t)stream, false);
+    return QS_OK;
+}
+
+extern "C" int qs_wrap_read(QsHandle* h, float* agg_host, int reset, void* stream) {
+    if (!h || !h->wrap_on || !agg_host) return fail(QS_ERR_INVALID_ARG, "null argument / wrappers not enabled");
+    QS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_CUDA(cudaMemcpyAsync(h->wrap_agg_host, h->wrap.agg, sizeof(float) * QS_WRAP_AGG, cudaMemcpyDeviceToHost, s));
+    if (reset) QS_CUDA(cudaMemsetAsync(h->wrap.agg, 0, sizeof(float) * QS_WRAP_AGG, s));
+    QS_CUDA(cudaStreamSynchronize(s));
+    memcpy(agg_host, h->wrap_agg_host, sizeof(float) * QS_WRAP_AGG);
+    note_async(h, s, false);
+    return QS_OK;
+}
+
+extern "C" int qs_wrap_true_reward(QsHandle* h, float* out_dev, void* stream) {
+    if (!h || !h->wrap_on || !out_dev) return fail(QS_ERR_INVALID_ARG, "null argument / wrappers not enabled");
+    QS_CUDA(cudaSetDevice(h->device));
+    QS_CUDA(cudaMemcpyAsync(out_dev, h->wrap.true_reward, sizeof(float) * h->A, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    note_async(h, (cudaStream_t)stream, false);
+    return QS_OK;
+}
 
 extern "C" int qs_set_chained(QsHandle* h, int on) {
     if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");

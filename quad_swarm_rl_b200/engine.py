@@ -212,6 +212,32 @@ class QuadSwarmEngine:
         m = self._dev_mask(env_mask)
         L.check(self.lib.qs_set_dynamics(self.h, _ptr(m), _ptr(r), int(bool(at_next_reset)), self._stream()))
 
+    # ---- the training wrappers as kernels (include/quadswarm.h, qs_wrap_*)
+    def wrap_enable(self, use_replay=False, replay_buffer_size=20, replay_prob=0.75, replay_always_active=False):
+        c = L.QsWrapConfig()
+        c.use_replay, c.replay_buffer_size = int(bool(use_replay)), int(replay_buffer_size)
+        c.replay_prob, c.replay_always_active = float(replay_prob), int(bool(replay_always_active))
+        L.check(self.lib.qs_wrap_enable(self.h, C.byref(c)))
+        self._agg = np.zeros(L.QS_WRAP_AGG, np.float32)
+        self._true_reward = torch.zeros((self.E, self.N), dtype=torch.float32, device=self.device)
+
+    def wrap_step(self, actions, obs_out=None, rewards_out=None, dones_out=None):
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+        obs = self.obs if obs_out is None else obs_out
+        rew = self.rewards if rewards_out is None else rewards_out
+        done = self.dones if dones_out is None else dones_out
+        self.push_reward_coeffs()
+        L.check(self.lib.qs_wrap_step(self.h, _ptr(actions), _ptr(obs), _ptr(rew), _ptr(done), self._stream()))
+        return obs, rew, done
+
+    def wrap_read(self, reset=True):
+        L.check(self.lib.qs_wrap_read(self.h, self._agg.ctypes.data_as(C.c_void_p), int(bool(reset)), self._stream()))
+        return self._agg.copy()
+
+    def wrap_true_reward(self):
+        L.check(self.lib.qs_wrap_true_reward(self.h, _ptr(self._true_reward), self._stream()))
+        return self._true_reward
+
     def set_chained(self, on=True):
         """Promise (or retract) that consecutive step() / rollout() calls follow each other directly on the stream
         (include/quadswarm.h, qs_set_chained): rollouts with pre-generated actions, CUDA graphs of steps."""

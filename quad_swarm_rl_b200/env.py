@@ -450,10 +450,14 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         obs = self._reset_all()
         return obs.view(self.num_agents, -1), {}
 
-    def step(self, actions, with_terms=False):
-        """with_terms: also fill engine.rew_terms [E,N,QS_NUM_TERMS] (raw reward terms of this step, batched.py)."""
+    def step(self, actions, with_terms=False, wrapped=False):
+        """with_terms: also fill engine.rew_terms [E,N,QS_NUM_TERMS] (raw reward terms of this step); wrapped: the step
+        runs with the training wrappers' kernel behind it (training.BatchedTrainingEnv, engine.wrap_enable)."""
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.engine.device).reshape(self.num_envs, self.num_agents_per_env, 4)
-        obs, rew, done = self.engine.step(a.contiguous(), with_terms=with_terms)
+        if wrapped:
+            obs, rew, done = self.engine.wrap_step(a.contiguous())
+        else:
+            obs, rew, done = self.engine.step(a.contiguous(), with_terms=with_terms)
         if self.device_scenario is not None:           # nothing to do on the host: episodes and goal events live in the kernels
             return obs.view(self.num_agents, -1), rew.view(-1), done.view(-1).bool(), self._truncated, {}
         self._tick += 1

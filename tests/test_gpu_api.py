@@ -342,10 +342,10 @@ def _ref_style_env(**over):
     return QuadrotorEnvMulti(**kw)
 
 
-def test_env_snapshot_restore_and_replay_wrapper():
-    """env.snapshot()/restore() (device SoA state + host episode state) replays bit-identically, and the replay wrapper
-    (quad_experience_replay.py semantics) stores the checkpoint taken 1.5 s before a collision and replays it."""
-    from quad_swarm_rl_b200.replay import ExperienceReplayWrapper
+def test_env_snapshot_restore():
+    """env.snapshot()/restore() (device SoA state + host episode state): with the RNG counters rewound the continuation is
+    bit-identical; by default they stay live (what a replayed event needs: same physics, fresh noise).  The collision-event
+    replay itself runs in the wrapper kernel: tests/test_gpu_batched.py."""
     env = _ref_style_env()
     env.reset()
     rs = np.random.RandomState(0)
@@ -366,21 +366,3 @@ def test_env_snapshot_restore_and_replay_wrapper():
     assert d.max() > 0 and d[:, :3].max() < 0.05 and d[:, 6:15].max() < 0.01 and d.max() < 1.0, d.max()   # fresh OU / sensor noise only
     env.close()
 
-    env = _ref_style_env(ep_time=4.0)
-    w = ExperienceReplayWrapper(env, 1.0, 0.2, 0.6)
-    w.reset()
-    env.activate_replay_buffer = True                 # as if the drones had already learnt to fly
-    ended = 0
-    for t in range(420):
-        if t == 320:                                  # plant a collision: all drones on top of each other
-            st = env.engine.get_state()
-            st['agent_f32'][0, :, 0:3] = torch.tensor([0.3, 0.2, 2.0], device='cuda') + 0.01 * torch.arange(8, device='cuda')[:, None]
-            env.engine.set_state(st)
-        obs, rew, dones, infos = w.step(rs.uniform(-1, 1, (8, 4)).astype(np.float32))
-        if dones[0]:
-            ended += 1
-            assert infos[0]['episode_extra_stats']['replay/replay_buffer_size'] == 1
-            assert set(infos[0]['episode_extra_stats']) >= {'num_collisions_replay', 'replay/replay_rate'}
-            assert env.envs[0].tick == 200            # replayed from the checkpoint 1.5 s before tick 321
-    assert ended == 1 and env.saved_in_replay_buffer and len(w.replay_buffer) == 1 and w.replayed_events == 1
-    env.close()

@@ -64,52 +64,53 @@ def test_spaces():
     assert make_action_space().shape == (4,) and float(make_action_space().low[0]) == -1.0
 
 
-class _FakeEnv:
-    """Stand-in with the QuadrotorEnvMulti protocol for wrapper tests."""
-    is_multiagent = True
-    num_agents = 2
+class _FakeBatched:
+    """Stand-in for training.BatchedTrainingEnv with one env of two drones (CPU tensors), for the single-env adapter."""
 
     def __init__(self):
-        self.rew_coeff = dict(pos=1.0, quadcol_bin=9.0, quadcol_bin_smooth_max=9.0, quadcol_bin_obst=9.0)
-        self.scenario = types.SimpleNamespace(name=lambda: 'Scenario_static_same_goal')
+        import torch
+        self.torch = torch
+        self.env = types.SimpleNamespace(num_agents_per_env=2)
+        self.engine = types.SimpleNamespace(device='cpu')
+        self.training_info = {}
         self.t = 0
-
-    @property
-    def unwrapped(self):
-        return self
+        self.flushed = 0
 
     def reset(self):
         self.t = 0
-        return np.zeros((2, 3))
+        return self.torch.zeros((2, 3)), {}
 
-    def step(self, action):
+    def step(self, a):
         self.t += 1
         done = self.t >= 3
-        infos = [{'rewards': {'rew_pos': -0.1, 'rew_crash': 0.0, 'rewraw_main': -0.2, 'rewraw_quadcol': -1.0 if i == 1 and self.t == 2 else 0.0}}
-                 for i in range(2)]
-        return np.ones((2, 3)) * self.t, [0.5, 0.5], [done, done], infos
+        return (self.torch.ones((2, 3)) * self.t, self.torch.tensor([0.5, 0.25]), self.torch.tensor([done, done]),
+                self.torch.tensor([False, False]), {})
+
+    def flush_stats(self):
+        self.flushed += 1
+        return {'episode_extra_stats': {'rew_pos': -0.3, 'z_anneal_quadcol_bin': 2.5}, 'true_reward': self.torch.tensor([[-0.6, -1000.6]]),
+                'episodes_finished': 1}
 
     def close(self):
         pass
 
 
-def test_reward_shaping_annealing_and_true_reward():
-    env = _FakeEnv()
-    scheme = dict(quad_rewards=dict(pos=1.0, quadcol_bin=0.0, quadcol_bin_smooth_max=0.0, quadcol_bin_obst=0.0))
-    ann = [wr.AnnealSchedule('quadcol_bin', 5.0, 1000)]
-    w = wr.QuadEnvCompatibility(wr.QuadsRewardShapingWrapper(env, reward_shaping_scheme=scheme, annealing=ann))
+def test_single_env_adapter_keeps_the_reference_protocol():
+    """QuadEnvCompatibility(QuadsTrainingEnv(...)): numpy observations, lists of per-agent rewards / dones / infos, the
+    gymnasium 5-tuple outside (compatibility.py:33-50); true_reward and episode_extra_stats appear on the terminal step."""
+    b = _FakeBatched()
+    w = wr.QuadEnvCompatibility(wr.QuadsTrainingEnv(b))
     obs, info = w.reset()
-    assert info == {} and obs.shape == (2, 3)
-    w.env.training_info['approx_total_training_steps'] = 500
+    assert info == {} and obs.shape == (2, 3) and obs.dtype == np.float64
     for t in range(3):
         obs, rew, term, trunc, infos = w.step(np.full((2, 4), 0.1 * t))
-    assert env.rew_coeff['quadcol_bin'] == 2.5            # annealed: 5.0 * 500 / 1000
-    assert term.all() and not trunc.any()
-    assert infos[0]['true_reward'] == pytest.approx(-0.6)
-    assert infos[1]['true_reward'] == pytest.approx(-0.6 - 1000.0)
-    st = infos[1]['episode_extra_stats']
-    assert st['Scenario_static_same_goal/rew_pos'] == pytest.approx(-0.3) and st['z_anneal_quadcol_bin'] == 2.5
-    assert st['z_action0_mean'] == pytest.approx(0.1)
+        assert isinstance(rew, list) and rew == [0.5, 0.25] and len(infos) == 2
+        if t < 2:
+            assert not term.any() and infos == [{}, {}] and b.flushed == 0
+    assert term.all() and not trunc.any() and b.flushed == 1
+    assert infos[0]['true_reward'] == pytest.approx(-0.6) and infos[1]['true_reward'] == pytest.approx(-1000.6)
+    assert infos[1]['episode_extra_stats']['z_anneal_quadcol_bin'] == 2.5
+    assert w.num_agents == 2 and w.is_multiagent
 
 
 def test_factory_rejects_what_is_out_of_scope():
@@ -118,63 +119,6 @@ def test_factory_rejects_what_is_out_of_scope():
         wr.make_quadrotor_env('quadrotor_multi', cfg=cfg)
     with pytest.raises(NotImplementedError):
         wr.make_quadrotor_env('quadrotor_single', cfg=cfg)
-
-
-class _FakeReplayEnv(_FakeEnv):
-    """Adds what ExperienceReplayWrapper reads (quad_experience_replay.py:71,140-151,183-188)."""
-    use_replay_buffer = True
-    use_obstacles = False
-    collisions_grace_period_seconds = 1.5
-    obst_density = 0.2
-
-    def __init__(self):
-        super().__init__()
-        self.activate_replay_buffer = True
-        self.saved_in_replay_buffer = False
-        self.tick = 0
-        self.envs = [types.SimpleNamespace(control_freq=100.0)]
-        self.last_step_unique_collisions = np.array([], dtype=int)
-        self.curr_quad_col = []
-        self.restored = []
-
-    def reset(self, obst_density=None, obst_size=None):
-        self.tick = 0
-        return np.zeros((2, 3))
-
-    def step(self, action):
-        self.tick += 1
-        self.envs[0].tick = self.tick
-        done = self.tick >= 400
-        self.last_step_unique_collisions = np.array([1, 2]) if self.tick == 320 else np.array([], dtype=int)
-        infos = [{'rewards': {}} for _ in range(2)]
-        if done:
-            self.tick = 0
-            self.envs[0].tick = 0
-        return np.full((2, 3), float(self.tick)), [0., 0.], [done, done], infos
-
-    def snapshot(self):
-        return {'tick': self.tick}
-
-    def restore(self, snap, zero_collision_counters=False):
-        self.restored.append(snap['tick'])
-        self.tick = snap['tick']
-        self.saved_in_replay_buffer = True
-
-
-def test_replay_wrapper_saves_the_checkpoint_from_1_5_s_before_a_collision():
-    from quad_swarm_rl_b200.replay import ExperienceReplayWrapper
-    env = _FakeReplayEnv()
-    w = ExperienceReplayWrapper(env, 1.0, 0.2, 0.6)
-    w.reset()
-    for t in range(400):
-        obs, rew, dones, infos = w.step(None)
-    assert env.saved_in_replay_buffer and len(w.replay_buffer) == 1
-    # collision at tick 320; checkpoints every 50 ticks -> [..., 200, 250, 300]; 1.5 s = 3 checkpoints back -> tick 200
-    assert w.replay_buffer.buffer[0].snapshot == {'tick': 200}
-    assert dones[0] and env.restored == [200] and w.replayed_events == 1
-    assert obs[0, 0] == 200.0                                          # the observation stored with that checkpoint
-    st = infos[0]['episode_extra_stats']
-    assert st['replay/replay_rate'] == 1.0 and st['replay/replay_buffer_size'] == 1
 
 
 def test_svd_period_is_100_substeps():
@@ -225,127 +169,35 @@ def test_sharding_two_ranks_gloo(tmp_path):
     assert r.stdout.count('ok') == 2
 
 
-# ---- batched wrappers (batched.py) on CPU tensors with a stand-in engine ----
-class _FakeBatchedEngine:
-    """Counts ticks per env, auto-resets after ep_len steps, reports a collision when told to."""
-
-    def __init__(self, E, N, D, ep_len):
-        import torch
-        self.device = torch.device('cpu')
-        self.E, self.N, self.D, self.ep_len, self.M = E, N, D, ep_len, 0
-        self.af = torch.zeros((E, N, 43)); self.au = torch.zeros((E, N, 4), dtype=torch.int32)
-        self.ei = torch.zeros((E, 36), dtype=torch.int32)
-        self.rew_terms = torch.zeros((E, N, 8))
-        self.rew_coeff = dict(pos=1.0, effort=0.05, crash=1.0, orient=1.0, spin=0.1, quadcol_bin=5.0,
-                              quadcol_bin_smooth_max=4.0, quadcol_bin_obst=5.0)
-        self.collide = torch.zeros(E, dtype=torch.bool)
-        self.stats_env = torch.zeros((E, 13), dtype=torch.int32)
-
-    def get_state(self):
-        import torch
-        return dict(agent_f32=self.af.clone(), agent_u32=self.au.clone(), env_i32=self.ei.clone(),
-                    obst_xy=torch.zeros((self.E, 0, 2)))
-
-    def set_state(self, st, env_mask=None):
-        m = env_mask.bool()
-        self.af[m] = st['agent_f32'][m]; self.au[m] = st['agent_u32'][m]; self.ei[m] = st['env_i32'][m]
-
-    def episode_stats(self):
-        import torch
-        return self.stats_env.clone(), torch.zeros((self.E, self.N, 4))
-
-
-class _FakeBatchedEnv:
-    device_scenario = 'static_same_goal'
-    use_obstacles = False
-    quads_mode = 'static_same_goal'
-
-    def __init__(self, E=6, N=2, D=5, ep_len=300):
-        self.engine = _FakeBatchedEngine(E, N, D, ep_len)
-        self.num_envs, self.num_agents_per_env, self.num_agents = E, N, E * N
-
-    def reset(self, **kw):
-        e = self.engine
-        e.af.zero_(); e.ei.zero_()
-        return e.af[..., :e.D].reshape(self.num_agents, -1).clone(), {}
-
-    def step(self, actions, with_terms=False):
-        import torch
-        e = self.engine
-        e.ei[:, 0] += 1
-        e.ei[:, 1] += 1                                   # RNG step counter: never rewinds
-        e.af += 1.0                                       # the "physics": every state entry counts steps of the episode
-        done = e.ei[:, 0] > e.ep_len
-        e.rew_terms.zero_()
-        e.rew_terms[..., 0] = -0.01
-        e.rew_terms[e.collide, 0, 5] = -1.0
-        e.collide.zero_()
-        if done.any():                                    # auto-reset inside the "kernel"
-            e.stats_env[done, 11] += 1
-            e.stats_env[done, 12] = 2
-            e.af[done] = 0.0
-            e.ei[done, 0] = 0
-            e.ei[done, 3] += 1
-        obs = e.af[..., :e.D].reshape(self.num_agents, -1).clone()
-        rew = e.rew_terms[..., 0].reshape(-1).clone()
-        term = done.repeat_interleave(self.num_agents_per_env)
-        return obs, rew, term, torch.zeros_like(term), {}
+# ---- training wrappers: aggregate of finished episodes -> the reference's episode_extra_stats keys ----
+def test_stats_dict_names_and_means():
+    """training.stats_dict turns the device-side sums (QS_WA_*, csrc/qs_wrap.cuh) into the keys reward_shaping.py:86-108
+    and quadrotor_multi.py:626-718 produce, as means over the agent-episodes / env-episodes they cover."""
+    from quad_swarm_rl_b200 import _lib as L
+    from quad_swarm_rl_b200.training import stats_dict
+    W = L.WA
+    agg = np.zeros(L.QS_WRAP_AGG, np.float32)
+    agg[W['AGENT_EPISODES']], agg[W['ENV_EPISODES']] = 16, 2          # two envs of 8 drones finished
+    agg[W['TRUE_REWARD']] = -160.0
+    agg[W['RAW0'] + 0], agg[W['REW0'] + 0] = -32.0, -64.0             # pos, coefficient 2
+    agg[W['REW0'] + 6] = -1.6                                         # proximity
+    agg[W['RAW0'] + 7], agg[W['REW0'] + 7] = -4.0, -20.0              # obstacle collisions
+    agg[W['ACT_MEAN0'] + 2], agg[W['ACT_STD0'] + 1] = 1.6, 8.0
+    agg[W['ENV_STAT0'] + 0], agg[W['ENV_STAT0'] + 7] = 6, 3
+    agg[W['DIST0']] = 4.0
+    agg[W['SUCCESS']], agg[W['COL']] = 4, 8
+    agg[W['SCN0'] + 6 * 1: W['SCN0'] + 6 * 1 + 6] = [8, -40.0, -8.0, 1, 5, 2.0]       # o_random: one env
+    agg[W['SCN0'] + 6 * 11: W['SCN0'] + 6 * 11 + 6] = [8, -24.0, 0.0, 1, 1, 2.0]      # o_static_same_goal
+    agg[W['REPLAY_ENV_EPISODES']], agg[W['REPLAY_COLLISIONS']] = 2, 3
+    st = stats_dict(agg, use_obstacles=True, fallback_scenario='mix')
+    assert st['rewraw_main'] == -10.0 and st['rewraw_pos'] == -2.0 and st['rew_pos'] == -4.0 and st['rew_main'] == -4.0
+    assert st['rew_proximity'] == pytest.approx(-0.1) and st['rewraw_quadcol_obstacle'] == -0.25 and st['rew_quadcol_obstacle'] == -1.25
+    assert st['z_action2_mean'] == pytest.approx(0.1) and st['z_action1_std'] == 0.5
+    assert st['num_collisions'] == 3.0 and st['num_collisions_obst_quad'] == 1.5 and st['distance_to_goal_1s'] == 0.25
+    assert st['metric/agent_success_rate'] == 0.25 and st['metric/agent_col_rate'] == 0.5
+    assert st['Scenario_o_random/rew_pos'] == -5.0 and st['o_random/num_collisions'] == 5.0
+    assert st['Scenario_o_static_same_goal/rew_pos'] == -3.0 and st['num_collisions_replay'] == 1.5
+    no_obst = stats_dict(agg, use_obstacles=False, fallback_scenario='mix')
+    assert 'rew_quadcol_obstacle' not in no_obst and 'num_collisions_obst_quad' not in no_obst
 
 
-def test_batched_replay_logic_on_cpu_tensors():
-    """BatchedExperienceReplay (quad_experience_replay.py:66-209 per env, masked): checkpoint every 50 ticks, the
-    checkpoint from 3 checkpoints back is stored on a collision after the grace period, one event per 5 s, replay at the
-    episode end restores that state (tick, state rows, observation) while the RNG step counter keeps running."""
-    import torch
-    from quad_swarm_rl_b200.batched import BatchedExperienceReplay
-    env = _FakeBatchedEnv()
-    rp = BatchedExperienceReplay(env, replay_buffer_sample_prob=1.0, always_active=True, seed=1)
-    rp.reset()
-    E, N = env.num_envs, env.num_agents_per_env
-    a = torch.zeros((E * N, 4))
-    for t in range(1, 302):
-        if t == 120:
-            env.engine.collide[0] = True                  # before the grace period (tick <= 150): ignored
-        if t == 231:
-            env.engine.collide[1] = True                  # checkpoints at 50..200 exist -> stores the one of tick 100
-            env.engine.collide[2] = True
-        if t == 260:
-            env.engine.collide[1] = True                  # same episode again: already saved, ignored
-        obs, rew, term, trunc, infos = rp.step(a)
-    assert term.all() and rp.episode_counter == E
-    assert rp.buf_valid.sum(dim=0).tolist() == [0, 1, 1, 0, 0, 0]
-    assert rp.buf['env_i32'][0, 1, 0] == 100 and torch.all(rp.buf['agent_f32'][0, 1] == 100.0)
-    # envs 1 and 2 were replayed (p = 1): tick 100, state rows of tick 100, the stored observation; others start fresh
-    assert rp.tick.tolist() == [0, 100, 100, 0, 0, 0] and rp.replayed_events == 2
-    assert torch.all(env.engine.af[1] == 100.0) and torch.all(env.engine.af[0] == 0.0)
-    assert torch.all(obs.view(E, N, -1)[2] == 100.0) and torch.all(obs.view(E, N, -1)[3] == 0.0)
-    assert env.engine.ei[1, 1] == 301 and env.engine.ei[1, 0] == 100          # step counter kept, tick restored
-    assert rp.saved.tolist() == [False, True, True, False, False, False]
-    # replayed envs end after ep_len + 1 - 100 more steps, and then (p = 1) replay the same event again
-    for t in range(1, 202):
-        obs, rew, term, trunc, infos = rp.step(a)
-    d = term.view(E, N)[:, 0].tolist()
-    assert d == [False, True, True, False, False, False]
-    assert rp.buf_replayed[0, 1] == 2 and rp.tick.tolist() == [201, 100, 100, 201, 201, 201]
-    assert infos['replay']['replay/replay_rate'] == pytest.approx(4 / 8)
-
-
-def test_batched_reward_shaping_on_cpu_tensors():
-    import torch
-    from quad_swarm_rl_b200.batched import BatchedRewardShaping
-    env = _FakeBatchedEnv(E=3, N=2, ep_len=4)
-    w = BatchedRewardShaping(env, reward_shaping_scheme=dict(quad_rewards=dict(pos=2.0)),
-                             annealing=[wr.AnnealSchedule('quadcol_bin', 5.0, 100)])
-    w.training_info['approx_total_training_steps'] = 50
-    w.reset()
-    infos = {}
-    for t in range(5):
-        env.engine.collide[0] = (t == 2)
-        obs, rew, term, trunc, infos = w.step(torch.full((6, 4), 0.5))
-    st = infos['episode_extra_stats']
-    assert term.all() and env.engine.rew_coeff['quadcol_bin'] == 2.5 and st['z_anneal_quadcol_bin'] == 2.5
-    assert st['rewraw_pos'] == pytest.approx(-0.05) and st['rew_pos'] == pytest.approx(-0.10)       # coefficient 2.0
-    assert st['rewraw_quadcol'] == pytest.approx(-1.0 / 6)                                          # one drone of six, once
-    assert infos['true_reward'][0, 0].item() == pytest.approx(-0.05 - 1000.0)
-    assert st['z_action0_mean'] == pytest.approx(0.5) and st['z_action0_std'] == pytest.approx(0.0, abs=1e-6)
-    assert 'Scenario_static_same_goal/rew_pos' in st
