@@ -60,10 +60,15 @@ extern "C" {
 #define QS_SCENARIO_DYNAMIC_FORMATIONS 7
 #define QS_SCENARIO_EP_LISSAJOUS3D 8
 #define QS_SCENARIO_SWARM_VS_SWARM 9
-#define QS_SCENARIO_MIX 10                  /* use_obstacles = 0: one of 2..9 per episode; = 1: o_random or o_static_same_goal (mix.py:45-57) */
+#define QS_SCENARIO_MIX 10                  /* use_obstacles = 0: one of 2..9 and 12 per episode (scenarios/utils.py:7-16); = 1: o_random or
+                                               o_static_same_goal (mix.py:45-57, utils.py:18) */
 /* obstacles/o_static_same_goal.py: pillars and spawn cells as o_random, one common goal above the centre of the
  * largest free square of the pillar grid (o_base.py:123-153), approch_goal_metric 1.0.  Needs use_obstacles. */
 #define QS_SCENARIO_O_STATIC_SAME_GOAL 11
+/* scenarios/ep_rand_bezier.py: one common goal that follows quadratic Bezier segments, two control points re-drawn 5..10 m
+ * away every 5 s (and at tick 1) until both lie inside the room.  Obstacle-free family; part of `mix`. */
+#define QS_SCENARIO_EP_RAND_BEZIER 12
+#define QS_SCENARIO_LAST QS_SCENARIO_EP_RAND_BEZIER
 #define QS_SCENARIO_DEVICE_FAMILY_FIRST QS_SCENARIO_STATIC_SAME_GOAL
 
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a

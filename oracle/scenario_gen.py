@@ -121,10 +121,12 @@ class DeviceORandomSource:
 # ------------------------------------------------------------------------------------------------------------------
 STATIC_SAME_GOAL, STATIC_DIFF_GOAL, DYNAMIC_SAME_GOAL, DYNAMIC_DIFF_GOAL, SWAP_GOALS, DYNAMIC_FORMATIONS, \
     EP_LISSAJOUS3D, SWARM_VS_SWARM, MIX = range(2, 11)
+EP_RAND_BEZIER = 12
+SV_BEZIER, BEZIER_STEPS, BEZIER_MAX_TRIES = 64, 500, 512
 MODE_NAMES = {STATIC_SAME_GOAL: 'static_same_goal', STATIC_DIFF_GOAL: 'static_diff_goal',
               DYNAMIC_SAME_GOAL: 'dynamic_same_goal', DYNAMIC_DIFF_GOAL: 'dynamic_diff_goal', SWAP_GOALS: 'swap_goals',
               DYNAMIC_FORMATIONS: 'dynamic_formations', EP_LISSAJOUS3D: 'ep_lissajous3D',
-              SWARM_VS_SWARM: 'swarm_vs_swarm', MIX: 'mix'}
+              SWARM_VS_SWARM: 'swarm_vs_swarm', MIX: 'mix', EP_RAND_BEZIER: 'ep_rand_bezier'}
 MODE_IDS = {v: k for k, v in MODE_NAMES.items()}
 FORMATION_NAMES = ('circle_horizontal', 'circle_vertical_xz', 'circle_vertical_yz', 'sphere',
                    'grid_horizontal', 'grid_vertical_xz', 'grid_vertical_yz', 'cube')          # utils.py:24-25
@@ -198,7 +200,7 @@ def formation_point(f, n, k, size, c, layer_dist, per_layer):
 
 def pick_formation(draws, stream, mode, n):
     count, low, high = 8, 0.25, 0.5
-    if mode in (STATIC_SAME_GOAL, DYNAMIC_SAME_GOAL, EP_LISSAJOUS3D):
+    if mode in (STATIC_SAME_GOAL, DYNAMIC_SAME_GOAL, EP_LISSAJOUS3D, EP_RAND_BEZIER):
         count, low, high = 1, 0.0, 0.0
     elif mode == SWAP_GOALS:
         low, high = 0.4, 0.8
@@ -265,9 +267,10 @@ class DeviceScenarioSource:
         mode = self.cfg_mode
         if mode == MIX:
             if N == 1:
-                mode = (STATIC_SAME_GOAL, STATIC_DIFF_GOAL, EP_LISSAJOUS3D, DYNAMIC_SAME_GOAL)[_pk(d, STREAM_RESET, SV_MIX, 4)]
+                mode = (STATIC_SAME_GOAL, STATIC_DIFF_GOAL, EP_LISSAJOUS3D, EP_RAND_BEZIER, DYNAMIC_SAME_GOAL)[_pk(d, STREAM_RESET, SV_MIX, 5)]
             else:
-                mode = STATIC_SAME_GOAL + _pk(d, STREAM_RESET, SV_MIX, 8)
+                k = _pk(d, STREAM_RESET, SV_MIX, 9)
+                mode = STATIC_SAME_GOAL + k if k < 8 else EP_RAND_BEZIER
         svs = mode == SWARM_VS_SWARM
         fm = pick_formation(d, STREAM_RESET, mode, N // 2 if svs else N)
         s = dict(mode=mode, period=0, next=NEVER, growing=0, speed=0.0, f=fm['f'], size=fm['size'], layer=fm['layer'],
@@ -294,6 +297,10 @@ class DeviceScenarioSource:
         elif mode == EP_LISSAJOUS3D:
             s['c1'] = np.array([-2.0, 0.0, 2.0])
             s['period'], s['next'] = 1, 1
+            goals = np.tile(s['c1'], (N, 1))
+        elif mode == EP_RAND_BEZIER:
+            s['period'], s['next'] = 1, 1
+            s['size'], s['layer'], s['hi'] = 0.0, 0.0, 2.0          # P0 of the running segment lives in these three slots
             goals = np.tile(s['c1'], (N, 1))
         else:
             if mode == DYNAMIC_FORMATIONS:
@@ -335,6 +342,28 @@ class DeviceScenarioSource:
         elif mode == EP_LISSAJOUS3D:
             t = tick / CONTROL_FREQ
             g = np.tile(g[0] + np.array([0.03 * np.sin(t), 0.01 * np.sin(2 * t + 90), 0.01 * np.cos(2 * t + 90)]), (N, 1))
+        elif mode == EP_RAND_BEZIER:
+            t = tick % BEZIER_STEPS
+            g0 = np.array(g[0], dtype=np.float64)
+            if t == 0 or tick == 1:
+                hx, hy, hz = 5.0, 5.0, 10.0
+                p1 = p2 = g0
+                for k in range(BEZIER_MAX_TRIES):
+                    v0 = SV_BEZIER + 8 * k
+                    u = [-h + 2.0 * h * _u(d, STREAM_TICK, v0 + j) for j, h in enumerate((hx, hy, hz, hx, hy, hz))]
+                    dist = float(5 + _pk(d, STREAM_TICK, v0 + 6, 6))
+                    a, b = np.array([u[0], u[2], u[4]]), np.array([u[1], u[3], u[5]])
+                    p1 = g0 + a * (dist / np.sqrt(np.sum(a * a)))
+                    p2 = g0 + b * (dist / np.sqrt(np.sum(b * b)))
+                    lo, hi = np.array([-hx + 0.5, -hy + 0.5, 0.5]), np.array([hx - 0.5, hy - 0.5, hz - 0.5])
+                    if (p1 > lo).all() and (p1 < hi).all() and (p2 > lo).all() and (p2 < hi).all():
+                        break
+                s['size'], s['layer'], s['hi'] = float(g0[0]), float(g0[1]), float(g0[2])
+                s['c1'], s['c2'] = p1, p2
+            if t != 0 and tick > 1:
+                sp = t / (BEZIER_STEPS - 1)
+                p0 = np.array([s['size'], s['layer'], s['hi']])
+                g = np.tile((1 - sp) ** 2 * p0 + 2 * (1 - sp) * sp * s['c1'] + sp ** 2 * s['c2'], (N, 1))
         elif mode == SWARM_VS_SWARM:
             s['c1'], s['c2'] = s['c2'], s['c1']
             fm = pick_formation(d, STREAM_TICK, mode, N // 2)

@@ -23,8 +23,11 @@ namespace qs {
 // draw slots (v) inside a stream
 enum ScnSlot {
     SV_MIX = 0, SV_PERIOD = 1, SV_FORMATION = 2, SV_SIZE = 3, SV_LAYER = 4, SV_CX = 5, SV_CY = 6, SV_CZ = 7,
-    SV_DIST = 8, SV_PHI = 9, SV_THETA = 10, SV_GROW = 11, SV_SPEED = 12, SV_SHUFFLE = 16      // SV_SHUFFLE + drone index
+    SV_DIST = 8, SV_PHI = 9, SV_THETA = 10, SV_GROW = 11, SV_SPEED = 12, SV_SHUFFLE = 16,     // SV_SHUFFLE + drone index
+    SV_BEZIER = 64          // + 8 * try + j: six direction uniforms (j = 0..5) and the distance draw (j = 6) of a rejection try
 };
+constexpr int BEZIER_STEPS = 500;      // int(num_secs * control_freq), ep_rand_bezier.py:13-14
+constexpr int BEZIER_MAX_TRIES = 512;  // the reference re-draws until both control points lie in the room (acceptance ~5 %)
 constexpr int SCN_STREAM_RESET = 1, SCN_STREAM_TICK = 2;
 constexpr int SCN_NEVER = 0x7fffffff;
 constexpr float SCN_BOX = 2.0f;                    // scenario box of the obstacle-free family (base.py:18, quadrotor_multi.py:118)
@@ -126,7 +129,8 @@ __device__ V3 formation_point(int f, int n, int k, float size, V3 c, float layer
 __device__ Formation pick_formation(const RngKey& key, int stream, int mode, int n) {
     int count = 8;
     float low = 0.25f, high = 0.5f;                              // 5 / 10 nominal arm lengths (utils.py:31-51)
-    if (mode == QS_SCENARIO_STATIC_SAME_GOAL || mode == QS_SCENARIO_DYNAMIC_SAME_GOAL || mode == QS_SCENARIO_EP_LISSAJOUS3D) {
+    if (mode == QS_SCENARIO_STATIC_SAME_GOAL || mode == QS_SCENARIO_DYNAMIC_SAME_GOAL || mode == QS_SCENARIO_EP_LISSAJOUS3D ||
+        mode == QS_SCENARIO_EP_RAND_BEZIER) {
         count = 1; low = 0.f; high = 0.f;
     } else if (mode == QS_SCENARIO_SWAP_GOALS) {
         low = 0.4f; high = 0.8f;
@@ -233,13 +237,14 @@ __device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, i
     ScnState s;
     s.mode = cfg_mode;
     if (cfg_mode == QS_SCENARIO_MIX) {
-        // mix.py:59-63 draws uniformly from the mode list; the bezier entries are not available
+        // mix.py:59-63 draws uniformly from the mode list of scenarios/utils.py:7-16 (9 modes, 5 for a single drone)
         if (N == 1) {
-            const int m4[4] = {QS_SCENARIO_STATIC_SAME_GOAL, QS_SCENARIO_STATIC_DIFF_GOAL, QS_SCENARIO_EP_LISSAJOUS3D,
-                               QS_SCENARIO_DYNAMIC_SAME_GOAL};
-            s.mode = m4[scn_pick(key, SCN_STREAM_RESET, SV_MIX, 4)];
+            const int m5[5] = {QS_SCENARIO_STATIC_SAME_GOAL, QS_SCENARIO_STATIC_DIFF_GOAL, QS_SCENARIO_EP_LISSAJOUS3D,
+                               QS_SCENARIO_EP_RAND_BEZIER, QS_SCENARIO_DYNAMIC_SAME_GOAL};
+            s.mode = m5[scn_pick(key, SCN_STREAM_RESET, SV_MIX, 5)];
         } else {
-            s.mode = QS_SCENARIO_STATIC_SAME_GOAL + scn_pick(key, SCN_STREAM_RESET, SV_MIX, 8);
+            const int k = scn_pick(key, SCN_STREAM_RESET, SV_MIX, 9);
+            s.mode = k < 8 ? QS_SCENARIO_STATIC_SAME_GOAL + k : QS_SCENARIO_EP_RAND_BEZIER;
         }
     }
     s.period = 0; s.next = SCN_NEVER; s.growing = 0; s.speed = 0.f;
@@ -260,6 +265,12 @@ __device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, i
         s.c1.x = -2.0f; s.c1.y = 0.f; s.c1.z = 2.0f;
         s.period = 1; s.next = 1;
         o.goal = s.c1;                                                            // size 0, layer distance 0
+    } else if (s.mode == QS_SCENARIO_EP_RAND_BEZIER) {
+        // standard_reset with formation size 0: every goal sits on the centre (0, 0, 2); the curve is drawn at tick 1.
+        // (size, layer, hi) hold P0 and (c1, c2) the control points P1, P2 of the running segment.
+        s.period = 1; s.next = 1;
+        s.size = 0.f; s.layer = 0.f; s.hi = 2.0f;
+        o.goal = s.c1;
     } else {
         if (s.mode == QS_SCENARIO_DYNAMIC_FORMATIONS) {
             s.growing = scn_u24(key, SCN_STREAM_RESET, SV_GROW) < (1u << 23) ? 1 : 0;
@@ -316,6 +327,40 @@ __device__ __noinline__ ScnOut scenario_tick(RngKey key, int N, int i, int tick,
             o.goal.x = goal.x + 0.03f * sinf(t);
             o.goal.y = goal.y + 0.01f * sinf(2.0f * t + 90.0f);
             o.goal.z = goal.z + 0.01f * cosf(2.0f * t + 90.0f);
+        } else if (s.mode == QS_SCENARIO_EP_RAND_BEZIER) {
+            // ep_rand_bezier.py:7-50 with room_dims - formation_size = the room (formation size 0): two control points at
+            // distance d = randint(5, 11) in independent random directions from the current goal, re-drawn until both lie
+            // 0.5 m inside the box [-5, 5] x [-5, 5] x [0, 10] (the reference's loop has no bound; 512 tries fail with
+            // probability < 1e-10); then the goal follows B(s) = (1-s)^2 P0 + 2 (1-s) s P1 + s^2 P2, s = t / 499
+            const int t = tick % BEZIER_STEPS;
+            if (t == 0 || tick == 1) {
+                const float hx = 5.0f, hy = 5.0f, hz = 10.0f;
+                V3 p1 = goal, p2 = goal;
+#pragma unroll 1
+                for (int k = 0; k < BEZIER_MAX_TRIES; ++k) {
+                    const int v0 = SV_BEZIER + 8 * k;
+                    // uniform(low=-high, high=high, size=(2, 3)).reshape(3, 2): draws u0..u5 in order, column c takes
+                    // (u[c], u[2 + c], u[4 + c]) with ranges (x, y | z, x | y, z): the reference's reshape quirk is kept
+                    const float u0 = -hx + 2.f * hx * scn_u(key, SCN_STREAM_TICK, v0 + 0), u1 = -hy + 2.f * hy * scn_u(key, SCN_STREAM_TICK, v0 + 1),
+                                u2 = -hz + 2.f * hz * scn_u(key, SCN_STREAM_TICK, v0 + 2), u3 = -hx + 2.f * hx * scn_u(key, SCN_STREAM_TICK, v0 + 3),
+                                u4 = -hy + 2.f * hy * scn_u(key, SCN_STREAM_TICK, v0 + 4), u5 = -hz + 2.f * hz * scn_u(key, SCN_STREAM_TICK, v0 + 5);
+                    const float d = (float)(5 + scn_pick(key, SCN_STREAM_TICK, v0 + 6, 6));
+                    const float n1 = d / sqrtf(u0 * u0 + u2 * u2 + u4 * u4), n2 = d / sqrtf(u1 * u1 + u3 * u3 + u5 * u5);
+                    p1.x = goal.x + u0 * n1; p1.y = goal.y + u2 * n1; p1.z = goal.z + u4 * n1;
+                    p2.x = goal.x + u1 * n2; p2.y = goal.y + u3 * n2; p2.z = goal.z + u5 * n2;
+                    const bool ok = p1.x > -hx + 0.5f && p1.x < hx - 0.5f && p1.y > -hy + 0.5f && p1.y < hy - 0.5f && p1.z > 0.5f && p1.z < hz - 0.5f &&
+                                    p2.x > -hx + 0.5f && p2.x < hx - 0.5f && p2.y > -hy + 0.5f && p2.y < hy - 0.5f && p2.z > 0.5f && p2.z < hz - 0.5f;
+                    if (ok) break;
+                }
+                s.size = goal.x; s.layer = goal.y; s.hi = goal.z;
+                s.c1 = p1; s.c2 = p2;
+            }
+            if (t != 0 && tick > 1) {
+                const float sp = (float)t / (float)(BEZIER_STEPS - 1), a = (1.f - sp) * (1.f - sp), b = 2.f * (1.f - sp) * sp, c = sp * sp;
+                o.goal.x = a * s.size + b * s.c1.x + c * s.c2.x;
+                o.goal.y = a * s.layer + b * s.c1.y + c * s.c2.y;
+                o.goal.z = a * s.hi + b * s.c1.z + c * s.c2.z;
+            }
         } else if (s.mode == QS_SCENARIO_SWARM_VS_SWARM) {
             const V3 t = s.c1; s.c1 = s.c2; s.c2 = t;
             const Formation fm = pick_formation(key, SCN_STREAM_TICK, s.mode, N / 2);

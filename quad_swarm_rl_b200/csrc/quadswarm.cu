@@ -395,7 +395,8 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     }
     const int pdl_env = h->pdl_env;
     using KernelFn = void (*)(StepParams);
-    const bool scn = !p.use_obst && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && p.scenario <= QS_SCENARIO_MIX;
+    const bool scn = !p.use_obst && ((p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && p.scenario <= QS_SCENARIO_MIX) ||
+                                     p.scenario == QS_SCENARIO_EP_RAND_BEZIER);
     KernelFn fn_wait = nullptr, fn_ho = nullptr;
     int rc = dispatch_np(h->NP, [&](auto np) {
         constexpr int NPv = decltype(np)::value;
@@ -504,9 +505,10 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     if (K < 0 || K > cfg->num_agents - 1) return fail(QS_ERR_INVALID_ARG, "Incorrect number of neigbors");
     if (cfg->use_obstacles && cfg->num_obstacles < 1) return fail(QS_ERR_INVALID_ARG, "use_obstacles needs num_obstacles >= 1");
     if (cfg->ep_time <= 0.f) return fail(QS_ERR_INVALID_ARG, "ep_time must be positive");
-    if (cfg->scenario < QS_SCENARIO_HOST_TABLES || cfg->scenario > QS_SCENARIO_O_STATIC_SAME_GOAL)
+    if (cfg->scenario < QS_SCENARIO_HOST_TABLES || cfg->scenario > QS_SCENARIO_LAST)
         return fail(QS_ERR_INVALID_ARG, "unknown scenario");
-    if (cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->scenario < QS_SCENARIO_MIX && cfg->use_obstacles)
+    if (((cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->scenario < QS_SCENARIO_MIX) || cfg->scenario == QS_SCENARIO_EP_RAND_BEZIER) &&
+        cfg->use_obstacles)
         return fail(QS_ERR_INVALID_ARG, "the device-side goal-formation scenarios are obstacle-free (use_obstacles must be 0)");
     if ((cfg->scenario == QS_SCENARIO_O_STATIC_SAME_GOAL || cfg->scenario == QS_SCENARIO_O_RANDOM) && !cfg->use_obstacles)
         return fail(QS_ERR_INVALID_ARG, "scenarios o_random / o_static_same_goal need use_obstacles");

@@ -328,6 +328,50 @@ class Lissajous3D(Scenario):
         self.goals = np.array([self.goals[0] + d for _ in range(self.num_agents)])
 
 
+def bezier_points(nodes, s):
+    """Points of the Bezier curve with control points nodes[:, k] at parameters s (Bernstein form); the reference gets them
+    from the third-party `bezier` package (ep_rand_bezier.py:40-42)."""
+    from math import comb
+    nodes = np.asarray(nodes, dtype=np.float64)
+    n = nodes.shape[1] - 1
+    out = np.zeros((nodes.shape[0], len(s)))
+    for k in range(n + 1):
+        out += np.outer(nodes[:, k], comb(n, k) * (1.0 - s) ** (n - k) * s ** k)
+    return out
+
+
+class RandBezier(Scenario):
+    """ep_rand_bezier.py: all drones chase one goal that follows quadratic Bezier segments: every `num_secs` seconds (and at
+    tick 1) two control points are drawn 5..10 m away in random directions, re-drawn until both lie inside the room."""
+    mode = 'ep_rand_bezier'
+    dynamic = True
+    num_secs = 5
+    z_low, z_high, cap = 0.0, None, 30
+
+    def _bounds(self):
+        room = np.array(self.room_dims) - self.formation_size
+        zh = room[2] if self.z_high is None else self.z_high
+        return room, np.array([-room[0] / 2, -room[1] / 2, self.z_low]), np.array([room[0] / 2, room[1] / 2, zh])
+
+    def step(self, tick):
+        control_steps = int(self.num_secs * self.control_freq)
+        t = tick % control_steps
+        room, low, high = self._bounds()
+        max_dist = min(self.cap, max(room))
+        min_dist = max_dist / 2
+        if t == 0 or tick == 1:
+            while True:
+                new_pos = self.rng.uniform(low=-high, high=high, size=(2, 3)).reshape(3, 2)
+                new_pos = new_pos * self.rng.randint(min_dist, max_dist + 1) / np.linalg.norm(new_pos, axis=0)
+                new_pos = self.goals[0].reshape(3, 1) + new_pos
+                if (new_pos > low[:, None] + 0.5).all() and (new_pos < high[:, None] - 0.5).all():
+                    break
+            nodes = np.concatenate((self.goals[0].reshape(3, 1), new_pos), axis=1)
+            self.interp = bezier_points(nodes, np.linspace(0, 1, control_steps))
+        if t != 0 and tick > 1:
+            self.goals = np.array([self.interp[:, t] for _ in range(self.num_agents)])
+
+
 class RunAway(Scenario):
     """run_away.py: every second the goals of drones 0 and 1 jump onto the goals of two random other drones."""
     mode = 'run_away'
@@ -521,13 +565,12 @@ class OSwapGoals(_ObstacleScenario):
 
 
 SCENARIOS = {c.mode: c for c in (StaticSameGoal, StaticDiffGoal, DynamicSameGoal, DynamicDiffGoal, SwapGoals,
-                                  DynamicFormations, Lissajous3D, RunAway, SwarmVsSwarm, ORandom, OStaticSameGoal,
+                                  DynamicFormations, Lissajous3D, RandBezier, RunAway, SwarmVsSwarm, ORandom, OStaticSameGoal,
                                   ODynamicSameGoal, OSwapGoals)}
 
 
 class Mix(Scenario):
-    """mix.py:37-93: a fresh scenario drawn uniformly per episode.  The two bezier modes need the third-party
-    `bezier` package, which this image does not have; they are re-drawn (documented deviation)."""
+    """mix.py:37-93: a fresh scenario drawn uniformly per episode from the reference's mode lists (scenarios/utils.py:7-28)."""
     mode = 'mix'
     dynamic = True
 

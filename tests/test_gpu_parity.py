@@ -234,7 +234,7 @@ def test_device_side_obstacle_scenarios_match_twin(scenario):
 
 
 DEVICE_FAMILY = ['static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals',
-                 'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix']
+                 'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix', 'ep_rand_bezier']
 
 
 @pytest.mark.parametrize('mode', DEVICE_FAMILY)
@@ -244,7 +244,7 @@ def test_device_side_scenario_family_matches_twin(mode):
     included, compared every step — stays in parity across goal events and auto-resets."""
     from oracle.scenario_gen import DeviceScenarioSource
     from tests import parity_util as pu
-    periodic = mode in ('dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals', 'swarm_vs_swarm')
+    periodic = mode in ('dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals', 'swarm_vs_swarm', 'ep_rand_bezier')   # events at 4-6 s / every 5 s
     kw = dict(num_agents=8, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=3, ep_time=6.3 if periodic else 1.2)
     E = 3 if periodic else 4
     pair = pu.DevicePair(E, kw, 97531, mode, lambda: DeviceScenarioSource(mode))
@@ -255,7 +255,7 @@ def test_device_side_scenario_family_matches_twin(mode):
         assert all(o.source.events >= 1 for o in pair.oracles)
     es, _ = pair.engine.episode_stats()
     names = {int(x) for x in es[:, 12].cpu().numpy()}
-    assert names <= set(range(2, 10)) and (mode == 'mix' or names == {pu.L.DEVICE_SCENARIOS[mode]})
+    assert names <= (set(range(2, 10)) | {12}) and (mode == 'mix' or names == {pu.L.DEVICE_SCENARIOS[mode]})
     pair.engine.close()
 
 

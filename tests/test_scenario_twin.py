@@ -150,19 +150,19 @@ def BOX_DIST_OK(c1, c2):
 def test_mix_draws_every_available_scenario():
     seen = set()
     cfg = pc.cfg_to_oracle(dict(num_agents=4, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=0, ep_time=0.05))
-    for env_id in range(60):
+    for env_id in range(150):
         src = sg.DeviceScenarioSource('mix')
         env = qo.OracleEnv(cfg, qo.PhiloxRng(7), src, env_id=env_id)
         env.reset()
         seen.add(src.s['mode'])
-    assert seen == set(range(sg.STATIC_SAME_GOAL, sg.SWARM_VS_SWARM + 1))
+    assert seen == set(range(sg.STATIC_SAME_GOAL, sg.SWARM_VS_SWARM + 1)) | {sg.EP_RAND_BEZIER}      # the 9 modes of scenarios/utils.py:7-10
     single = set()
     cfg1 = pc.cfg_to_oracle(dict(num_agents=1, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=0, ep_time=0.05))
     for env_id in range(40):
         src = sg.DeviceScenarioSource('mix')
         qo.OracleEnv(cfg1, qo.PhiloxRng(7), src, env_id=env_id).reset()
         single.add(src.s['mode'])
-    assert single == {sg.STATIC_SAME_GOAL, sg.STATIC_DIFF_GOAL, sg.EP_LISSAJOUS3D, sg.DYNAMIC_SAME_GOAL}
+    assert single == {sg.STATIC_SAME_GOAL, sg.STATIC_DIFF_GOAL, sg.EP_LISSAJOUS3D, sg.EP_RAND_BEZIER, sg.DYNAMIC_SAME_GOAL}
 
 
 def test_largest_free_square_equals_host_generator():
@@ -208,3 +208,32 @@ def test_obstacle_twin_episode_semantics(scenario):
         for t in range(12):
             env.step(np.zeros((8, 4)))
     assert modes == ({sg.O_STATIC_SAME_GOAL} if scenario == 'o_static_same_goal' else {sg.O_RANDOM, sg.O_STATIC_SAME_GOAL})
+
+
+def test_device_bezier_twin_follows_the_host_scenario_semantics():
+    """oracle/scenario_gen.py's ep_rand_bezier (twin of the kernels') against the reference-pinned host class
+    (scenarios.RandBezier, replayed against the reference in test_oracle_vs_reference.py[ep_rand_bezier_3]): same schedule
+    (new segment at tick 1 and every 500 ticks, goal unchanged on those ticks), control points 5..10 m from the segment's
+    start and 0.5 m inside the room, and the quadratic Bernstein interpolation at s = t / 499."""
+    cfg = pc.cfg_to_oracle(dict(num_agents=3, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=2, ep_time=11.0))
+    src = sg.DeviceScenarioSource('ep_rand_bezier')
+    env = qo.OracleEnv(cfg, qo.PhiloxRng(11), src, env_id=3)
+    env.reset()
+    assert np.allclose(src.goals, [[0.0, 0.0, 2.0]] * 3)
+    prev = src.goals.copy()
+    for tick in range(1, 1010):
+        g = src.step(env, tick)
+        g = prev if g is None else g
+        s = src.s
+        p0, p1, p2 = np.array([s['size'], s['layer'], s['hi']]), np.asarray(s['c1']), np.asarray(s['c2'])
+        if tick == 1 or tick % 500 == 0:
+            assert np.allclose(g, prev) and np.allclose(p0, prev[0])                      # re-drawn, goal not moved
+            for q in (p1, p2):
+                d = np.linalg.norm(q - p0)
+                assert abs(d - round(d)) < 1e-9 and 5 <= round(d) <= 10
+                assert (q > [-4.5, -4.5, 0.5]).all() and (q < [4.5, 4.5, 9.5]).all()
+        else:
+            sp = (tick % 500) / 499.0
+            want = hs.bezier_points(np.stack([p0, p1, p2], 1), np.array([sp]))[:, 0]
+            assert np.allclose(g, np.tile(want, (3, 1)), atol=1e-12)
+        prev = np.array(g)
