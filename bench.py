@@ -563,10 +563,65 @@ def run_cuda_arm(args):
     os.environ['QS_ZERO_COPY'] = '0'
     e2e_copy_s = host_loop(n_e2e)
     os.environ.pop('QS_ZERO_COPY', None)
+    # the same envs as TWO halves stepped double-buffered (qs_step_host_async / qs_wait): the kernel of one half overlaps the
+    # PCIe traffic of the other, the way Sample Factory's double-buffered sampling would drive it
+    eng.close()
+    Eh = E // 2
+    halves = []
+    for gi in range(2):
+        e_ = QuadSwarmEngine(num_envs=Eh, seed=args.seed, device=local_rank, env_id_offset=rank * E + gi * Eh, rew_coeff=cfg['rew'],
+                             ep_time=args.ep_time, device_scenario=dev_scn, **kw)
+        if dev_scn is None:
+            goals, spawn, obst = make_episode_tables(cfg, Eh, seed=1000 + rank * 2 + gi)
+            e_.set_next_episode(goals, spawn, obst)
+        e_.reset()
+        halves.append(e_)
+
+    def pipe_loop(n):
+        sl = [slice(0, Eh), slice(Eh, 2 * Eh)]
+        for k in range(3):
+            for gi, e_ in enumerate(halves):
+                e_.step_host_async(a_host[k % 8, sl[gi]], obs_h[sl[gi]], rew_h[sl[gi]], done_h[sl[gi]])
+            for e_ in halves:
+                e_.wait()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        halves[0].step_host_async(a_host[0, sl[0]], obs_h[sl[0]], rew_h[sl[0]], done_h[sl[0]])
+        for k in range(n):
+            halves[1].step_host_async(a_host[k % 8, sl[1]], obs_h[sl[1]], rew_h[sl[1]], done_h[sl[1]])
+            halves[0].wait()                                    # A's observations are on the host: the policy would run here
+            if k + 1 < n:
+                halves[0].step_host_async(a_host[(k + 1) % 8, sl[0]], obs_h[sl[0]], rew_h[sl[0]], done_h[sl[0]])
+            halves[1].wait()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    pipe_s = pipe_loop(n_e2e)
+    os.environ['QS_ZERO_COPY'] = '0'
+    pipe_copy_s = pipe_loop(n_e2e)
+    os.environ.pop('QS_ZERO_COPY', None)
+    for e_ in halves:
+        e_.close()
+    # PCIe reference: one cudaMemcpyAsync of 64 MiB between page-locked host memory and the device, each direction
+    big_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    big_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    pcie = {}
+    for name, (dst, src) in (('d2h', (big_h, big_d)), ('h2d', (big_d, big_h))):
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dst.copy_(src, non_blocking=True); e1.record()
+            torch.cuda.synchronize()
+            best = max(best, (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        pcie[name] = best
+    del big_d, big_h
+    eng = None
     if world > 1:
-        t = torch.tensor([e2e_s, e2e_copy_s], device=dev)
+        t = torch.tensor([e2e_s, e2e_copy_s, pipe_s, pipe_copy_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_copy_s = float(t[0].item()), float(t[1].item())
+        e2e_s, e2e_copy_s, pipe_s, pipe_copy_s = [float(x) for x in t.tolist()]
 
     # ---- extras: they explain the headline, they are not the headline
     extra = {}
@@ -584,8 +639,15 @@ def run_cuda_arm(args):
             acts = (torch.rand((T, E, N, 4), device=dev, generator=g) * 2 - 1).contiguous()
             o = torch.empty((T, E, N, D), device=dev); r = torch.empty((T, E, N), device=dev)
             d_ = torch.empty((T, E, N), dtype=torch.uint8, device=dev)
-            eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_)
-            sec = _events(lambda: eng.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_), 8)
+            eng_r = QuadSwarmEngine(num_envs=E, seed=args.seed, device=local_rank, env_id_offset=rank * E, rew_coeff=cfg['rew'],
+                                    ep_time=args.ep_time, device_scenario=dev_scn, **kw)
+            if dev_scn is None:
+                goals, spawn, obst = make_episode_tables(cfg, E, seed=1000 + rank)
+                eng_r.set_next_episode(goals, spawn, obst)
+            eng_r.reset()
+            eng_r.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_)
+            sec = _events(lambda: eng_r.rollout(acts, obs_out=o, rewards_out=r, dones_out=d_), 8)
+            eng_r.close()
             extra['rollout'] = {'steps_per_launch': T, 'us_per_step': sec / T * 1e6, 'agent_steps_per_s': A * T / sec,
                                 'roofline_frac': main['b_alg'] * A * T / sec / 1e9 / main['peak'],
                                 'note': 'qs_rollout: T control steps per launch, all observations written'}
@@ -655,10 +717,18 @@ def run_cuda_arm(args):
             'e2e': {'value': world * A * n_e2e / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': A * 16,
                     'd2h_bytes_per_step': A * (4 * D + 4 + 1), 'steps': n_e2e,
                     'explicit_copies_value': world * A * n_e2e / e2e_copy_s,
+                    'pipelined_value': world * A * n_e2e / pipe_s, 'pipelined_explicit_copies_value': world * A * n_e2e / pipe_copy_s,
+                    'pcie_measured_gbs': pcie,
+                    'd2h_gbs_achieved': {'value': A * (4 * D + 4 + 1) * n_e2e / e2e_s / 1e9, 'pipelined': A * (4 * D + 4 + 1) * n_e2e / pipe_s / 1e9},
+                    'frac_of_pcie_d2h': {'value': A * (4 * D + 4 + 1) * n_e2e / e2e_s / 1e9 / pcie['d2h'],
+                                         'pipelined': A * (4 * D + 4 + 1) * n_e2e / pipe_s / 1e9 / pcie['d2h']},
                     'note': 'qs_step_host with page-locked numpy buffers, stream sync every step.  value: the kernel reads the '
                             'actions from and writes obs/rewards/dones to the mapped host buffers itself (zero-copy: the bytes '
                             'listed cross PCIe inside the timed region, no separate copy launches); explicit_copies_value: '
-                            'cudaMemcpyAsync H2D actions, step kernel, cudaMemcpyAsync D2H obs/rewards/dones (QS_ZERO_COPY=0)'},
+                            'cudaMemcpyAsync H2D actions, step kernel, cudaMemcpyAsync D2H obs/rewards/dones (QS_ZERO_COPY=0); '
+                            'pipelined_value: the envs as two halves with their own handles, qs_step_host_async / qs_wait, the kernel '
+                            'of one half overlapping the PCIe traffic of the other; pcie_measured_gbs: one 64 MiB cudaMemcpyAsync per '
+                            'direction on this box'},
             'gpu_launches': int(K),
             'roofline': {'bound': 'hbm', 'achieved': main['achieved'], 'peak': main['peak'], 'unit': 'GB/s', 'frac': main['frac'],
                          'traffic': measured_traffic(args.config) if E == cfg['E'] else None, 'peak_source': main['peak_src'],
@@ -668,7 +738,6 @@ def run_cuda_arm(args):
         }
         line.update(extra)
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

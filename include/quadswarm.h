@@ -183,6 +183,13 @@ int qs_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* reward
 int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
                  float* rew_terms_host);
 int qs_reset_host(QsHandle* h, const uint8_t* env_mask_host, float* obs_host);
+/* The same step without the final synchronisation (page-locked buffers only): the call returns once the work is enqueued on
+ * the handle's private stream; qs_wait blocks until the outputs are in the host buffers.  With two handles (two halves of
+ * the envs, double-buffered sampling as Sample Factory runs its rollout workers) the kernel of one half overlaps the
+ * PCIe transfer of the other:  A.async; B.async; A.wait -> policy on A's observations; B.wait -> ... */
+int qs_step_host_async(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                       float* rew_terms_host);
+int qs_wait(QsHandle* h);
 
 /* T consecutive control steps in ONE launch (persistent CTAs keep the env block in registers):
  * actions_dev [T,E,N,4], obs_dev [T,E,N,D] or, when last_obs_only != 0, [E,N,D]; rewards_dev [T,E,N];

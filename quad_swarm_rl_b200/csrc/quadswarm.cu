@@ -889,49 +889,82 @@ extern "C" int qs_rollout(QsHandle* h, int num_steps, const float* actions_dev, 
 #ifndef QS_ZERO_COPY_DEFAULT
 #define QS_ZERO_COPY_DEFAULT true          // measured on c3: 148 -> 134 us per host-buffer step (profiles/r01_notes.md)
 #endif
-// true when the host pointer is page-locked (cudaHostAlloc / cudaHostRegister): DMA can use it directly
-static bool is_pinned(const void* p) {
+// true when the host pointer is page-locked (cudaHostAlloc / cudaHostRegister): DMA can use it directly.  `dev` receives the
+// device alias of a mapped buffer (or null).  The last few answers are cached: a rollout worker passes the same buffers on
+// every step, and the two driver queries per buffer cost more host time than enqueueing the step.
+static bool is_pinned(const void* p, void** dev = nullptr) {
+    struct Entry { const void* p; bool pinned; void* dev; };
+    static thread_local Entry cache[16];
+    static thread_local int next = 0;
+    for (int k = 0; k < 16; ++k)
+        if (cache[k].p == p && p != nullptr) {
+            if (dev) *dev = cache[k].dev;
+            return cache[k].pinned;
+        }
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeHost;
+    bool pinned = false;
+    void* d = nullptr;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else pinned = at.type == cudaMemoryTypeHost;
+    if (pinned && cudaHostGetDevicePointer(&d, (void*)p, 0) != cudaSuccess) { cudaGetLastError(); d = nullptr; }
+    cache[next] = {p, pinned, d};
+    next = (next + 1) % 16;
+    if (dev) *dev = d;
+    return pinned;
 }
+
+static int step_host_impl(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                          float* rew_terms_host, bool sync);
 
 extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
                             float* rew_terms_host) {
+    return step_host_impl(h, actions_host, obs_host, rewards_host, dones_host, rew_terms_host, true);
+}
+
+extern "C" int qs_step_host_async(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                                  float* rew_terms_host) {
+    return step_host_impl(h, actions_host, obs_host, rewards_host, dones_host, rew_terms_host, false);
+}
+
+extern "C" int qs_wait(QsHandle* h) {
+    if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
+    QS_CUDA(cudaSetDevice(h->device));
+    QS_CUDA(cudaStreamSynchronize(h->own_stream));
+    return QS_OK;
+}
+
+static int step_host_impl(QsHandle* h, const float* actions_host, float* obs_host, float* rewards_host, uint8_t* dones_host,
+                          float* rew_terms_host, bool sync) {
     if (!h || !actions_host || !obs_host || !rewards_host || !dones_host) return fail(QS_ERR_INVALID_ARG, "null argument");
     QS_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->own_stream;
     join_caller_stream(h);
     const long long A = h->A;
     // pageable buffers go through the handle's pinned staging; page-locked caller buffers are used as they are
-    const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rewards_host), pd = is_pinned(dones_host),
-               pt = rew_terms_host && is_pinned(rew_terms_host);
+    void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
+    const bool pa = is_pinned(actions_host, &da), po = is_pinned(obs_host, &dob), pr = is_pinned(rewards_host, &dr),
+               pd = is_pinned(dones_host, &dd), pt = rew_terms_host && is_pinned(rew_terms_host, &dt);
+    if (!sync && !(pa && po && pr && pd && (!rew_terms_host || pt)))
+        return fail(QS_ERR_INVALID_ARG, "qs_step_host_async needs page-locked buffers (pageable ones would need a copy after the wait)");
     // Zero-copy path (all caller buffers page-locked and mapped): the kernel reads the actions from, and writes its
     // outputs straight to, host memory — coalesced 128-bit stores over PCIe overlap the transfer with the step and save
     // the four copy launches (QS_ZERO_COPY=0 falls back to explicit copies).
     const char* zc_env = getenv("QS_ZERO_COPY");          // read per call: bench.py times both paths in one process
     const bool zero_copy = zc_env ? atoi(zc_env) != 0 : QS_ZERO_COPY_DEFAULT;
     if (zero_copy && pa && po && pr && pd && (!rew_terms_host || pt)) {
-        void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
-        bool ok = cudaHostGetDevicePointer(&da, (void*)actions_host, 0) == cudaSuccess &&
-                  cudaHostGetDevicePointer(&dob, obs_host, 0) == cudaSuccess &&
-                  cudaHostGetDevicePointer(&dr, rewards_host, 0) == cudaSuccess &&
-                  cudaHostGetDevicePointer(&dd, dones_host, 0) == cudaSuccess &&
-                  (!rew_terms_host || cudaHostGetDevicePointer(&dt, rew_terms_host, 0) == cudaSuccess);
+        const bool ok = da && dob && dr && dd && (!rew_terms_host || dt);
+        static int zc_bulk = -1;                           // QS_ZC_BULK=1 (experiment): observation tiles leave through the bulk-copy engine
+        if (zc_bulk < 0) { const char* e = getenv("QS_ZC_BULK"); zc_bulk = e ? atoi(e) : 0; }
         if (ok) {
             StepParams p;
             fill_params(h, p);
             p.actions = (const float4*)da;
             p.obs = (float*)dob; p.rewards = (float*)dr; p.dones = (uint8_t*)dd; p.rew_terms = (float*)dt;
-            int rc0 = launch_step(h, p, s, /*obs_in_device_memory=*/false);
+            int rc0 = launch_step(h, p, s, /*obs_in_device_memory=*/zc_bulk != 0);
             if (rc0 != QS_OK) return rc0;
-            QS_CUDA(cudaStreamSynchronize(s));
+            if (sync) QS_CUDA(cudaStreamSynchronize(s));
             return QS_OK;
         }
-        cudaGetLastError();          // not mapped: use the copy path
     }
     const float* a_src = actions_host;
     if (!pa) { memcpy(h->h_actions, actions_host, sizeof(float) * 4 * A); a_src = h->h_actions; }
@@ -943,6 +976,7 @@ extern "C" int qs_step_host(QsHandle* h, const float* actions_host, float* obs_h
     QS_CUDA(cudaMemcpyAsync(pd ? dones_host : h->h_dones, h->d_dones, A, cudaMemcpyDeviceToHost, s));
     if (rew_terms_host)
         QS_CUDA(cudaMemcpyAsync(pt ? rew_terms_host : h->h_terms, h->d_terms, sizeof(float) * QS_NUM_TERMS * A, cudaMemcpyDeviceToHost, s));
+    if (!sync) return QS_OK;
     QS_CUDA(cudaStreamSynchronize(s));
     if (!po) memcpy(obs_host, h->h_obs, sizeof(float) * h->D * A);
     if (!pr) memcpy(rewards_host, h->h_rewards, sizeof(float) * A);

@@ -174,6 +174,16 @@ class QuadSwarmEngine:
                                       rewards_np.ctypes.data_as(C.c_void_p), dones_np.ctypes.data_as(C.c_void_p),
                                       terms_np.ctypes.data_as(C.c_void_p) if terms_np is not None else C.c_void_p(0)))
 
+    def step_host_async(self, actions_np, obs_np, rewards_np, dones_np, terms_np=None):
+        """step_host without the final synchronisation (page-locked buffers only); wait() completes it."""
+        self.push_reward_coeffs()
+        L.check(self.lib.qs_step_host_async(self.h, actions_np.ctypes.data_as(C.c_void_p), obs_np.ctypes.data_as(C.c_void_p),
+                                            rewards_np.ctypes.data_as(C.c_void_p), dones_np.ctypes.data_as(C.c_void_p),
+                                            terms_np.ctypes.data_as(C.c_void_p) if terms_np is not None else C.c_void_p(0)))
+
+    def wait(self):
+        L.check(self.lib.qs_wait(self.h))
+
     def reset_host(self, obs_np, env_mask_np=None):
         L.check(self.lib.qs_reset_host(self.h, env_mask_np.ctypes.data_as(C.c_void_p) if env_mask_np is not None else C.c_void_p(0),
                                        obs_np.ctypes.data_as(C.c_void_p)))
