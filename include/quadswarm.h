@@ -278,6 +278,10 @@ int qs_wrap_enable(QsHandle* h, const QsWrapConfig* cfg);
 /* one control step of the wrapped envs: qs_step, then the wrappers' bookkeeping for this step (rows of obs_dev of envs that
  * restart from a replayed event are overwritten with the event's observation, as ExperienceReplayWrapper.step returns it) */
 int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev, void* stream);
+/* the wrappers' kernel alone, on caller-supplied per-step inputs (what qs_step would have produced): actions_dev [E,N,4],
+ * rew_terms_dev [E,N,QS_NUM_TERMS], dones_dev [E,N]; obs_dev [E,N,D] as in qs_wrap_step.  For callers that step the envs
+ * themselves (qs_step with rew_terms_dev) and for parity tests against the reference's wrappers on recorded inputs. */
+int qs_wrap_apply(QsHandle* h, const float* actions_dev, const float* rew_terms_dev, float* obs_dev, const uint8_t* dones_dev, void* stream);
 /* sums over the episodes finished since the last read with reset != 0, layout QS_WA_* below; synchronises `stream`.
  * A mean statistic = its sum / the matching episode count (QS_WA_AGENT_EPISODES or QS_WA_ENV_EPISODES). */
 #define QS_WRAP_AGG 149

@@ -91,6 +91,7 @@ EXPORTS = {
     'qs_set_dynamics': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'qs_wrap_enable': (C.c_int, [C.c_void_p, C.POINTER(QsWrapConfig)]),
     'qs_wrap_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qs_wrap_apply': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_wrap_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'qs_wrap_true_reward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'qs_launch_count': (C.c_int64, [C.c_void_p]),

@@ -252,6 +252,15 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
 
     // ---- episode end: statistics of the finished episode (reward_shaping.py:80-118, quadrotor_multi.py:626-718) ----
     if (__any_sync(0xffffffffu, env_done)) {
+        // action sums of the whole env (all lanes of the warp take part in the shuffles)
+        float4 env_asum = valid ? asum : make_float4(0.f, 0.f, 0.f, 0.f), env_asq = valid ? asq : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = NP / 2; o > 0; o >>= 1) {
+            env_asum.x += __shfl_xor_sync(0xffffffffu, env_asum.x, o, NP); env_asum.y += __shfl_xor_sync(0xffffffffu, env_asum.y, o, NP);
+            env_asum.z += __shfl_xor_sync(0xffffffffu, env_asum.z, o, NP); env_asum.w += __shfl_xor_sync(0xffffffffu, env_asum.w, o, NP);
+            env_asq.x += __shfl_xor_sync(0xffffffffu, env_asq.x, o, NP); env_asq.y += __shfl_xor_sync(0xffffffffu, env_asq.y, o, NP);
+            env_asq.z += __shfl_xor_sync(0xffffffffu, env_asq.z, o, NP); env_asq.w += __shfl_xor_sync(0xffffffffu, env_asq.w, o, NP);
+        }
         if (env_done && valid) {
             const float true_reward = raw[QS_TERM_RAW_POS] + 1000.0f * raw[QS_TERM_RAW_QUADCOL];
             w.true_reward[a] = true_reward;
@@ -262,9 +271,11 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
                 agg_add(w.agg, WA_TRUE_REWARD, true_reward);
 #pragma unroll
                 for (int k = 0; k < QS_NUM_TERMS; ++k) { agg_add(w.agg, WA_RAW0 + k, raw[k]); agg_add(w.agg, WA_REW0 + k, rwd[k]); }
-                const float inv = 1.0f / (float)max(steps, 1);
-                const float am[4] = {asum.x * inv, asum.y * inv, asum.z * inv, asum.w * inv};
-                const float aq[4] = {asq.x * inv, asq.y * inv, asq.z * inv, asq.w * inv};
+                // z_action{k}_mean / _std: over ALL agents and steps of the env's episode jointly (reward_shaping.py:100-106
+                // transposes the [T, N, 4] action log to [4, N, T] and takes np.mean / np.std of each of the 4 slices)
+                const float inv = 1.0f / (float)(max(steps, 1) * p.N);
+                const float am[4] = {env_asum.x * inv, env_asum.y * inv, env_asum.z * inv, env_asum.w * inv};
+                const float aq[4] = {env_asq.x * inv, env_asq.y * inv, env_asq.z * inv, env_asq.w * inv};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     agg_add(w.agg, WA_ACT_MEAN0 + k, am[k]);

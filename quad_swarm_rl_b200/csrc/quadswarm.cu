@@ -717,10 +717,24 @@ extern "C" int qs_wrap_enable(QsHandle* h, const QsWrapConfig* cfg) {
     return QS_OK;
 }
 
+static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream);
+
 extern "C" int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev, void* stream) {
     if (!h || !h->wrap_on) return fail(QS_ERR_INVALID_ARG, "qs_wrap_enable first");
     int rc = qs_step(h, actions_dev, obs_dev, rewards_dev, dones_dev, h->d_terms, stream);
     if (rc != QS_OK) return rc;
+    return launch_wrap(h, actions_dev, h->d_terms, obs_dev, dones_dev, stream);
+}
+
+extern "C" int qs_wrap_apply(QsHandle* h, const float* actions_dev, const float* rew_terms_dev, float* obs_dev, const uint8_t* dones_dev,
+                             void* stream) {
+    if (!h || !h->wrap_on || !actions_dev || !rew_terms_dev || !obs_dev || !dones_dev) return fail(QS_ERR_INVALID_ARG, "null argument / wrappers not enabled");
+    if ((((uintptr_t)actions_dev | (uintptr_t)rew_terms_dev) & 15u) != 0) return fail(QS_ERR_INVALID_ARG, "actions / terms must be 16-byte aligned");
+    return launch_wrap(h, actions_dev, rew_terms_dev, obs_dev, (uint8_t*)dones_dev, stream);
+}
+
+static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream) {
+    int rc = QS_OK;
     static int probe = -1;                 // QS_WRAP_PROBE (tuning): 1 = skip the wrapper kernel, 2 = launch it without PDL
     if (probe < 0) { const char* e = getenv("QS_WRAP_PROBE"); probe = e ? atoi(e) : 0; }
     if (probe == 1) return QS_OK;
@@ -728,7 +742,7 @@ extern "C" int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_de
     fill_params(h, q.sp);
     q.w = h->wrap;
     q.actions = (const float4*)actions_dev;
-    q.terms = h->d_terms;
+    q.terms = terms_dev;
     q.dones = dones_dev;
     q.obs = obs_dev;
     const int kBlock = 128;

@@ -240,6 +240,12 @@ class QuadSwarmEngine:
         L.check(self.lib.qs_wrap_step(self.h, _ptr(actions), _ptr(obs), _ptr(rew), _ptr(done), self._stream()))
         return obs, rew, done
 
+    def wrap_apply(self, actions, terms, dones, obs=None):
+        """The wrappers' kernel alone on caller-supplied per-step inputs (include/quadswarm.h, qs_wrap_apply)."""
+        obs = self.obs if obs is None else obs
+        self.push_reward_coeffs()
+        L.check(self.lib.qs_wrap_apply(self.h, _ptr(actions), _ptr(terms), _ptr(obs), _ptr(dones), self._stream()))
+
     def wrap_read(self, reset=True):
         L.check(self.lib.qs_wrap_read(self.h, self._agg.ctypes.data_as(C.c_void_p), int(bool(reset)), self._stream()))
         return self._agg.copy()

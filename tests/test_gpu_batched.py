@@ -58,7 +58,9 @@ def test_reward_shaping_statistics_and_annealing():
     np.testing.assert_allclose(st['rewraw_main'], true_reward.mean().item(), rtol=1e-4)
     A = torch.stack(acts)
     np.testing.assert_allclose(st['z_action2_mean'], A[..., 2].mean().item(), atol=1e-5)
-    np.testing.assert_allclose(st['z_action1_std'], A[..., 1].std(dim=0, unbiased=False).mean().item(), rtol=1e-4)
+    # std over all agents and steps of an env's episode jointly (reward_shaping.py:100-106), then the mean over the envs
+    joint = A[..., 1].permute(1, 0, 2).reshape(E, -1).std(dim=1, unbiased=False).mean().item()
+    np.testing.assert_allclose(st['z_action1_std'], joint, rtol=1e-4)
     es, ags = twin.engine.episode_stats()
     np.testing.assert_allclose(st['num_collisions'], es[:, 0].float().mean().item(), rtol=1e-6)
     np.testing.assert_allclose(st['distance_to_goal_1s'], ags[..., 0].mean().item(), rtol=1e-5)
@@ -188,4 +190,86 @@ def test_single_env_factory_object_protocol():
     assert term.all() and not trunc.any()
     assert all('true_reward' in i and 'rew_pos' in i['episode_extra_stats'] for i in infos)
     assert any(k.startswith('Scenario_') for k in infos[0]['episode_extra_stats'])
+    env.close()
+
+
+# ---- the wrapper kernel against the reference's own wrappers (fixtures: tests/golden/wrappers.npz, oracle/gen_golden_wrappers.py) ----
+@pytest.mark.parametrize('case', [0, 1])
+def test_reward_shaping_kernel_reproduces_the_reference_wrapper(case, golden_dir):
+    """The UNMODIFIED QuadsRewardShapingWrapper was driven by a stand-in env with synthetic per-step reward dicts, actions
+    and dones; the same per-step inputs go through qs_wrap_apply here.  Per episode: every agent's true_reward, and the
+    episode_extra_stats keys as means over the agents (cumulative rew_* / rewraw_*, the joint action mean / std, the
+    per-scenario copies), with the coefficients (shaping scheme at the first step, annealing at episode ends) in force."""
+    import json, os
+    from quad_swarm_rl_b200 import _lib as L
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    from quad_swarm_rl_b200.training import stats_dict
+    g = np.load(os.path.join(golden_dir, 'wrappers.npz'))
+    terms, actions, dones, coeffs = (g[f'shaping{case}_{k}'] for k in ('terms', 'actions', 'dones', 'coeffs'))
+    episodes = json.loads(str(g[f'shaping{case}_episodes']))
+    T, N = terms.shape[:2]
+    eng = QuadSwarmEngine(num_envs=1, num_agents=N, neighbor_visible_num=min(2, N - 2), use_obstacles=True, obst_density=0.2, seed=1)
+    eng.wrap_enable(use_replay=False)
+    dev = eng.device
+    ep_iter = iter(episodes)
+    for t in range(T):
+        for k, name in enumerate(L.REW_KEYS):
+            eng.rew_coeff[name] = float(coeffs[t, k])
+        eng.wrap_apply(torch.tensor(actions[t], dtype=torch.float32, device=dev).view(1, N, 4).contiguous(),
+                       torch.tensor(terms[t], dtype=torch.float32, device=dev).view(1, N, 8).contiguous(),
+                       torch.full((1, N), int(dones[t]), dtype=torch.uint8, device=dev))
+        if dones[t]:
+            ref = next(ep_iter)
+            assert ref['t'] == t
+            agg = eng.wrap_read(reset=True)
+            st = stats_dict(agg, use_obstacles=True, fallback_scenario='static_same_goal')
+            tr = eng.wrap_true_reward().cpu().numpy().reshape(-1)
+            np.testing.assert_allclose(tr, ref['true_reward'], rtol=2e-5, atol=1e-5)
+            mean = lambda key: float(np.mean([s[key] for s in ref['stats']]))
+            for key in ('rewraw_main', 'rewraw_pos', 'rew_pos', 'rew_main', 'rewraw_action', 'rew_action', 'rewraw_crash', 'rew_crash',
+                        'rewraw_orient', 'rew_orient', 'rewraw_spin', 'rew_spin', 'rewraw_quadcol', 'rew_quadcol', 'rew_proximity',
+                        'rewraw_quadcol_obstacle', 'rew_quadcol_obstacle', 'z_action0_mean', 'z_action3_mean', 'z_action1_std', 'z_action2_std'):
+                np.testing.assert_allclose(st[key], mean(key), rtol=3e-5, atol=2e-6, err_msg=f'{key} episode ending at {t}')
+            np.testing.assert_allclose(st['Scenario_static_same_goal/rew_pos'], mean('Scenario_static_same_goal/rew_pos'), rtol=3e-5)
+            np.testing.assert_allclose(st['Scenario_static_same_goal/rew_crash'], mean('Scenario_static_same_goal/rew_crash'), rtol=3e-5, atol=2e-6)
+    eng.close()
+
+
+def test_replay_kernel_follows_the_reference_wrapper_schedule(golden_dir):
+    """The UNMODIFIED ExperienceReplayWrapper on a stand-in env with collisions at ticks 120 (grace period), 201, 260 (inside
+    the 5 s cooldown) and 720 stored the checkpoints of ticks 100 and 600 and started every later episode from one of them
+    (p = 1).  The same collisions are planted in a real env here: same stored checkpoints, same start ticks."""
+    import json, os
+    from quad_swarm_rl_b200 import _lib as L
+    from quad_swarm_rl_b200.training import BatchedTrainingEnv
+    ref = json.loads(str(np.load(os.path.join(golden_dir, 'wrappers.npz'))['replay']))
+    assert ref['stored_checkpoint_ticks'] == [100, 600] and set(ref['episode_start_ticks']) == {100, 600}
+    env = _env(num_envs=2, num_agents=2, ep_time=9.0, neighbor_visible_num=0, quads_mode='static_diff_goal', seed=11)
+    w = BatchedTrainingEnv(env, replay_buffer_sample_prob=1.0, replay_always_active=True, stats_every=1 << 30)
+    w.reset()
+    g = torch.Generator(device='cuda'); g.manual_seed(5)
+    hover = torch.zeros((4, 4), device='cuda') + 0.05
+    starts = []
+    for t in range(1, 4600):
+        tick_next = int(env.engine.get_state()['env_i32'][0, 0]) + 1
+        fresh = len(starts) == 0
+        if fresh and tick_next in ref['collision_ticks']:          # plant: drone 1 of env 0 onto drone 0, as the stand-in env did
+            st = env.engine.get_state()
+            st['agent_f32'][0, 1, 0:3] = st['agent_f32'][0, 0, 0:3] + 0.01
+            st['agent_f32'][0, :, 3:6] = 0
+            env.engine.set_state(st, env_mask=torch.tensor([1, 0], dtype=torch.uint8, device='cuda'))
+        elif fresh and tick_next - 1 in ref['collision_ticks']:    # and apart again, so that the next planted contact is a new one
+            st = env.engine.get_state()
+            st['agent_f32'][0, 1, 0:3] = st['agent_f32'][0, 0, 0:3] + torch.tensor([0.6, 0.0, 0.0], device='cuda')
+            st['agent_f32'][0, :, 3:6] = 0
+            env.engine.set_state(st, env_mask=torch.tensor([1, 0], dtype=torch.uint8, device='cuda'))
+        obs, rew, term, trunc, infos = w.step(hover + 0.02 * (torch.rand((4, 4), device='cuda', generator=g) * 2 - 1))
+        if bool(term[0]):
+            starts.append(int(env.engine.get_state()['env_i32'][0, 0]))
+            if len(starts) == 1:
+                agg = env.engine.wrap_read(reset=False)
+                assert agg[L.WA['EVENTS_STORED']] == 2, agg[L.WA['EVENTS_STORED']]        # 201 and 720; 120 and 260 ignored
+            if len(starts) == len(ref['episode_start_ticks']):
+                break
+    assert len(starts) == len(ref["episode_start_ticks"]) and set(starts) <= {100, 600}, starts
     env.close()
