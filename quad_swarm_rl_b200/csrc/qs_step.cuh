@@ -553,6 +553,11 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     Agent s;
     EnvCtr ctr = {0, 0, 0, 0};
     if (valid && role == 0) load_agent<HO>(st, a, s);      // state loads are issued before the pillar staging barrier
+    // running sums of the goal distance over the last 1 / 3 / 5 s of the episode: loaded with the state (an env in its last
+    // 5 s — a third of all envs when they run out of phase — would otherwise pay a dependent L2 round trip mid-step)
+    float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool dsum_dirty = false;
+    if (valid && role == 0) dsum = ld_state<HO>(st.slots + SL_DIST_SUMS * st.a_pad + a);
     Phys ph;
     if (DYN) load_phys(st.dyn, valid ? a : 0, ph);
     // env-level words: issued together with the state loads, BEFORE the pillar staging below waits for its own loads (one
@@ -566,7 +571,6 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         prefetch_l2(st.epi + env);
         prefetch_l2(st.next_goal + a);
         prefetch_l2(st.next_spawn + a);
-        prefetch_l2(st.slots + SL_DIST_SUMS * st.a_pad + a);
         prefetch_l2(st.slots + SL_STALE_VEL * st.a_pad + a);
         if (i == 0) {
             prefetch_l2(st.env_cnt + (long long)env * QS_NUM_ENV_STATS);
@@ -911,11 +915,10 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
             const int len = p.ep_len + 1;
             const int w5 = min(len, 500);
             if (valid && ctr.tick > len - w5) {
-                float4 sums = ld_state<HO>(st.slots + SL_DIST_SUMS * st.a_pad + a);
-                if (ctr.tick > len - min(len, 100)) sums.x += dist;
-                if (ctr.tick > len - min(len, 300)) sums.y += dist;
-                sums.z += dist;
-                st.slots[SL_DIST_SUMS * st.a_pad + a] = sums;
+                if (ctr.tick > len - min(len, 100)) dsum.x += dist;
+                if (ctr.tick > len - min(len, 300)) dsum.y += dist;
+                dsum.z += dist;
+                dsum_dirty = true;
             }
         }
 
@@ -1022,7 +1025,9 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         if (__any_sync(0xffffffffu, do_reset)) {          // warp-uniform branch
             QS_TL(9);
             if (do_reset && valid) {
-                const float4 sums = QS_LD(st.slots + SL_DIST_SUMS * st.a_pad + a);
+                const float4 sums = dsum;
+                dsum = make_float4(0.f, 0.f, 0.f, 0.f);           // reset_env zeroes the slot
+                dsum_dirty = false;
                 const int len = p.ep_len + 1;
                 const uint32_t fbits = ((s.flags & QS_FLAG_NO_COL_AGENT) ? 1u : 0u) | ((s.flags & QS_FLAG_NO_COL_OBST) ? 2u : 0u) |
                                        ((s.flags & QS_FLAG_REACHED_GOAL) ? 4u : 0u);
@@ -1122,6 +1127,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
     QS_TL(6);
     if (valid) store_agent(st, a, s, goal_dirty);
+    if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
     if (!SPLIT && p.obs_bulk) bulk_drain();           // shared memory must outlive the bulk copy's reads
     if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
     if (HO) {

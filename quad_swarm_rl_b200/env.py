@@ -85,12 +85,11 @@ class _EnvBase:
                  dyn_sampler_1, sense_noise, init_random_state, render_mode='human', device=0, seed=None,
                  env_id_offset=0, device_scenario=None):
         # the env factory's fixed choices (swarm_rl/env_wrappers/quad_utils.py:22-31) are the only supported ones
-        if dynamics_params != 'Crazyflie':
-            raise NotImplementedError("only the Crazyflie parameter set is built into the CUDA kernels")
+        from .quad_models import SAMPLERS
+        if isinstance(dynamics_params, str) and dynamics_params not in SAMPLERS:
+            raise AttributeError(f"module 'quadrotor_randomization' has no attribute {dynamics_params!r}")     # getattr(quad_rand, name)
         if not (raw_control and raw_control_zero_middle):
             raise NotImplementedError("only RawControl with zero_action_middle is supported")
-        if dynamics_randomize_every is not None or dyn_sampler_1 is not None:
-            raise NotImplementedError("dynamics randomisation is not supported (SURVEY.md §8f-4)")
         if init_random_state:
             raise NotImplementedError("init_random_state=True is not supported")
         if quads_render:
@@ -138,16 +137,36 @@ class _EnvBase:
             seed = int(np.random.SeedSequence().entropy % (2 ** 62))
         self.seed_value = seed
         self._host_rng = np.random.RandomState(seed % (2 ** 32))
+        # physical model of every drone (quadrotor_single.py:186-211): the Crazyflie constants compiled into the kernels, or one
+        # dynamics source per drone (parameter set -> dynamics_change -> samplers -> limits -> derived constants) whose rows
+        # are uploaded with qs_set_dynamics; `dynamics_randomize_every` resamples them every that many episodes
+        factory_change = dict(noise=dict(thrust_noise_ratio=0.05), damp=dict(vel=0, omega_quadratic=0))      # quad_utils.py:31
+        self.dynamics_randomize_every = dynamics_randomize_every
+        self._dyn_sources = None
+        quad_arm = 0.0
+        if dynamics_params != 'Crazyflie' or dyn_sampler_1 is not None or dynamics_randomize_every is not None or \
+                (dynamics_change is not None and dynamics_change != factory_change):
+            from .quad_models import DynamicsSource, DYN_FIELDS
+            self._dyn_sources = [DynamicsSource(dynamics_params, dynamics_change, dyn_sampler_1, rs=self._host_rng)
+                                 for _ in range(self.num_envs * num_agents)]
+            self._dyn_rows = np.stack([src.sample_row() for src in self._dyn_sources]).reshape(self.num_envs, num_agents, -1)
+            quad_arm = float(self._dyn_rows[0, 0, DYN_FIELDS.index('arm')])          # quadrotor_multi.py:81: envs[0].dynamics.arm
+            self.quad_arm = quad_arm
+            self.collision_threshold = collision_hitbox_radius * quad_arm
+            self.collision_falloff_threshold = collision_falloff_radius * quad_arm
+        self._traj_count = np.zeros(self.num_envs, np.int64)
         self.engine = QuadSwarmEngine(
             num_envs=self.num_envs, num_agents=num_agents, obs_repr=obs_repr, neighbor_visible_num=neighbor_visible_num,
             neighbor_obs_type=neighbor_obs_type, use_obstacles=use_obstacles, obst_density=obst_density,
             obst_size=obst_size, obst_spawn_area=obst_spawn_area, use_downwash=use_downwash, room_dims=room_dims,
             ep_time=ep_time, collision_hitbox_radius=collision_hitbox_radius,
             collision_falloff_radius=collision_falloff_radius, sense_noise=sense_noise, rew_coeff=rew_coeff,
-            seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario,
+            seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario, quad_arm=quad_arm,
             # scenario.approch_goal_metric (o_base.py:16: 1.0 for the goal-sharing obstacle scenarios, else 0.5); with the
             # host-side `mix` over obstacle scenarios the value of o_random is used for every episode
             approch_goal_metric=1.0 if quads_mode in ('o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals') else 0.5)
+        if self._dyn_sources is not None:
+            self.engine.set_dynamics(self._dyn_rows)
         self.device_scenario = device_scenario
         self.rew_coeff = self.engine.rew_coeff               # the live, mutable dict (reward_shaping.py:55-61 writes it)
         self.ep_len = self.engine.ep_len
@@ -199,6 +218,8 @@ class _EnvBase:
             self.crashes_in_recent_episodes.append(self.crashes_last_episode)
             self.activate_replay_buffer = self.can_drones_fly()
             self.crashes_last_episode = 0
+        self._traj_count[list(envs)] += 1
+        self.resample_dynamics(list(envs))            # constants for the reset that will END the episode starting now
         if self.device_scenario is not None:          # episodes are generated inside the kernels: only the tick restarts
             self._tick[list(envs)] = 0
             return
@@ -422,6 +443,25 @@ class QuadrotorEnvMulti(_EnvBase):
         self.saved_in_replay_buffer = snap['saved_in_replay_buffer']
 
 
+def _resample_dynamics(self, env_ids):
+    """QuadrotorSingle._reset, quadrotor_single.py:387-390: every `dynamics_randomize_every`-th episode of an env its drones get
+    freshly sampled constants; they are uploaded now and latched by the env's (auto-)reset (qs_set_dynamics, at_next_reset)."""
+    if self._dyn_sources is None or self.dynamics_randomize_every is None:
+        return
+    N = self.num_agents_per_env
+    mask = np.zeros(self.num_envs, np.uint8)
+    for e in env_ids:
+        if (self._traj_count[e] + 1) % self.dynamics_randomize_every == 0:
+            for i in range(N):
+                self._dyn_rows[e, i] = self._dyn_sources[e * N + i].sample_row()
+            mask[e] = 1
+    if mask.any():
+        self.engine.set_dynamics(self._dyn_rows, env_mask=mask, at_next_reset=True)
+
+
+_EnvBase.resample_dynamics = _resample_dynamics
+
+
 class QuadrotorEnvMultiBatched(_EnvBase):
     """E independent envs behind one object for a batched sampler: `num_agents = E * N`; device tensors in and out
     (gymnasium 5-tuple step API, terminated = dones, truncated all False as in swarm_rl/env_wrappers/compatibility.py)."""
@@ -431,7 +471,8 @@ class QuadrotorEnvMultiBatched(_EnvBase):
                  collision_falloff_radius=4.0, use_obstacles=False, obst_density=0.2, obst_size=0.6,
                  obst_spawn_area=(8.0, 8.0), use_downwash=False, quads_mode='static_same_goal',
                  room_dims=(10., 10., 10.), sense_noise='default', device=0, seed=None, env_id_offset=0,
-                 device_scenarios=True):
+                 device_scenarios=True, dynamics_params='Crazyflie', dynamics_randomize_every=None, dynamics_change=None,
+                 dyn_sampler_1=None):
         # device-side generators (no host work per episode or per tick): o_random with obstacles, the goal-formation
         # family and mix without; every other mode uses host tables
         dev_scn = None
@@ -441,8 +482,8 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         super().__init__(num_envs, num_agents, ep_time, rew_coeff, obs_repr, neighbor_visible_num, neighbor_obs_type,
                          collision_hitbox_radius, collision_falloff_radius, use_obstacles, obst_density, obst_size,
                          obst_spawn_area, use_downwash, True, quads_mode, room_dims, False, ['topdown'], False,
-                         'Crazyflie', True, True, None, None, None, sense_noise, False, device=device, seed=seed,
-                         env_id_offset=env_id_offset, device_scenario=dev_scn)
+                         dynamics_params, True, True, dynamics_randomize_every, dynamics_change, dyn_sampler_1, sense_noise, False,
+                         device=device, seed=seed, env_id_offset=env_id_offset, device_scenario=dev_scn)
         self.num_agents = num_envs * num_agents
         self._truncated = torch.zeros(self.num_agents, dtype=torch.bool, device=self.engine.device)
 
@@ -459,6 +500,14 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         else:
             obs, rew, done = self.engine.step(a.contiguous(), with_terms=with_terms)
         if self.device_scenario is not None:           # nothing to do on the host: episodes and goal events live in the kernels
+            if self._dyn_sources is not None and self.dynamics_randomize_every is not None:
+                # dynamics randomisation without reading `dones` back: envs that never left lock-step end their episodes every
+                # ep_len + 1 steps; replayed episodes (training.BatchedTrainingEnv) just latch the pending constants later
+                self._steps_since_upload = getattr(self, '_steps_since_upload', 0) + 1
+                if self._steps_since_upload >= self.ep_len + 1:
+                    self._steps_since_upload = 0
+                    self._traj_count += 1
+                    self.resample_dynamics(range(self.num_envs))
             return obs.view(self.num_agents, -1), rew.view(-1), done.view(-1).bool(), self._truncated, {}
         self._tick += 1
         finished = np.nonzero(self._tick > self.ep_len)[0]           # lock-step episodes: known on the host without a sync

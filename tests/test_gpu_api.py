@@ -366,3 +366,29 @@ def test_env_snapshot_restore():
     assert d.max() > 0 and d[:, :3].max() < 0.05 and d[:, 6:15].max() < 0.01 and d.max() < 1.0, d.max()   # fresh OU / sensor noise only
     env.close()
 
+
+
+def test_env_objects_with_other_physical_models():
+    """dynamics_params / dyn_sampler_1 / dynamics_randomize_every of the reference's constructor (quadrotor_single.py:99-211):
+    the env objects sample one airframe per drone on the host (quad_models.py, pinned to the reference) and upload the
+    constants; resampled constants are latched by the env's next auto-reset."""
+    from quad_swarm_rl_b200.env import QuadrotorEnvMultiBatched
+    from quad_swarm_rl_b200.quad_models import DYN_FIELDS
+    env = QuadrotorEnvMultiBatched(num_envs=6, num_agents=4, ep_time=0.3, neighbor_visible_num=2, quads_mode='static_diff_goal', seed=9,
+                                   dynamics_params='RandomQuad', dynamics_randomize_every=1,
+                                   dyn_sampler_1={'class': 'RelativeSampler', 'noise_ratio': 0.05, 'sampler': 'normal'})
+    rows0 = env._dyn_rows.copy()
+    assert len(np.unique(rows0[..., DYN_FIELDS.index('mass')])) == 24               # every drone its own airframe
+    assert env.quad_arm == pytest.approx(float(rows0[0, 0, DYN_FIELDS.index('arm')]))
+    obs, _ = env.reset()
+    for t in range(70):
+        obs, rew, term, trunc, _ = env.step(torch.rand((24, 4), device='cuda') * 2 - 1)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert not np.array_equal(env._dyn_rows, rows0)                                  # resampled after the first episode
+    env.close()
+    single = _ref_style_env(dynamics_params='DefaultQuad', ep_time=0.3)
+    single.reset()
+    for t in range(35):
+        o, r, d, i = single.step(np.random.RandomState(t).uniform(-1, 1, (8, 4)).astype(np.float32))
+    assert np.isfinite(o).all() and single.quad_arm == pytest.approx(0.12 * 2 ** 0.5)
+    single.close()
