@@ -50,11 +50,14 @@ CONFIGS = {
 def measured_traffic(config):
     """dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per launch, from the committed ncu --set full
     capture of this workload (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    try:
-        return json.load(open(p)).get(config, {}).get('dram_bytes_per_launch')
-    except Exception:
-        return None
+    for name in ('r02_traffic.json', 'r01_traffic.json'):
+        try:
+            v = json.load(open(os.path.join(ROOT, 'profiles', name))).get(config, {}).get('dram_bytes_per_launch')
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def hbm_peak():

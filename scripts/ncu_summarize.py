@@ -26,7 +26,7 @@ def tobytes(u, v):
     v = float(v.replace(',', ''))
     return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
 traffic = tobytes(*d['dram__bytes_read.sum']) + tobytes(*d['dram__bytes_write.sum'])
-tj = 'profiles/r01_traffic.json'
+tj = 'profiles/r02_traffic.json'
 t = json.load(open(tj)) if os.path.exists(tj) else {}
 t[cfg] = {'dram_bytes_per_launch': traffic, 'source': f'profiles/{tag}_ncu_full_{cfg}.txt (ncu --set full, cache control all: cold caches)'}
 json.dump(t, open(tj, 'w'), indent=1, sort_keys=True)
