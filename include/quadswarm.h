@@ -34,6 +34,7 @@ extern "C" {
 #define QS_ERR_CUDA (-3)
 
 #define QS_MAX_AGENTS 32
+#define QS_MAX_OBST_CHOICES 16
 
 /* obs_repr: quad_utils.py:30-34 (QUADS_OBS_REPR) */
 #define QS_OBS_XYZ_VXYZ_R_OMEGA 0       /* 18 floats */
@@ -228,6 +229,15 @@ int qs_set_state(QsHandle* h, const uint8_t* env_mask_dev, const float* agent_f3
  * (quadrotor_multi.py:81,154-155). */
 #define QS_DYN_ROW 40
 int qs_set_dynamics(QsHandle* h, const uint8_t* env_mask_dev, const float* rows_dev, int at_next_reset, void* stream);
+
+/* Per-episode pillar density / size randomisation — replaces ExperienceReplayWrapper's domain randomisation
+ * (gym_art/quadrotor_multi/quad_experience_replay.py:76-88,108-118,196-205: np.random.choice over np.arange(min, max, step))
+ * and QuadrotorEnvMulti.reset(obst_density, obst_size) (quadrotor_multi.py:339-351).  densities_host [n_densities] and
+ * sizes_host [n_sizes] (pillar diameters) are the choice lists; every (auto-)reset of an env draws one of each, places
+ * int(density * area) pillars (at most QsConfig.num_obstacles, the table size) and uses size / 2 as the pillar radius for the
+ * collision test, the contact response and the 3x3 distance patch of that episode.  Needs a device-side obstacle scenario.
+ * n_densities = n_sizes = 0 switches the randomisation off. */
+int qs_set_obstacle_randomization(QsHandle* h, const float* densities_host, int n_densities, const float* sizes_host, int n_sizes);
 
 /* flag bits in agent_u32[.,0] */
 #define QS_FLAG_ON_FLOOR (1u << 0)

@@ -82,7 +82,9 @@ class DeviceORandomSource:
     """Episode source for OracleEnv that mirrors the device-side obstacle scenarios (needs a PhiloxRng):
     QS_SCENARIO_O_RANDOM (default), QS_SCENARIO_O_STATIC_SAME_GOAL, or QS_SCENARIO_MIX over the two."""
 
-    def __init__(self, L=8, W=8, scenario=O_RANDOM):
+    def __init__(self, L=8, W=8, scenario=O_RANDOM, densities=None, sizes=None):
+        # densities / sizes: the choice lists of the per-episode randomisation (qs_set_obstacle_randomization), or None
+        self.densities, self.sizes = densities, sizes
         self.L, self.W = L, W
         self.scenario = {'o_random': O_RANDOM, 'mix': O_MIX, 'o_static_same_goal': O_STATIC_SAME_GOAL}.get(scenario, scenario)
         self.mode = O_RANDOM if self.scenario == O_MIX else self.scenario
@@ -96,7 +98,13 @@ class DeviceORandomSource:
 
     def reset(self, env):
         d = env.rng.episode_draws
-        goals, spawn, obst = o_random_episode(d, env.num_agents, env.cfg.num_obstacles, self.L, self.W)
+        M = env.cfg.num_obstacles
+        if self.densities is not None:
+            # int(density * area) pillars (quadrotor_multi.py:128), the float32 list entry as the kernels hold it
+            M = int(float(np.float32(self.densities[_pick(d, 322, len(self.densities))])) * self.L * self.W)
+            env.obst_size = 2.0 * float(np.float32(0.5 * np.float32(self.sizes[_pick(d, 323, len(self.sizes))])))
+        self.num_pillars = M
+        goals, spawn, obst = o_random_episode(d, env.num_agents, M, self.L, self.W)
         if self.scenario == O_MIX:
             self.mode = O_RANDOM if _pick(d, 321, 2) == 0 else O_STATIC_SAME_GOAL
         if self.mode == O_STATIC_SAME_GOAL:

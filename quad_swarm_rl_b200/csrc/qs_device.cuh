@@ -120,6 +120,11 @@ struct StepParams {
     unsigned long long* tl;             // debug build only: [64 slots][4096 blocks][8] %globaltimer stamps of warp 0 of every block
     int tl_slot;
 #endif
+    // per-episode pillar density / size randomisation (qs_set_obstacle_randomization): the number of pillars and their radius
+    // are drawn per env at every reset from these lists; the env's values live in scn_f[3 env].xy (radius, count)
+    int obst_random, n_obst_counts, n_obst_radii;
+    int obst_counts[QS_MAX_OBST_CHOICES];
+    float obst_radii[QS_MAX_OBST_CHOICES];
     int chained;                        // 1: the stream predecessor of this launch is a step grid of the same handle (qs_set_chained):
                                         //    actions are prefetched before the dependency wait; hand-over kernels skip the grid-wide wait
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
@@ -824,8 +829,15 @@ __device__ __noinline__ int largest_free_square_cell(unsigned long long mask, in
 // The draws are the keyed values scenario_u(key, v) (one Philox block serves four consecutive v: it is computed once
 // per four picks here, not once per pick).
 __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario, int i, int n_agents, int M, int L, int W, int lane_i,
-                                                        int stride, float2* obst_smem, float2* obst_glob) {
+                                                        int stride, float2* obst_smem, float2* obst_glob, int M_table) {
     const int cells = L * W;
+    // the table keeps M_table slots; with fewer pillars this episode (density randomisation) the rest stand far outside
+    // the room, where no test or distance can see them
+    for (int m = M + lane_i; m < M_table; m += stride) {
+        const float2 far = make_float2(1.0e4f, 1.0e4f);
+        if (obst_smem != nullptr) obst_smem[m] = far;
+        obst_glob[m] = far;
+    }
     unsigned long long mask = 0ull;
     float4 ub = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1

@@ -61,7 +61,7 @@ __device__ __forceinline__ float nbv(float mine, const float* hand, int arr, int
 template <int NP, bool SM = false>
 __device__ __forceinline__ void write_observation(const StepParams& p, const Agent& s, const float nvel[3], const Noise9& nz,
                                                   int i, bool valid, const float2* s_obst_env, float dmin2,
-                                                  float* __restrict__ row, const float* hand = nullptr, int gbase = 0) {
+                                                  float* __restrict__ row, float obst_r, const float* hand = nullptr, int gbase = 0) {
     // ---- self observation
     {
         const float px = s.pos[0] + nz.p[0], py = s.pos[1] + nz.p[1], pz = s.pos[2] + nz.p[2];
@@ -188,7 +188,7 @@ __device__ __forceinline__ void write_observation(const StepParams& p, const Age
 #undef QS_SDF_UPDATE
         if (valid) {
             float* srow = row + p.S + 6 * p.K;
-            const float r = p.obst_radius;
+            const float r = obst_r;
             srow[0] = fsqrt(b0) - r; srow[1] = fsqrt(b1) - r; srow[2] = fsqrt(b2) - r;
             srow[3] = fsqrt(b3) - r; srow[4] = fsqrt(b4) - r; srow[5] = fsqrt(b5) - r;
             srow[6] = fsqrt(b6) - r; srow[7] = fsqrt(b7) - r; srow[8] = fsqrt(b8) - r;
@@ -297,7 +297,7 @@ __device__ __forceinline__ void emit_observation_tile(const StepParams& p, const
 // record (next_goal / next_spawn / next_obst / next_scn_*) off the step's critical path; an (auto-)reset that finds the
 // record of its episode only copies it.  (Envs that reset in different steps, as in training with collision-event replay,
 // would otherwise put one ~20 k-instruction generator on the critical path of EVERY step.)
-struct EpisodeLane { V3 goal; ResetPose pose; int scn_next; float approach; };
+struct EpisodeLane { V3 goal; ResetPose pose; int scn_next; float approach; float obst_r; };
 
 __device__ __forceinline__ RngKey episode_key(const StepParams& p, int env, int episode) {
     RngKey k;
@@ -320,17 +320,25 @@ __device__ __forceinline__ EpisodeLane generate_episode(const StepParams& p, con
     EpisodeLane e;
     e.scn_next = SCN_NEVER;
     e.approach = p.approach_metric;
+    e.obst_r = p.obst_radius;
     V3 spawn;
     if (p.use_obst) {
+        // pillar count and size of this episode (ExperienceReplayWrapper's domain randomisation, quad_experience_replay.py:
+        // 108-118 -> reset(obst_density, obst_size), quadrotor_multi.py:339-351): uniform picks from the configured lists
+        int M_e = p.M;
+        if (p.obst_random) {
+            M_e = p.obst_counts[scenario_pick(ekey, 322, p.n_obst_counts)];
+            e.obst_r = p.obst_radii[scenario_pick(ekey, 323, p.n_obst_radii)];
+        }
         // o_random / o_static_same_goal / their mix; every lane also writes its share of the pillar table
-        const ORandomEpisode ep = o_random_episode(ekey, p.scenario, i, p.N, p.M, p.grid_l, p.grid_w, i, p.N, obst_smem, obst_dst);
+        const ORandomEpisode ep = o_random_episode(ekey, p.scenario, i, p.N, M_e, p.grid_l, p.grid_w, i, p.N, obst_smem, obst_dst, p.M);
         e.goal = ep.goal;
         spawn = ep.spawn;
         if (p.scenario != QS_SCENARIO_O_RANDOM)           // per-episode scenario id + its approch_goal_metric (o_base.py:16)
             e.approach = ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL ? 1.0f : 0.5f;
         if (i == 0) {
             scn_i_dst[0] = make_int4(ep.mode, 0, SCN_NEVER, 0);
-            scn_f_dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            scn_f_dst[0] = make_float4(e.obst_r, (float)M_e, 0.f, 0.f);
             scn_f_dst[1] = make_float4(0.f, 0.f, 0.f, e.approach);
             scn_f_dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -354,7 +362,7 @@ __device__ __forceinline__ EpisodeLane generate_episode(const StepParams& p, con
 template <int NP, bool SCN>
 __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key, Agent& s, long long a, int env, int i,
                                           bool do_reset, bool valid, int tick_before_reset, float2* s_obst_env,
-                                          float nvel[3], int& scn_next, float& approach) {
+                                          float nvel[3], int& scn_next, float& approach, float& obst_r) {
     const DevState& st = p.st;
     if (do_reset && valid) {
         // stale velocity (Appendix D-6): the multi-env's self.vel is only refreshed by step()
@@ -384,6 +392,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
                 }
                 const int4 nsi = QS_LD(st.next_scn_i + env);
                 const float4 f1 = QS_LD(st.next_scn_f + e3 + 1);
+                if (p.obst_random) obst_r = QS_LD(st.next_scn_f + e3).x;
                 scn_next = nsi.z;
                 if (p.use_obst && p.scenario != QS_SCENARIO_O_RANDOM) approach = f1.w;
                 if (i == 0) {
@@ -398,6 +407,7 @@ __device__ __forceinline__ void reset_env(const StepParams& p, const RngKey& key
                 s.goal[0] = e.goal.x; s.goal[1] = e.goal.y; s.goal[2] = e.goal.z;
                 rp = e.pose;
                 scn_next = e.scn_next;
+                obst_r = e.obst_r;
                 if (p.use_obst && p.scenario != QS_SCENARIO_O_RANDOM) approach = e.approach;
             }
         } else {
@@ -587,6 +597,8 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     const bool env_metric = p.use_obst && p.scenario > QS_SCENARIO_O_RANDOM;
     float approach = p.approach_metric;
     if (env_metric && env_ok && role == 0) approach = QS_LD(st.scn_f + 3 * (long long)env + 1).w;
+    float obst_r = p.obst_radius;                 // per-episode pillar radius where the size is randomised
+    if (p.obst_random && env_ok) obst_r = QS_LD(st.scn_f + 3 * (long long)env).x;
     // stage the pillar tables in shared memory.  Single-warp shape: every warp stages the tables of ITS envs (a contiguous
     // [32 / NP][M] float2 span) and only a warp-level barrier follows; split shape: the block's two warps share them.
     if (p.use_obst) {
@@ -647,7 +659,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
             if (want) {
                 hand_load(s_hand, lane, o, nvel);
                 const float dmin2 = p.use_obst ? min_pillar_dist2(p, o, s_obst_env) : 1e4f;
-                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand, gbase);
+                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, p.obst_radius, s_hand, gbase);
             }
             bar_sync(2);                                              // final state + flags
             const uint32_t hf = s_hflag[gbase];
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 hand_load(s_hand2, lane, o, nvel);
                 if (p.sense_noise) nz = sensor_noise(key, (hf & HF_RESET) ? SITE_SENSOR_RESET : SITE_SENSOR1, i);
                 const float dmin2 = p.use_obst ? min_pillar_dist2(p, o, s_obst_env) : 1e4f;
-                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, s_hand2, gbase);
+                write_observation<NP, true>(p, o, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, p.obst_radius, s_hand2, gbase);
             }
             if (want) {
                 float* gbase_ptr = p.obs + (p.last_obs_only ? 0 : (long long)t * A) * p.D;
@@ -682,7 +694,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
 
     bool goal_dirty = false;
     const float col_thr2 = p.col_thr * p.col_thr, falloff2 = p.falloff_thr * p.falloff_thr;
-    const float obst_thr2 = p.obst_col_thr * p.obst_col_thr;
+    const float quad_arm = p.obst_col_thr - p.obst_half_size;                  // QuadrotorEnvMulti.quad_arm
 
 #pragma unroll 1
     for (int t = 0; t < p.T; ++t) {
@@ -804,12 +816,14 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         int hit = -1;
         float dmin2 = 1e4f;                          // smallest squared centre distance to a pillar (prunes the SDF pass)
         if (p.use_obst) {
+            const float obst_thr = p.obst_random ? quad_arm + obst_r : p.obst_col_thr;
+            const float obst_thr2 = obst_thr * obst_thr;
 #pragma unroll 4
             for (int m = p.M - 1; m >= 0; --m) {
                 const float2 ob = s_obst_env[m];
                 const float dx = s.pos[0] - ob.x, dy = s.pos[1] - ob.y;
                 const float d2 = dx * dx + dy * dy;
-                hit = (d2 <= obst_thr2) ? m : hit;
+                hit = (d2 <= obst_thr2) ? m : hit;      // obst_thr2 = (quad_arm + radius)^2, obstacles/utils.py:33
                 dmin2 = fminf(dmin2, d2);
             }
         }
@@ -961,7 +975,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 const float2 ob = s_obst_env[hit];
                 V3 pos = {s.pos[0], s.pos[1], s.pos[2]}, vel = {s.vel[0], s.vel[1], s.vel[2]};
                 const KickVO o = obstacle_response(key, i, pos, vel, ob.x, ob.y, 0.5f * (p.room_hi[2] - p.room_lo[2]) + p.room_lo[2],
-                                                   p.obst_half_size);
+                                                   obst_r);
                 s.vel[0] = o.vel.x; s.vel[1] = o.vel.y; s.vel[2] = o.vel.z;
                 s.om[0] += o.dom.x; s.om[1] += o.dom.y; s.om[2] += o.dom.z;
             }
@@ -1046,7 +1060,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 o[QS_STAT_EPISODES_DONE] = ctr.episode_idx + 1;
                 o[QS_STAT_SCENARIO] = (dev_scn || env_metric) ? QS_LD(st.scn_i + env).x : p.scenario;
             }
-            reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next, approach);
+            reset_env<NP, SCN>(p, key, s, a, env, i, do_reset, valid, ctr.tick, SPLIT ? nullptr : s_obst_env, nvel, scn_next, approach, obst_r);
             if (DYN) {
                 // resample_dynamics inside _reset (quadrotor_single.py:387-390): constants uploaded with at_next_reset are
                 // latched now; update_dynamics builds a fresh QuadrotorDynamics, so OU state and SVD counter restart
@@ -1099,7 +1113,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 // rows go to the warp's shared-memory tile, then out through the bulk-copy engine (or coalesced vector stores)
                 const int slot = (lane / NP) * p.N + i;               // row of this drone inside the warp's tile
                 if (p.obs_bulk && p.T > 1) bulk_drain();              // the previous step's copy has read the tile
-                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp);
+                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, s_tile + slot * p.obs_dp, obst_r);
                 QS_TL(5);
                 const int env_first = blockIdx.x * envs_per_block + (threadIdx.x >> 5) * (32 / NP);
                 const int envs_here = min(32 / NP, p.E - env_first);
@@ -1108,7 +1122,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                                           p.last_obs_only ? 0 : t, envs_here * p.N, lane);
                 __syncwarp();
             } else {
-                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, gbase + a * p.D);
+                write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, dmin2, gbase + a * p.D, obst_r);
             }
         }
         if (!SPLIT && dev_scn && __any_sync(0xffffffffu, scn_ev && !kicked)) {      // scenario tick, site B
@@ -1176,7 +1190,8 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     // every lane of the warp takes part in the shuffles below; lanes of unmasked envs write nothing
     int scn_next = SCN_NEVER;
     float approach = p.approach_metric;
-    reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next, approach);
+    float obst_r = p.obst_radius;
+    reset_env<NP, true>(p, key, s, a, env, i, env_ok, valid, ctr.tick, s_obst_env, nvel, scn_next, approach, obst_r);
     if (st.dyn != nullptr) {          // pending physical constants are latched by explicit resets too
         const int pend = env_ok ? QS_LD(st.dyn_pending + env) : 0;
         if (pend != 0) {
@@ -1201,7 +1216,7 @@ __global__ void __launch_bounds__(128) qs_reset_kernel(const __grid_constant__ S
     for (int k = 0; k < 3; ++k) { nz.p[k] = 0.f; nz.v[k] = 0.f; nz.w[k] = 0.f; }
     if (p.sense_noise) nz = sensor_noise(key, SITE_SENSOR_RESET, i);
     write_observation<NP>(p, s, nvel, nz, i, valid, s_obst_env, p.use_obst ? min_pillar_dist2(p, s, s_obst_env) : 1e4f,
-                          p.obs + a * p.D);
+                          p.obs + a * p.D, obst_r);
     if (valid) store_agent(st, a, s, true);
 }
 

@@ -29,6 +29,9 @@ struct QsHandle {
     int split_mode;       // -1 auto, 0 single-warp kernel, 1 split kernel (QS_SPLIT, read at qs_create)
     int pdl_env;          // QS_PDL at the first step launch (-2 = not read yet, -1 = unset)
     int handover;         // -1 not decided yet, 0 grid-wide wait between step grids, 1 per-block hand-over (launch_step)
+    int obst_random, n_obst_counts, n_obst_radii;
+    int obst_counts[QS_MAX_OBST_CHOICES];
+    float obst_radii[QS_MAX_OBST_CHOICES];
     bool wrap_on;
     WrapState wrap;
     float* wrap_agg_host; // pinned
@@ -111,6 +114,8 @@ static void fill_params(const QsHandle* h, StepParams& p) {
     p.obs_stage = (D <= 72) ? 1 : 0;
     p.obs_bulk = 0;
     p.chained = 0;
+    p.obst_random = h->obst_random; p.n_obst_counts = h->n_obst_counts; p.n_obst_radii = h->n_obst_radii;
+    for (int k = 0; k < QS_MAX_OBST_CHOICES; ++k) { p.obst_counts[k] = h->obst_counts[k]; p.obst_radii[k] = h->obst_radii[k]; }
     p.scenario = c.scenario; p.grid_l = c.obst_grid[0]; p.grid_w = c.obst_grid[1];
 }
 
@@ -358,7 +363,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     choose_obs_writeout(h, p, obs_in_device_memory);
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
     const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
-    const bool split = want_split && p.obs_stage && h->NP > 1 && h->st.dyn == nullptr;
+    const bool split = want_split && p.obs_stage && h->NP > 1 && h->st.dyn == nullptr && !h->obst_random;
     // QS_BALANCE=1 (experiment): one CTA per SM, ceil(warps / SMs) warps each — every SM then holds the same number of warps
     // whatever the CTA scheduler does while two step grids overlap (the timeline of the debug build showed SMs with 6 CTAs
     // of 2 warps next to SMs with 2, and the step ends with the slowest block)
@@ -789,6 +794,29 @@ extern "C" int qs_set_chained(QsHandle* h, int on) {
     if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
     h->chained = on ? 1 : 0;
     h->last_was_step = 0;
+    return QS_OK;
+}
+
+extern "C" int qs_set_obstacle_randomization(QsHandle* h, const float* densities_host, int n_densities, const float* sizes_host, int n_sizes) {
+    if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
+    if (n_densities == 0 && n_sizes == 0) { h->obst_random = 0; return QS_OK; }
+    if (!h->cfg.use_obstacles || h->cfg.scenario == QS_SCENARIO_HOST_TABLES)
+        return fail(QS_ERR_INVALID_ARG, "obstacle randomisation needs use_obstacles and a device-side obstacle scenario");
+    if (n_densities < 1 || n_sizes < 1 || n_densities > QS_MAX_OBST_CHOICES || n_sizes > QS_MAX_OBST_CHOICES || !densities_host || !sizes_host)
+        return fail(QS_ERR_INVALID_ARG, "1..16 densities and sizes are needed");
+    const double area = (double)h->cfg.obst_grid[0] * h->cfg.obst_grid[1];
+    for (int k = 0; k < n_densities; ++k) {
+        const int m = (int)((double)densities_host[k] * area);                   // quadrotor_multi.py:128
+        if (m < 0 || m > h->M) return fail(QS_ERR_INVALID_ARG, "a density needs more pillars than QsConfig.num_obstacles (the table size)");
+        if ((int)area - m < h->cfg.num_agents) return fail(QS_ERR_INVALID_ARG, "a density leaves fewer free cells than drones");
+        h->obst_counts[k] = m;
+    }
+    for (int k = 0; k < n_sizes; ++k) {
+        if (!(sizes_host[k] >= 0.f)) return fail(QS_ERR_INVALID_ARG, "negative pillar size");
+        h->obst_radii[k] = sizes_host[k] * 0.5f;
+    }
+    h->n_obst_counts = n_densities; h->n_obst_radii = n_sizes;
+    h->obst_random = 1;
     return QS_OK;
 }
 

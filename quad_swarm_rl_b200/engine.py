@@ -254,6 +254,13 @@ class QuadSwarmEngine:
         L.check(self.lib.qs_wrap_true_reward(self.h, _ptr(self._true_reward), self._stream()))
         return self._true_reward
 
+    def set_obstacle_randomization(self, densities, sizes):
+        """Per-episode pillar density / size drawn on the device from these choice lists (include/quadswarm.h,
+        qs_set_obstacle_randomization); the engine must have been built with obst_density = the largest one."""
+        d = (C.c_float * len(densities))(*[float(x) for x in densities])
+        z = (C.c_float * len(sizes))(*[float(x) for x in sizes])
+        L.check(self.lib.qs_set_obstacle_randomization(self.h, d, len(densities), z, len(sizes)))
+
     def set_chained(self, on=True):
         """Promise (or retract) that consecutive step() / rollout() calls follow each other directly on the stream
         (include/quadswarm.h, qs_set_chained): rollouts with pre-generated actions, CUDA graphs of steps."""

@@ -124,10 +124,23 @@ def make_quadrotor_env_multi_batched(cfg, num_envs, env_id_offset=0, stats_every
         rew_coeff=dict(DEFAULT_QUAD_REWARD_SHAPING['quad_rewards']), obs_repr=cfg.quads_obs_repr,
         neighbor_visible_num=cfg.quads_neighbor_visible_num, neighbor_obs_type=cfg.quads_neighbor_obs_type,
         collision_hitbox_radius=cfg.quads_collision_hitbox_radius, collision_falloff_radius=cfg.quads_collision_falloff_radius,
-        use_obstacles=cfg.quads_use_obstacles, obst_density=cfg.quads_obst_density, obst_size=cfg.quads_obst_size,
+        use_obstacles=cfg.quads_use_obstacles,
+        # the pillar table is sized for the largest density the randomisation can draw
+        obst_density=(max(cfg.quads_obst_density, float(np.arange(cfg.quads_obst_density_min, cfg.quads_obst_density_max, 0.05).max()))
+                      if (getattr(cfg, 'quads_domain_random', False) and getattr(cfg, 'quads_obst_density_random', False)) else cfg.quads_obst_density),
+        obst_size=cfg.quads_obst_size,
         obst_spawn_area=cfg.quads_obst_spawn_area, use_downwash=cfg.quads_use_downwash, quads_mode=cfg.quads_mode,
         room_dims=cfg.quads_room_dims, device=getattr(cfg, 'quads_device', 0), seed=getattr(cfg, 'seed', None),
         env_id_offset=env_id_offset)
+    # quad_utils.py:67-70: domain randomisation of the pillar field (per fresh episode, on the device)
+    if cfg.quads_use_obstacles and getattr(cfg, 'quads_domain_random', False) and env.device_scenario is not None:
+        dens = [cfg.quads_obst_density]
+        sizes = [cfg.quads_obst_size]
+        if getattr(cfg, 'quads_obst_density_random', False):
+            dens = list(np.arange(cfg.quads_obst_density_min, cfg.quads_obst_density_max, 0.05))
+        if getattr(cfg, 'quads_obst_size_random', False):
+            sizes = list(np.arange(cfg.quads_obst_size_min, cfg.quads_obst_size_max, 0.1))
+        env.engine.set_obstacle_randomization(dens, sizes)
     reward_shaping, annealing = _shaping_and_annealing(cfg)
     return BatchedTrainingEnv(env, reward_shaping_scheme=reward_shaping, annealing=annealing,
                               replay_buffer_sample_prob=cfg.replay_buffer_sample_prob, stats_every=stats_every)

@@ -155,7 +155,11 @@ class Pair:
                                o.obst_quad_collisions_per_episode, o.obst_quad_collisions_after_settle,
                                o.distance_to_goal_3_5, o.distance_to_goal_5]
             if M > 0 and o.obst_xy is not None:
-                ob[e, :M] = o.obst_xy
+                ob[e, :] = 1.0e4                                    # unused table slots stand far outside the room
+                ob[e, :len(o.obst_xy)] = o.obst_xy
+                base = 4 + L.QS_NUM_ENV_STATS
+                if getattr(o.source, 'densities', None) is not None:      # per-episode pillar radius / count (scn_f[0].xy)
+                    ei[e, base + 4:base + 6] = np.array([o.obst_size / 2.0, float(len(o.obst_xy))], np.float32).view(np.int32)
             sc = getattr(o.source, 's', None)                 # twin of the device-side scenario state (scenario_gen.py)
             if sc is not None:
                 base = 4 + L.QS_NUM_ENV_STATS

@@ -487,3 +487,36 @@ def test_per_drone_dynamics_models_match_oracle(kw_name, kind):
     frac = rep['skipped_env_steps'] / max(1, rep['skipped_env_steps'] + rep['compared_env_steps'])
     assert frac < 0.10, rep
     pair.engine.close()
+
+
+def test_per_episode_obstacle_density_and_size_randomisation():
+    """qs_set_obstacle_randomization (ExperienceReplayWrapper's domain randomisation -> reset(obst_density, obst_size),
+    quad_experience_replay.py:108-118, quadrotor_multi.py:339-351): every episode of every env draws its pillar count and
+    pillar size on the device; collision test, contact response and the 3x3 distance patch use the episode's radius.  The
+    twin (oracle/scenario_gen.py) makes the same draws; trajectories stay in parity across auto-resets."""
+    from oracle.scenario_gen import DeviceORandomSource
+    from tests import parity_util as pu
+    dens = [0.05, 0.1, 0.15000000000000002, 0.2]           # np.arange(0.05, 0.25, 0.05)
+    sizes = [0.3, 0.4, 0.5, 0.6000000000000001, 0.7000000000000002]
+    kw = dict(C3, ep_time=0.4)
+    E = 10
+    pair = pu.DevicePair(E, kw, 1357, 'o_random', lambda: DeviceORandomSource(densities=dens, sizes=sizes))
+    pair.engine.set_obstacle_randomization(dens, sizes)
+    seen_m, seen_r = set(), set()
+
+    def hook(p, t):
+        if t % 41 == 5:
+            st = p.engine.get_state()
+            base = 4 + pu.L.QS_NUM_ENV_STATS
+            rad_m = st['env_i32'][:, base + 4:base + 6].cpu().numpy().view(np.float32)
+            for e, o in enumerate(p.oracles):
+                assert rad_m[e, 0] == np.float32(o.obst_size / 2) and int(rad_m[e, 1]) == len(o.obst_xy) == o.source.num_pillars
+                ob = st['obst_xy'][e].cpu().numpy()
+                assert np.array_equal(ob[:len(o.obst_xy)], o.obst_xy.astype(np.float32)) and (ob[len(o.obst_xy):] == 1.0e4).all()
+                seen_m.add(len(o.obst_xy)); seen_r.add(float(rad_m[e, 0]))
+    rep = pu.run_parity(pair, 170, np.random.RandomState(8), resync=20, hook=hook)
+    print(rep, sorted(seen_m), sorted(seen_r))
+    assert rep['dones'] >= 4 * E and len(seen_m) >= 3 and len(seen_r) >= 3
+    frac = rep['skipped_env_steps'] / max(1, rep['skipped_env_steps'] + rep['compared_env_steps'])
+    assert frac < 0.10, rep
+    pair.engine.close()
