@@ -69,7 +69,17 @@ extern "C" {
 /* scenarios/ep_rand_bezier.py: one common goal that follows quadratic Bezier segments, two control points re-drawn 5..10 m
  * away every 5 s (and at tick 1) until both lie inside the room.  Obstacle-free family; part of `mix`. */
 #define QS_SCENARIO_EP_RAND_BEZIER 12
-#define QS_SCENARIO_LAST QS_SCENARIO_EP_RAND_BEZIER
+/* The evaluation scenarios of the obstacle family (scenarios/utils.py:18-20), generated and ticked on the device; pillars
+ * and spawn cells as o_random; all need use_obstacles and have approch_goal_metric 1.0 (o_base.py:16):
+ *   O_DYNAMIC_SAME_GOAL  common goal above the centre of the largest free square; at tick 1 and then every 4-6 s it hops to a
+ *                        random free cell at most 4 m away, z ~ U(0.75, 3) (o_dynamic_same_goal.py:17-51);
+ *   O_SWAP_GOALS         a formation around that centre, permuted among the drones every 4-6 s (o_swap_goals.py);
+ *   O_EP_RAND_BEZIER     common goal above a random free cell, then quadratic Bezier segments of 6 s whose two control
+ *                        points lie 2..5 m away and inside x, y in (-4.5, 4.5), z in (2, 2.5) (o_ep_rand_bezier.py:14-57). */
+#define QS_SCENARIO_O_DYNAMIC_SAME_GOAL 13
+#define QS_SCENARIO_O_SWAP_GOALS 14
+#define QS_SCENARIO_O_EP_RAND_BEZIER 15
+#define QS_SCENARIO_LAST QS_SCENARIO_O_EP_RAND_BEZIER
 #define QS_SCENARIO_DEVICE_FAMILY_FIRST QS_SCENARIO_STATIC_SAME_GOAL
 
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a

@@ -106,6 +106,9 @@ CASES = [
     # goal following quadratic Bezier segments re-drawn every 5 s (third-party `bezier` restated in oracle/stubs/bezier)
     dict(name='ep_rand_bezier_3', kw=dict(num_agents=3, neighbor_visible_num=2, ep_time=10.4,
                                           quads_mode='ep_rand_bezier'), T=1100, seed=99, obs_stride=25),
+    dict(name='o_ep_rand_bezier_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.4, use_obstacles=True,
+                                            quads_mode='o_ep_rand_bezier', obs_repr='xyz_vxyz_R_omega_floor'),
+         T=700, seed=104, obs_stride=20),
     # other physical models: per-drone constants derived by the reference are stored in the fixture
     dict(name='defaultquad_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=1.0, quads_mode='static_diff_goal',
                                        dynamics_params='DefaultQuad'), T=130, seed=101, obs_stride=1, plant='room4', plant_at=[30]),

@@ -76,50 +76,123 @@ def largest_free_square_cell(mask, L, W):
 
 
 O_RANDOM, O_MIX, O_STATIC_SAME_GOAL = 1, 10, 11
+O_DYNAMIC_SAME_GOAL, O_SWAP_GOALS, O_EP_RAND_BEZIER = 13, 14, 15
+O_NAMES = {O_RANDOM: 'o_random', O_MIX: 'mix', O_STATIC_SAME_GOAL: 'o_static_same_goal', O_DYNAMIC_SAME_GOAL: 'o_dynamic_same_goal',
+           O_SWAP_GOALS: 'o_swap_goals', O_EP_RAND_BEZIER: 'o_ep_rand_bezier'}
+O_BEZIER_STEPS, O_BEZIER_MAX_TRIES, O_DYN_MAX_TRIES = 600, 4096, 256
 
 
 class DeviceORandomSource:
     """Episode source for OracleEnv that mirrors the device-side obstacle scenarios (needs a PhiloxRng):
-    QS_SCENARIO_O_RANDOM (default), QS_SCENARIO_O_STATIC_SAME_GOAL, or QS_SCENARIO_MIX over the two."""
+    QS_SCENARIO_O_RANDOM (default), QS_SCENARIO_O_STATIC_SAME_GOAL, QS_SCENARIO_MIX over the two, or one of the ticked
+    scenarios o_dynamic_same_goal / o_swap_goals / o_ep_rand_bezier (qs_scenario.cuh: o_episode_extras,
+    obstacle_scenario_tick; reference: scenarios/obstacles/*.py)."""
 
     def __init__(self, L=8, W=8, scenario=O_RANDOM, densities=None, sizes=None):
         # densities / sizes: the choice lists of the per-episode randomisation (qs_set_obstacle_randomization), or None
         self.densities, self.sizes = densities, sizes
         self.L, self.W = L, W
-        self.scenario = {'o_random': O_RANDOM, 'mix': O_MIX, 'o_static_same_goal': O_STATIC_SAME_GOAL}.get(scenario, scenario)
+        self.scenario = {v: k for k, v in O_NAMES.items()}.get(scenario, scenario)
         self.mode = O_RANDOM if self.scenario == O_MIX else self.scenario
+        self.period, self.next, self.events = 0, NEVER, 0
 
     @property
     def approch_goal_metric(self):
-        return 1.0 if self.mode == O_STATIC_SAME_GOAL else 0.5          # o_base.py:16, o_random.py:10
+        return 0.5 if self.mode == O_RANDOM else 1.0                    # o_base.py:16, o_random.py:10
 
     def name(self):
-        return 'Scenario_o_static_same_goal' if self.mode == O_STATIC_SAME_GOAL else 'Scenario_o_random'
+        return 'Scenario_' + O_NAMES[self.mode]
+
+    def _mask(self, obst):
+        mask = 0
+        for xy in obst:                                    # the occupancy mask from the pillar cells
+            if xy[0] > 1.0e3:
+                continue
+            cid = int(np.floor(xy[0] + self.L // 2))
+            rid = self.W - 1 - int(np.floor(xy[1] + self.W // 2))
+            mask |= 1 << (rid * self.W + cid)
+        return mask
 
     def reset(self, env):
         d = env.rng.episode_draws
         M = env.cfg.num_obstacles
+        N = env.num_agents
         if self.densities is not None:
             # int(density * area) pillars (quadrotor_multi.py:128), the float32 list entry as the kernels hold it
             M = int(float(np.float32(self.densities[_pick(d, 322, len(self.densities))])) * self.L * self.W)
             env.obst_size = 2.0 * float(np.float32(0.5 * np.float32(self.sizes[_pick(d, 323, len(self.sizes))])))
         self.num_pillars = M
-        goals, spawn, obst = o_random_episode(d, env.num_agents, M, self.L, self.W)
+        goals, spawn, obst = o_random_episode(d, N, M, self.L, self.W)
         if self.scenario == O_MIX:
             self.mode = O_RANDOM if _pick(d, 321, 2) == 0 else O_STATIC_SAME_GOAL
-        if self.mode == O_STATIC_SAME_GOAL:
-            mask = 0
-            for xy in obst:                                    # rebuild the occupancy mask from the pillar cells
-                cid = int(round(xy[0] - 0.5 + self.L // 2))
-                rid = self.W - 1 - int(round(xy[1] - 0.5 + self.W // 2))
-                mask |= 1 << (rid * self.W + cid)
+        self.mask = mask = self._mask(obst)
+        self.period, self.next = 0, NEVER
+        cells = self.L * self.W
+        if self.mode in (O_STATIC_SAME_GOAL, O_DYNAMIC_SAME_GOAL, O_SWAP_GOALS):
             c = _cell_center(largest_free_square_cell(mask, self.L, self.W), self.L, self.W)
             z = 1.5 + (3.0 - 1.5) * d.uniform(px.SITE_SCENARIO_U, 0, 0, 320)
-            goals = np.tile(np.array([c[0], c[1], z]), (env.num_agents, 1))
+            center = np.array([c[0], c[1], z])
+            goals = np.tile(center, (N, 1))
+            if self.mode != O_STATIC_SAME_GOAL:
+                self.period = 400 + _pk(d, STREAM_RESET, SV_PERIOD, 200)
+                self.next = 1 if self.mode == O_DYNAMIC_SAME_GOAL else self.period
+            if self.mode == O_SWAP_GOALS:
+                fm = pick_formation(d, STREAM_RESET, O_SWAP_GOALS, N)
+                goals = np.array([formation_point(fm['f'], N, shuffle_rank(d, STREAM_RESET, i, 0, N), fm['size'], center, fm['layer'],
+                                                  fm['per_layer']) for i in range(N)])
+        elif self.mode == O_EP_RAND_BEZIER:
+            c = _cell_center(_nth_free(mask, _pk(d, STREAM_RESET, SV_CX, cells - M), cells), self.L, self.W)
+            goals = np.tile(np.array([c[0], c[1], 0.75 + (3.0 - 0.75) * _u(d, STREAM_RESET, SV_CZ)]), (N, 1))
+            self.period, self.next = 1, 1
+            self.p0 = self.p1 = self.p2 = goals[0].copy()
+        self.goals = goals
         return goals, spawn, obst
 
     def step(self, env, tick):
-        return None
+        if tick != self.next:
+            return None
+        d, N = env.rng.draws, env.num_agents
+        g = self.goals
+        nxt = tick + self.period if self.period > 0 else NEVER
+        cells = self.L * self.W
+        if self.mode == O_SWAP_GOALS:
+            g = np.array([g[shuffle_rank(d, STREAM_TICK, i, 0, N)] for i in range(N)])
+        elif self.mode == O_DYNAMIC_SAME_GOAL:
+            g0 = np.array(g[0], dtype=np.float64)
+            free = cells - bin(self.mask).count('1')
+            for k in range(O_DYN_MAX_TRIES):
+                v0 = SV_BEZIER + 8 * k
+                c = _cell_center(_nth_free(self.mask, _pk(d, STREAM_TICK, v0, free), cells), self.L, self.W)
+                cand = np.array([c[0], c[1], 0.75 + (3.0 - 0.75) * _u(d, STREAM_TICK, v0 + 1)])
+                if np.sqrt(np.sum((g0 - cand) ** 2)) <= 4.0:
+                    g = np.tile(cand, (N, 1))
+                    break
+            nxt = (tick // self.period + 1) * self.period
+        elif self.mode == O_EP_RAND_BEZIER:
+            t = tick % O_BEZIER_STEPS
+            g0 = np.array(g[0], dtype=np.float64)
+            if t == 0 or tick == 1:
+                hx, hy, hz = 5.0, 5.0, 3.0
+                p1 = p2 = g0
+                lo, hi = np.array([-hx + 0.5, -hy + 0.5, 1.5 + 0.5]), np.array([hx - 0.5, hy - 0.5, hz - 0.5])
+                for k in range(O_BEZIER_MAX_TRIES):
+                    v0 = SV_BEZIER + 8 * k
+                    u = [-h + 2.0 * h * _u(d, STREAM_TICK, v0 + j) for j, h in enumerate((hx, hy, hz, hx, hy, hz))]
+                    dist = float(2 + _pk(d, STREAM_TICK, v0 + 6, 4))
+                    a, b = np.array([u[0], u[2], u[4]]), np.array([u[1], u[3], u[5]])
+                    q1 = g0 + a * (dist / np.sqrt(np.sum(a * a)))
+                    q2 = g0 + b * (dist / np.sqrt(np.sum(b * b)))
+                    if (q1 > lo).all() and (q1 < hi).all() and (q2 > lo).all() and (q2 < hi).all():
+                        p1, p2 = q1, q2
+                        break
+                self.p0, self.p1, self.p2 = g0, p1, p2
+            if t != 0 and tick > 1:
+                sp = t / (O_BEZIER_STEPS - 1)
+                g = np.tile((1 - sp) ** 2 * self.p0 + 2 * (1 - sp) * sp * self.p1 + sp ** 2 * self.p2, (N, 1))
+        self.next = nxt
+        self.events += 1
+        self.goals = g
+        return g
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -212,6 +285,8 @@ def pick_formation(draws, stream, mode, n):
         count, low, high = 1, 0.0, 0.0
     elif mode == SWAP_GOALS:
         low, high = 0.4, 0.8
+    elif mode == O_SWAP_GOALS:
+        count, low, high = 7, 0.4, 0.8
     elif mode == DYNAMIC_FORMATIONS:
         low, high = 0.0, 1.0
     f = _pk(draws, stream, SV_FORMATION, count) if count > 1 else 0

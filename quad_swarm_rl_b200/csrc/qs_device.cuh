@@ -793,7 +793,7 @@ __device__ __forceinline__ float2 cell_center(int cell, int L, int W) {
     return make_float2((float)cid + 0.5f - (float)(L / 2), (float)(W - 1 - rid) + 0.5f - (float)(W / 2));
 }
 
-struct ORandomEpisode { V3 spawn, goal; int mode; };
+struct ORandomEpisode { V3 spawn, goal; int mode; unsigned long long mask; };
 
 // word w of a uniform block
 __device__ __forceinline__ float u4_word(const float4& u, int w) { return w == 0 ? u.x : (w == 1 ? u.y : (w == 2 ? u.z : u.w)); }
@@ -825,7 +825,8 @@ __device__ __noinline__ int largest_free_square_cell(unsigned long long mask, in
 }
 
 // pillar table of the env -> `obst_out[m]` for m = lane, lane + stride, ... ; this lane's spawn / goal returned
-// `scenario`: QS_SCENARIO_O_RANDOM, QS_SCENARIO_O_STATIC_SAME_GOAL or QS_SCENARIO_MIX (one of the two per episode, slot 321).
+// `scenario`: QS_SCENARIO_O_RANDOM, QS_SCENARIO_O_STATIC_SAME_GOAL, QS_SCENARIO_MIX (one of the two per episode, slot 321) or one
+// of the ticked obstacle scenarios (their goals are finished by o_episode_extras, qs_scenario.cuh).
 // The draws are the keyed values scenario_u(key, v) (one Philox block serves four consecutive v: it is computed once
 // per four picks here, not once per pick).
 __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario, int i, int n_agents, int M, int L, int W, int lane_i,
@@ -877,7 +878,10 @@ __device__ __noinline__ ORandomEpisode o_random_episode(RngKey key, int scenario
         ep.spawn.x = a.x; ep.spawn.y = a.y; ep.spawn.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 128 + k);
         ep.goal.x = b.x; ep.goal.y = b.y; ep.goal.z = 1.0f + (3.0f - 1.0f) * scenario_u(key, 256 + k);
     }
-    if (ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL) {          // one goal for the whole swarm (o_static_same_goal.py:44-52)
+    ep.mask = mask;
+    if (ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL || ep.mode == QS_SCENARIO_O_DYNAMIC_SAME_GOAL || ep.mode == QS_SCENARIO_O_SWAP_GOALS) {
+        // one goal for the whole swarm (o_static_same_goal.py:44-52; the start of o_dynamic_same_goal.py:45, the formation
+        // centre of o_swap_goals.py:46)
         const float2 c = cell_center(largest_free_square_cell(mask, L, W), L, W);
         ep.goal.x = c.x; ep.goal.y = c.y; ep.goal.z = 1.5f + (3.0f - 1.5f) * scenario_u(key, 320);
     }

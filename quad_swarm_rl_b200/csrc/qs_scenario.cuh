@@ -134,6 +134,10 @@ __device__ Formation pick_formation(const RngKey& key, int stream, int mode, int
         count = 1; low = 0.f; high = 0.f;
     } else if (mode == QS_SCENARIO_SWAP_GOALS) {
         low = 0.4f; high = 0.8f;
+    } else if (mode == QS_SCENARIO_O_SWAP_GOALS) {
+        // utils.py:55-57 indexes QUADS_FORMATION_LIST with a draw below len(QUADS_FORMATION_LIST_OBSTACLES) = 7: every
+        // formation except the cube, circle_horizontal included
+        count = 7; low = 0.4f; high = 0.8f;
     } else if (mode == QS_SCENARIO_DYNAMIC_FORMATIONS) {
         low = 0.f; high = 1.0f;
     }
@@ -372,6 +376,172 @@ __device__ __noinline__ ScnOut scenario_tick(RngKey key, int N, int i, int tick,
         s.next = s.period > 0 ? tick + s.period : SCN_NEVER;
         o.next = s.next;
         if (i == 0) scn_store(st, env, s);
+    }
+    __syncwarp();
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Ticked obstacle scenarios (obstacles/o_dynamic_same_goal.py, o_swap_goals.py, o_ep_rand_bezier.py).  Pillars, spawn cells
+// and the centre of the largest free square come from o_random_episode (qs_device.cuh); this part finishes the goals and
+// writes the env's scenario words.  State layout of an obstacle env (differs from ScnState: the first two floats belong to
+// the per-episode pillar size / count):
+//   scn_i = (mode, period, next event tick, 0)
+//   scn_f[0] = (pillar radius, pillar count, P0.x, P0.y)   scn_f[1] = (P1, approch_goal_metric)   scn_f[2] = (P2, P0.z)
+// with P0..P2 the running Bezier segment of o_ep_rand_bezier (zero otherwise).  Twin: oracle/scenario_gen.py.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int O_BEZIER_STEPS = 600;        // int(6 s * control_freq), o_ep_rand_bezier.py:18-19
+constexpr int O_BEZIER_MAX_TRIES = 4096;   // acceptance ~0.5 %: the reference loops until it succeeds (P(fail) ~ 1e-10 here)
+constexpr int O_DYN_MAX_TRIES = 256;
+
+__device__ __forceinline__ bool ticked_obstacle_scenario(int mode) {
+    return mode == QS_SCENARIO_O_DYNAMIC_SAME_GOAL || mode == QS_SCENARIO_O_SWAP_GOALS || mode == QS_SCENARIO_O_EP_RAND_BEZIER;
+}
+
+// `goal`: what o_random_episode returned (the largest-square centre for the first two modes).  Every lane of the env
+// computes the same env-level values; lane 0 stores them.
+__device__ __noinline__ ScnOut o_episode_extras(RngKey key, int mode, int N, int i, unsigned long long mask, int L, int W, V3 goal,
+                                                float obst_r, int M_e, int4* si, float4* sf) {
+    ScnOut o;
+    o.goal = goal;
+    int period = 0;
+    V3 p0 = {0.f, 0.f, 0.f};
+    if (mode == QS_SCENARIO_O_DYNAMIC_SAME_GOAL) {
+        period = 400 + scn_pick(key, SCN_STREAM_RESET, SV_PERIOD, 200);           // int(U(4, 6) s * 100 Hz), :33-34
+        o.next = 1;                                                                // first hop at tick 1 (:20)
+    } else if (mode == QS_SCENARIO_O_SWAP_GOALS) {
+        period = 400 + scn_pick(key, SCN_STREAM_RESET, SV_PERIOD, 200);
+        o.next = period;
+        const Formation fm = pick_formation(key, SCN_STREAM_RESET, mode, N);
+        o.goal = formation_point(fm.f, N, shuffle_rank(key, SCN_STREAM_RESET, i, 0, N), fm.size, goal, fm.layer, fm.per_layer);
+    } else {
+        // o_ep_rand_bezier.py:71-72: the common goal starts above a random free cell, z ~ U(0.75, 3) (o_base.py:54-69)
+        const int cells = L * W;
+        const int c = nth_free_cell(mask, scn_pick(key, SCN_STREAM_RESET, SV_CX, cells - M_e), cells);
+        const float2 xy = cell_center(c, L, W);
+        o.goal.x = xy.x; o.goal.y = xy.y; o.goal.z = 0.75f + (3.0f - 0.75f) * scn_u(key, SCN_STREAM_RESET, SV_CZ);
+        period = 1;
+        o.next = 1;
+        p0 = o.goal;
+    }
+    if (i == 0) {
+        si[0] = make_int4(mode, period, o.next, 0);
+        sf[0] = make_float4(obst_r, (float)M_e, p0.x, p0.y);
+        sf[1] = make_float4(p0.x, p0.y, p0.z, 1.0f);
+        sf[2] = make_float4(p0.x, p0.y, p0.z, p0.z);
+    }
+    return o;
+}
+
+// occupancy mask of the env's pillar table (slots beyond this episode's pillar count stand far outside the grid)
+__device__ __forceinline__ unsigned long long pillar_mask(const float2* obst, int M_table, int L, int W) {
+    unsigned long long mask = 0ull;
+#pragma unroll 1
+    for (int m = 0; m < M_table; ++m) {
+        const float2 xy = QS_LD(obst + m);
+        if (xy.x > 1.0e3f) continue;
+        const int cid = (int)floorf(xy.x + (float)(L / 2)), rid = W - 1 - (int)floorf(xy.y + (float)(W / 2));
+        mask |= 1ull << (rid * W + cid);
+    }
+    return mask;
+}
+
+// scenario.step() of the three scenarios on an event tick.  Called by every lane of the warp from a warp-uniform branch
+// (`active` is uniform over the NP lanes of an env): the goal permutation and the parallel rejection search use shuffles.
+template <int NP>
+__device__ __noinline__ ScnOut obstacle_scenario_tick(RngKey key, int N, int i, int tick, V3 goal, bool active, DevState st, int env,
+                                                      int L, int W, int M_table) {
+    ScnOut o;
+    o.goal = goal; o.next = SCN_NEVER;
+    int4 a = make_int4(-1, 0, SCN_NEVER, 0);
+    float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, f2 = f0;
+    const long long e3 = 3 * (long long)env;
+    if (active) {
+        a = QS_LD(st.scn_i + env);
+        f0 = QS_LD(st.scn_f + e3); f1 = QS_LD(st.scn_f + e3 + 1); f2 = QS_LD(st.scn_f + e3 + 2);
+    }
+    const int mode = a.x, period = a.y;
+    // o_swap_goals.py:14-17: the goals are permuted among the drones
+    const int src = (active && mode == QS_SCENARIO_O_SWAP_GOALS) ? shuffle_rank(key, SCN_STREAM_TICK, i, 0, N) : i;
+    const float gx = shfl<NP>(goal.x, src), gy = shfl<NP>(goal.y, src), gz = shfl<NP>(goal.z, src);
+    int next = period > 0 ? tick + period : SCN_NEVER;
+
+    // o_ep_rand_bezier.py:27-45: a new segment at tick 1 and at every multiple of 600 ticks.  The NP lanes of the env test
+    // NP consecutive tries per round; the lowest accepted try wins, as in the reference's sequential loop.
+    const int t = tick % O_BEZIER_STEPS;
+    bool searching = active && mode == QS_SCENARIO_O_EP_RAND_BEZIER && (t == 0 || tick == 1);
+    const bool new_segment = searching;
+    V3 p1 = goal, p2 = goal;
+    // every drone carries the same goal; the padding lanes of the group take part in the search with drone 0's copy
+    const V3 g0 = {shfl<NP>(goal.x, 0), shfl<NP>(goal.y, 0), shfl<NP>(goal.z, 0)};
+#pragma unroll 1
+    for (int base = 0; base < O_BEZIER_MAX_TRIES && __any_sync(0xffffffffu, searching); base += NP) {
+        bool ok = false;
+        V3 q1 = g0, q2 = g0;
+        if (searching) {
+            const float hx = 5.0f, hy = 5.0f, hz = 3.0f;
+            const int v0 = SV_BEZIER + 8 * (base + i);
+            // uniform(low=-high, high=high, size=(2, 3)).reshape(3, 2): u0..u5 in draw order; column c takes (u[c], u[2 + c],
+            // u[4 + c]) — the ranges follow the draw order (x, y, z, x, y, z), the reference's reshape quirk is kept
+            const float u0 = -hx + 2.f * hx * scn_u(key, SCN_STREAM_TICK, v0 + 0), u1 = -hy + 2.f * hy * scn_u(key, SCN_STREAM_TICK, v0 + 1),
+                        u2 = -hz + 2.f * hz * scn_u(key, SCN_STREAM_TICK, v0 + 2), u3 = -hx + 2.f * hx * scn_u(key, SCN_STREAM_TICK, v0 + 3),
+                        u4 = -hy + 2.f * hy * scn_u(key, SCN_STREAM_TICK, v0 + 4), u5 = -hz + 2.f * hz * scn_u(key, SCN_STREAM_TICK, v0 + 5);
+            const float d = (float)(2 + scn_pick(key, SCN_STREAM_TICK, v0 + 6, 4));     // randint(2.5, 6) truncates its bounds: 2..5
+            const float n1 = d / sqrtf(u0 * u0 + u2 * u2 + u4 * u4), n2 = d / sqrtf(u1 * u1 + u3 * u3 + u5 * u5);
+            q1.x = g0.x + u0 * n1; q1.y = g0.y + u2 * n1; q1.z = g0.z + u4 * n1;
+            q2.x = g0.x + u1 * n2; q2.y = g0.y + u3 * n2; q2.z = g0.z + u5 * n2;
+            ok = q1.x > -hx + 0.5f && q1.x < hx - 0.5f && q1.y > -hy + 0.5f && q1.y < hy - 0.5f && q1.z > 1.5f + 0.5f && q1.z < hz - 0.5f &&
+                 q2.x > -hx + 0.5f && q2.x < hx - 0.5f && q2.y > -hy + 0.5f && q2.y < hy - 0.5f && q2.z > 1.5f + 0.5f && q2.z < hz - 0.5f;
+        }
+        const uint32_t b = group_ballot<NP>(ok);
+        const int w = b ? (__ffs(b) - 1) : 0;
+        const float a1 = shfl<NP>(q1.x, w), a2 = shfl<NP>(q1.y, w), a3 = shfl<NP>(q1.z, w);
+        const float b1 = shfl<NP>(q2.x, w), b2 = shfl<NP>(q2.y, w), b3 = shfl<NP>(q2.z, w);
+        if (searching && b) {
+            p1.x = a1; p1.y = a2; p1.z = a3; p2.x = b1; p2.y = b2; p2.z = b3;
+            searching = false;
+        }
+    }
+
+    if (active) {
+        if (mode == QS_SCENARIO_O_SWAP_GOALS) {
+            o.goal.x = gx; o.goal.y = gy; o.goal.z = gz;
+        } else if (mode == QS_SCENARIO_O_DYNAMIC_SAME_GOAL) {
+            // o_dynamic_same_goal.py:20-28: a random free cell, z ~ U(0.75, 3), re-drawn while it is more than 4 m from the
+            // current goal (the goal's own cell always qualifies; after O_DYN_MAX_TRIES failures the goal stays)
+            const unsigned long long mask = pillar_mask(st.obst + (long long)env * M_table, M_table, L, W);
+            const int cells = L * W, free_cells = cells - __popcll(mask);
+#pragma unroll 1
+            for (int k = 0; k < O_DYN_MAX_TRIES; ++k) {
+                const int v0 = SV_BEZIER + 8 * k;
+                const float2 xy = cell_center(nth_free_cell(mask, scn_pick(key, SCN_STREAM_TICK, v0, free_cells), cells), L, W);
+                const float z = 0.75f + (3.0f - 0.75f) * scn_u(key, SCN_STREAM_TICK, v0 + 1);
+                const float dx = goal.x - xy.x, dy = goal.y - xy.y, dz = goal.z - z;
+                if (sqrtf(dx * dx + dy * dy + dz * dz) <= 4.0f) { o.goal.x = xy.x; o.goal.y = xy.y; o.goal.z = z; break; }
+            }
+            next = (tick / period + 1) * period;
+        } else if (mode == QS_SCENARIO_O_EP_RAND_BEZIER) {
+            V3 p0 = {f0.z, f0.w, f2.w};
+            if (new_segment) {
+                p0 = goal;
+                f0.z = p0.x; f0.w = p0.y; f2.w = p0.z;
+                f1.x = p1.x; f1.y = p1.y; f1.z = p1.z;
+                f2.x = p2.x; f2.y = p2.y; f2.z = p2.z;
+            }
+            if (t != 0 && tick > 1) {
+                const float sp = (float)t / (float)(O_BEZIER_STEPS - 1), ca = (1.f - sp) * (1.f - sp), cb = 2.f * (1.f - sp) * sp, cc = sp * sp;
+                o.goal.x = ca * p0.x + cb * f1.x + cc * f2.x;
+                o.goal.y = ca * p0.y + cb * f1.y + cc * f2.y;
+                o.goal.z = ca * p0.z + cb * f1.z + cc * f2.z;
+            }
+        }
+        o.next = next;
+        if (i == 0) {
+            st.scn_i[env] = make_int4(mode, period, next, 0);
+            if (mode == QS_SCENARIO_O_EP_RAND_BEZIER && new_segment) {
+                st.scn_f[e3] = f0; st.scn_f[e3 + 1] = f1; st.scn_f[e3 + 2] = f2;
+            }
+        }
     }
     __syncwarp();
     return o;

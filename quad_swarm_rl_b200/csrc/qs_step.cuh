@@ -310,7 +310,8 @@ __device__ __forceinline__ RngKey episode_key(const StepParams& p, int env, int 
 // true when the kernels generate the episodes (no host tables)
 template <bool SCN>
 __device__ __forceinline__ bool device_generated(const StepParams& p) {
-    return (p.use_obst && p.scenario != QS_SCENARIO_HOST_TABLES) || (SCN && !p.use_obst && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST);
+    return (p.use_obst && p.scenario != QS_SCENARIO_HOST_TABLES && (SCN || !ticked_obstacle_scenario(p.scenario))) ||
+           (SCN && !p.use_obst && p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST);
 }
 
 // this lane's share of the env's next episode; the env-level parts go to (obst_smem,) obst_dst, scn_i_dst, scn_f_dst
@@ -335,8 +336,12 @@ __device__ __forceinline__ EpisodeLane generate_episode(const StepParams& p, con
         e.goal = ep.goal;
         spawn = ep.spawn;
         if (p.scenario != QS_SCENARIO_O_RANDOM)           // per-episode scenario id + its approch_goal_metric (o_base.py:16)
-            e.approach = ep.mode == QS_SCENARIO_O_STATIC_SAME_GOAL ? 1.0f : 0.5f;
-        if (i == 0) {
+            e.approach = ep.mode == QS_SCENARIO_O_RANDOM ? 0.5f : 1.0f;
+        if (SCN && ticked_obstacle_scenario(ep.mode)) {
+            const ScnOut o = o_episode_extras(ekey, ep.mode, p.N, i, ep.mask, p.grid_l, p.grid_w, ep.goal, e.obst_r, M_e, scn_i_dst, scn_f_dst);
+            e.goal = o.goal;
+            e.scn_next = o.next;
+        } else if (i == 0) {
             scn_i_dst[0] = make_int4(ep.mode, 0, SCN_NEVER, 0);
             scn_f_dst[0] = make_float4(e.obst_r, (float)M_e, 0.f, 0.f);
             scn_f_dst[1] = make_float4(0.f, 0.f, 0.f, e.approach);
@@ -693,6 +698,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     }
 
     bool goal_dirty = false;
+    bool stored_early = false, late_goal = false;      // state stores issued before the last observation; goal event after it
     const float col_thr2 = p.col_thr * p.col_thr, falloff2 = p.falloff_thr * p.falloff_thr;
     const float quad_arm = p.obst_col_thr - p.obst_half_size;                  // QuadrotorEnvMulti.quad_arm
 
@@ -1007,7 +1013,8 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         if (dev_scn && __any_sync(0xffffffffu, scn_ev && (SPLIT || kicked))) {
             const V3 g = {s.goal[0], s.goal[1], s.goal[2]};
             const bool act = scn_ev && (SPLIT || kicked);
-            const ScnOut o = scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
+            const ScnOut o = p.use_obst ? obstacle_scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env, p.grid_l, p.grid_w, p.M)
+                                         : scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
             if (act) {
                 s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
                 scn_next = o.next;
@@ -1104,6 +1111,16 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
             bar_sync(2);
         }
 
+        // The env state is final here (only a goal event at site B below touches it again): its stores are issued before
+        // the observation is built, so that the fence of the per-block hand-over at the end of the kernel finds them
+        // acknowledged instead of waiting a memory round trip for them (timeline: 1.4 -> 0.4 us after the last emit).
+        if (!SPLIT && t == p.T - 1) {
+            if (valid) store_agent(st, a, s, goal_dirty);
+            if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
+            if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count + 1, ctr.svd_count, ctr.episode_idx);
+            stored_early = true;
+        }
+
         // ================= observation (of the post-response, or freshly reset, state) =================
         if (SPLIT) {
             bar_sync(3);                                               // observer is done with this step's hand-off
@@ -1128,11 +1145,13 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         if (!SPLIT && dev_scn && __any_sync(0xffffffffu, scn_ev && !kicked)) {      // scenario tick, site B
             const V3 g = {s.goal[0], s.goal[1], s.goal[2]};
             const bool act = scn_ev && !kicked;
-            const ScnOut o = scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
+            const ScnOut o = p.use_obst ? obstacle_scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env, p.grid_l, p.grid_w, p.M)
+                                         : scenario_tick<NP>(key, p.N, i, ctr.tick, g, act, st, env);
             if (act) {
                 s.goal[0] = o.goal.x; s.goal[1] = o.goal.y; s.goal[2] = o.goal.z;
                 scn_next = o.next;
                 goal_dirty = true;
+                late_goal = true;
             }
         }
         ctr.step_count += 1;
@@ -1140,10 +1159,12 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
 
     if (p.pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;");     // late trigger: overlap only the launch latency
     QS_TL(6);
-    if (valid) store_agent(st, a, s, goal_dirty);
-    if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
+    if (!stored_early || late_goal) {
+        if (valid) store_agent(st, a, s, goal_dirty);
+        if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
+        if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
+    }
     if (!SPLIT && p.obs_bulk) bulk_drain();           // shared memory must outlive the bulk copy's reads
-    if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
     if (HO) {
         if (SPLIT) bar_sync(4); else __syncthreads();
         if (threadIdx.x == 0) handover_release(st.ready + blockIdx.x);

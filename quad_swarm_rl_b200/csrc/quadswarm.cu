@@ -37,6 +37,7 @@ struct QsHandle {
     float* wrap_agg_host; // pinned
     int pregen_every;     // step launches between two launches of the next-episode generator (0 = never), QS_PREGEN overrides
     int since_pregen;
+    unsigned long long capture_id;   // id of the stream capture that saw the last generator launch at its head
     int chained;          // qs_set_chained: consecutive qs_step / qs_rollout launches follow each other directly on the stream
     int last_was_step;    // the last launch this handle enqueued was a step / rollout grid
     int bulk_mode;        // QS_OBS_BULK: -1 auto, 0 never use the bulk-copy engine for the observation write-out, 2 linear copies only
@@ -355,9 +356,22 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // Measured (profiles/r01_notes.md): splitting shortens one warp's dependency chain (32 envs: 6.9 -> 5.8 us per
     // launch, 8 x 1024 envs: 8.05 -> 7.17 us) but adds work, so it only pays while the GPU has idle issue slots, i.e.
     // up to about one physics warp per SM sub-partition (4 x 148 on B200).
-    if (h->pregen_every > 0 && (h->since_pregen += p_in.T) >= h->pregen_every) {
-        int rcp = launch_pregen(h, s);          // next-episode records for the envs that consumed theirs (qs_pregen_kernel)
-        if (rcp != QS_OK) return rcp;
+    if (h->pregen_every > 0) {
+        // next-episode records for the envs that consumed theirs (qs_pregen_kernel): every pregen_every steps — and at the
+        // head of every captured graph, because a graph that is replayed forever repeats exactly the launches of its
+        // capture (a 20-step graph captured between two generator launches would otherwise never refill a record, and every
+        // auto-reset would generate its episode inside the step: same results, ~12 us per reset on c3)
+        bool due = (h->since_pregen += p_in.T) >= h->pregen_every;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        unsigned long long cid = 0;
+        if (cudaStreamGetCaptureInfo(s, &cs, &cid) == cudaSuccess && cs == cudaStreamCaptureStatusActive && cid != h->capture_id) {
+            h->capture_id = cid;
+            due = true;
+        }
+        if (due) {
+            int rcp = launch_pregen(h, s);
+            if (rcp != QS_OK) return rcp;
+        }
     }
     StepParams p = p_in;
     choose_obs_writeout(h, p, obs_in_device_memory);
@@ -400,8 +414,10 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     }
     const int pdl_env = h->pdl_env;
     using KernelFn = void (*)(StepParams);
-    const bool scn = !p.use_obst && ((p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && p.scenario <= QS_SCENARIO_MIX) ||
-                                     p.scenario == QS_SCENARIO_EP_RAND_BEZIER);
+    const bool ticked_obst = p.scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL && p.scenario <= QS_SCENARIO_O_EP_RAND_BEZIER;
+    const bool scn = p.use_obst ? ticked_obst
+                                : ((p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && p.scenario <= QS_SCENARIO_MIX) ||
+                                   p.scenario == QS_SCENARIO_EP_RAND_BEZIER);
     KernelFn fn_wait = nullptr, fn_ho = nullptr;
     int rc = dispatch_np(h->NP, [&](auto np) {
         constexpr int NPv = decltype(np)::value;
@@ -515,8 +531,9 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     if (((cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->scenario < QS_SCENARIO_MIX) || cfg->scenario == QS_SCENARIO_EP_RAND_BEZIER) &&
         cfg->use_obstacles)
         return fail(QS_ERR_INVALID_ARG, "the device-side goal-formation scenarios are obstacle-free (use_obstacles must be 0)");
-    if ((cfg->scenario == QS_SCENARIO_O_STATIC_SAME_GOAL || cfg->scenario == QS_SCENARIO_O_RANDOM) && !cfg->use_obstacles)
-        return fail(QS_ERR_INVALID_ARG, "scenarios o_random / o_static_same_goal need use_obstacles");
+    if ((cfg->scenario == QS_SCENARIO_O_STATIC_SAME_GOAL || cfg->scenario == QS_SCENARIO_O_RANDOM ||
+         cfg->scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL) && !cfg->use_obstacles)
+        return fail(QS_ERR_INVALID_ARG, "the o_* scenarios need use_obstacles");
     if (cfg->use_obstacles && cfg->scenario != QS_SCENARIO_HOST_TABLES) {
         const int cells = cfg->obst_grid[0] * cfg->obst_grid[1];
         if (cfg->obst_grid[0] < 1 || cfg->obst_grid[1] < 1 || cells > 64)

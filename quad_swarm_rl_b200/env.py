@@ -164,7 +164,8 @@ class _EnvBase:
             seed=seed, device=device, env_id_offset=env_id_offset, device_scenario=device_scenario, quad_arm=quad_arm,
             # scenario.approch_goal_metric (o_base.py:16: 1.0 for the goal-sharing obstacle scenarios, else 0.5); with the
             # host-side `mix` over obstacle scenarios the value of o_random is used for every episode
-            approch_goal_metric=1.0 if quads_mode in ('o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals') else 0.5)
+            approch_goal_metric=1.0 if quads_mode in ('o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals',
+                                                       'o_ep_rand_bezier') else 0.5)
         if self._dyn_sources is not None:
             self.engine.set_dynamics(self._dyn_rows)
         self.device_scenario = device_scenario

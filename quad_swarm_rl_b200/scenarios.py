@@ -564,9 +564,41 @@ class OSwapGoals(_ObstacleScenario):
             self.rng.shuffle(self.goals)
 
 
+class OEpRandBezier(_ObstacleScenario):
+    """obstacles/o_ep_rand_bezier.py: spawn on free cells, one common goal above a random free cell that then follows
+    quadratic Bezier segments of 6 s; control points 2..5 m away (randint(2.5, 6) truncates its bounds), accepted when both
+    lie in x, y within +-4.5 m and z in (2, 2.5)."""
+    mode = 'o_ep_rand_bezier'
+    dynamic = True
+    num_secs = 6
+    z_low, z_high, cap = 1.5, 3.0, 5
+    _bounds = RandBezier._bounds
+    step = RandBezier.step
+
+    def reset(self, obst_map=None, cell_centers=None):
+        self._free_cells(obst_map, cell_centers)
+        start = self._sample_free_points(self.num_agents)
+        end = self._sample_free_point()
+        # o_ep_rand_bezier.py:74-93: ten "trajectory points" are drawn with distance rejections and never used afterwards;
+        # the draws are repeated here (quirks included: the index into the shrinking free-cell list is used as an index into
+        # the cell-centre table) so that the stream stays aligned with the reference
+        picked = []
+        free = list(self.free_space)
+        while len(picked) < 10:
+            idx = self.rng.choice(len(free))
+            if picked and np.any(np.array([np.linalg.norm(cell_centers[q] - cell_centers[idx]) for q in picked]) > 4.0):
+                continue
+            picked.append(idx)
+            free.pop(idx)
+        self.pick_formation()
+        self.spawn_points = start.copy()
+        self.goals = np.array([end for _ in range(self.num_agents)])
+        self.approch_goal_metric = 1.0
+
+
 SCENARIOS = {c.mode: c for c in (StaticSameGoal, StaticDiffGoal, DynamicSameGoal, DynamicDiffGoal, SwapGoals,
                                   DynamicFormations, Lissajous3D, RandBezier, RunAway, SwarmVsSwarm, ORandom, OStaticSameGoal,
-                                  ODynamicSameGoal, OSwapGoals)}
+                                  ODynamicSameGoal, OSwapGoals, OEpRandBezier)}
 
 
 class Mix(Scenario):

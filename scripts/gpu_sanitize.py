@@ -1,5 +1,6 @@
 """Small workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): both step-kernel shapes, both
-launch-chaining modes, resets, contacts, every device-side scenario id, rollout, state and statistics kernels."""
+launch-chaining modes, resets, contacts, every device-side scenario id, rollout, state and statistics kernels, the
+pre-generated episode records, per-drone dynamics, obstacle randomisation and the training-wrapper kernel (replay on)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,12 +12,13 @@ WALL = dict(num_agents=5, neighbor_visible_num=-1, obs_repr='xyz_vxyz_R_omega_wa
 WIDE = dict(num_agents=32, neighbor_visible_num=6)
 
 
-def run(kw, E, scn, steps=14):
+def run(kw, E, scn, steps=14, chained=True):
     eng = QuadSwarmEngine(num_envs=E, seed=1, ep_time=0.12, device_scenario=scn, **kw)
     if scn is None:
         t = make_tables(np.random.RandomState(2), E, kw['num_agents'], eng.M, kw.get('use_obstacles', False), episodes=1, spread=0.05)[0]
         t['spawn'] = t['goals'].copy() if not kw.get('use_obstacles') else t['spawn']     # tight clusters -> contacts
         eng.set_next_episode(t['goals'], t['spawn'], t['obst'])
+    eng.set_chained(chained)
     eng.reset()
     a = torch.rand((steps + 8, E, kw['num_agents'], 4), device='cuda') * 2 - 1
     for k in range(steps):
@@ -38,6 +40,27 @@ os.environ['QS_PDL'] = '2'                           # grid-wide wait
 run(OBST, 13, 'o_static_same_goal', steps=10)
 os.environ['QS_PDL'] = '3'
 for scn in ('static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals', 'dynamic_formations',
-            'ep_lissajous3D', 'swarm_vs_swarm'):
-    run(dict(num_agents=8, neighbor_visible_num=3), 5, scn, steps=4)
+            'ep_lissajous3D', 'swarm_vs_swarm', 'ep_rand_bezier'):
+    run(dict(num_agents=8, neighbor_visible_num=3), 5, scn, steps=4, chained=False)
+
+
+def run_extras():
+    """Round-2 kernels: dynamics rows latched at reset, obstacle density / size per episode, wrapper epilogue with replay."""
+    from quad_swarm_rl_b200 import quad_models as qm
+    kw = dict(OBST, obst_density=0.8)
+    eng = QuadSwarmEngine(num_envs=9, seed=3, ep_time=0.1, device_scenario='o_random', **kw)
+    eng.set_obstacle_randomization([0.2, 0.8], [0.6, 0.85])
+    rows = np.stack([np.stack([qm.constants_row(qm.crazyflie_params()) for _ in range(8)]) for _ in range(9)])
+    eng.set_dynamics(rows.astype(np.float32), at_next_reset=True)
+    eng.wrap_enable(use_replay=True, replay_buffer_size=4, replay_prob=0.75)
+    eng.reset()
+    a = torch.rand((40, 9, 8, 4), device='cuda') * 2 - 1
+    for k in range(40):
+        eng.wrap_step(a[k].contiguous())
+    eng.wrap_read()
+    torch.cuda.synchronize()
+    eng.close()
+
+
+run_extras()
 print('sanitize workload done')

@@ -233,6 +233,30 @@ def test_device_side_obstacle_scenarios_match_twin(scenario):
     pair.engine.close()
 
 
+@pytest.mark.parametrize('scenario,n', [('o_dynamic_same_goal', 8), ('o_swap_goals', 8), ('o_ep_rand_bezier', 8), ('o_ep_rand_bezier', 5),
+                                        ('o_swap_goals', 3)])
+def test_device_side_ticked_obstacle_scenarios_match_twin(scenario, n):
+    """QS_SCENARIO_O_DYNAMIC_SAME_GOAL / O_SWAP_GOALS / O_EP_RAND_BEZIER (the evaluation scenarios of the obstacle family,
+    scenarios/utils.py:18-20): pillars, spawn cells, goals and every goal event (hop to a free cell <= 4 m away, permutation,
+    Bezier segments with the lane-parallel rejection search) happen inside the kernels and equal the twin, step by step,
+    across the events at tick 1 / 4-6 s / 6 s and an auto-reset."""
+    from oracle.scenario_gen import DeviceORandomSource
+    from tests import parity_util as pu
+    kw = dict(C3, ep_time=6.3, num_agents=n)
+    E = 3
+    pair = pu.DevicePair(E, kw, 8642 + n, scenario, lambda: DeviceORandomSource(scenario=scenario))
+    rep = pu.run_parity(pair, 660, np.random.RandomState(6), resync=20)
+    assert rep['dones'] >= E
+    assert all(o.source.events >= 1 for o in pair.oracles)
+    st = pair.engine.get_state()
+    goals_dev = st['agent_f32'][..., 30:33].cpu().numpy()
+    for e, o in enumerate(pair.oracles):
+        np.testing.assert_allclose(goals_dev[e], np.array([d.goal for d in o.drones]), rtol=1e-5, atol=1e-5)
+    es, _ = pair.engine.episode_stats()
+    assert {int(x) for x in es[:, 12].cpu().numpy()} == {pu.L.DEVICE_SCENARIOS[scenario]}
+    pair.engine.close()
+
+
 DEVICE_FAMILY = ['static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals',
                  'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix', 'ep_rand_bezier']
 

@@ -237,3 +237,57 @@ def test_device_bezier_twin_follows_the_host_scenario_semantics():
             want = hs.bezier_points(np.stack([p0, p1, p2], 1), np.array([sp]))[:, 0]
             assert np.allclose(g, np.tile(want, (3, 1)), atol=1e-12)
         prev = np.array(g)
+
+
+@pytest.mark.parametrize('scenario', ['o_dynamic_same_goal', 'o_swap_goals', 'o_ep_rand_bezier'])
+def test_ticked_obstacle_twin_follows_the_reference_semantics(scenario):
+    """Twin of the kernels' ticked obstacle scenarios against what obstacles/o_dynamic_same_goal.py, o_swap_goals.py and
+    o_ep_rand_bezier.py do (the host classes of scenarios.py replay those against the reference in
+    test_oracle_vs_reference.py): event schedule, hop distance, free cells, permutation, control-point box, Bernstein form."""
+    kw = dict(num_agents=5, obs_repr='xyz_vxyz_R_omega_floor', neighbor_visible_num=2, use_obstacles=True, ep_time=13.0)
+    cfg = pc.cfg_to_oracle(kw)
+    for env_id in range(3):
+        src = sg.DeviceORandomSource(scenario=scenario)
+        env = qo.OracleEnv(cfg, qo.PhiloxRng(5), src, env_id=env_id)
+        env.reset()
+        assert src.approch_goal_metric == 1.0 and src.name() == 'Scenario_' + scenario
+        pill = {tuple(p) for p in env.obst_xy}
+        goals = src.goals.copy()
+        spawn = np.array([d.pos for d in env.drones])
+        assert len({tuple(np.round(p[:2] * 2) / 2) for p in spawn}) <= 5                     # jittered around distinct free cells
+        if scenario == 'o_swap_goals':
+            assert 400 <= src.period <= 599 and src.next == src.period
+            assert len({tuple(g) for g in goals}) == 5 and np.linalg.norm(goals - goals.mean(0), axis=1).max() < 1.5
+        else:
+            assert np.all(goals == goals[0]) and tuple(goals[0, :2]) not in pill
+            assert src.next == 1
+        events = []
+        for tick in range(1, 1250):
+            prev = src.goals.copy()
+            g = src.step(env, tick)
+            if g is None:
+                continue
+            events.append(tick)
+            if scenario == 'o_dynamic_same_goal':
+                assert np.all(g == g[0]) and np.linalg.norm(g[0] - prev[0]) <= 4.0 + 1e-9
+                assert tuple(g[0, :2]) not in pill and 0.75 <= g[0, 2] <= 3.0
+                assert abs(g[0, 0] % 1.0 - 0.5) < 1e-9 and abs(g[0, 1] % 1.0 - 0.5) < 1e-9     # a cell centre
+            elif scenario == 'o_swap_goals':
+                assert sorted(map(tuple, g)) == sorted(map(tuple, prev))
+            else:
+                if tick == 1 or tick % 600 == 0:
+                    assert np.allclose(g, prev) and np.allclose(src.p0, prev[0])
+                    for q in (src.p1, src.p2):
+                        d = np.linalg.norm(q - src.p0)
+                        assert min(abs(d - k) for k in (2, 3, 4, 5)) < 1e-9                   # randint(2.5, 6) -> 2..5
+                        assert abs(q[0]) < 4.5 and abs(q[1]) < 4.5 and 2.0 < q[2] < 2.5      # o_ep_rand_bezier.py:31-44
+                else:
+                    t = tick % 600
+                    want = hs.bezier_points(np.stack([src.p0, src.p1, src.p2], axis=1), np.linspace(0, 1, 600))[:, t]
+                    assert np.allclose(g[0], want, atol=1e-12) and np.all(g == g[0])
+        if scenario == 'o_dynamic_same_goal':
+            assert events == [1] + list(range(src.period, 1250, src.period))
+        elif scenario == 'o_swap_goals':
+            assert events == list(range(src.period, 1250, src.period))
+        else:
+            assert events == list(range(1, 1250))
