@@ -126,6 +126,7 @@ struct StepParams {
     int obst_counts[QS_MAX_OBST_CHOICES];
     float obst_radii[QS_MAX_OBST_CHOICES];
     int chained;                        // 1: the stream predecessor of this launch is a step grid of the same handle (qs_set_chained):
+    int courier;            // per-block hand-over with a courier warp (last warp of the block, no envs): early release of the state
                                         //    actions are prefetched before the dependency wait; hand-over kernels skip the grid-wide wait
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
     int pdl_mode;                       // 0 off, 1 trigger dependents at kernel start, 2 trigger before the final stores,

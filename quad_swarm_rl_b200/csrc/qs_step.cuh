@@ -480,6 +480,16 @@ __device__ __forceinline__ void handover_release(int* ready) {
     __threadfence();
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(1) : "memory");
 }
+// Early hand-over (courier warp, see the kernel): a block publishes its env state BEFORE it writes the observation rows, so
+// its successor must not take "state ready" for "everything written".  A second word per block, `done`, is set when ALL
+// stores of the block are out; the successor's courier takes it (waits for 1, writes 0 — handover_acquire) before the
+// successor's own observation rows may be written (same addresses when the caller reuses one array).  No launch numbers:
+// a replayed CUDA graph repeats its kernel parameters.
+__device__ __forceinline__ void handover_publish_done(int* done) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(1) : "memory");
+}
+__device__ __forceinline__ void bulk_drain_writes() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // physics warp -> shared hand-off arrays
 __device__ __forceinline__ void hand_store(float* hand, int lane, const Agent& s, const float nvel[3]) {
@@ -521,9 +531,37 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     const int i = lane & (NP - 1);
     const int role = SPLIT ? (threadIdx.x >> 5) : 0;                 // 0 physics (or everything), 1 observer
     const int tid = SPLIT ? lane : threadIdx.x;
-    const int envs_per_block = (SPLIT ? 32 : blockDim.x) / NP;
+    // courier warp (p.courier, single-warp shape with the per-block hand-over): the last warp of the block carries no envs;
+    // it takes the predecessor's state word, waits for the predecessor's observation rows, publishes this block's state as
+    // soon as the workers have stored it (before they build the observation) and the block's completion at the end — the
+    // fences and flag round trips of the hand-over then cost the worker warps nothing.
+    const bool has_courier = HO && !SPLIT && p.courier != 0;
+    const int work_threads = has_courier ? (int)blockDim.x - 32 : (int)blockDim.x;
+    const int envs_per_block = (SPLIT ? 32 : work_threads) / NP;
     const int env_local = tid / NP;
     const int env = blockIdx.x * envs_per_block + env_local;
+    if (has_courier && (int)threadIdx.x >= work_threads) {
+        int* const ready = st.ready + blockIdx.x;
+        int* const done = st.ready + p.E + 1 + blockIdx.x;
+        if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (lane == 0) handover_acquire(ready, st.ready + p.E, st.err_flag);
+        __syncthreads();                                              // the workers start loading the state
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (lane == 0) {
+            // the predecessor block's observation rows are complete: its `done` word is taken; after the grid-wide wait of
+            // an unchained launch everything before this grid is complete and the word is simply cleared
+            if (p.chained) handover_acquire(done, st.ready + p.E, st.err_flag);
+            else asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(0) : "memory");
+        }
+        const int late = __syncthreads_or(0);                         // the workers have stored the block's state
+        if (!late && lane == 0) handover_release(ready);
+        __syncthreads();                                              // the workers' last stores (bulk copies drained) are issued
+        if (lane == 0) {
+            handover_publish_done(done);
+            if (late) handover_release(ready);
+        }
+        return;
+    }
     const bool env_ok = env < p.E;
     const bool valid = env_ok && i < p.N;
     const long long a = (long long)env * p.N + i;
@@ -546,7 +584,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         // not chained: the stream predecessor may be a foreign kernel (it never triggers early, so this grid starts when
         // it has completed; the wait makes its writes formally visible).  Chained step grids (qs_set_chained) skip it.
         if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
+        if (threadIdx.x == 0 && !has_courier) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
     } else {
@@ -1119,6 +1157,13 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
             if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
             if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count + 1, ctr.svd_count, ctr.episode_idx);
             stored_early = true;
+            if (has_courier) {
+                // Early hand-over: the successor block only needs this block's env STATE, which is complete now; the
+                // observation rows still to be written belong to this step's output arrays (the courier has made sure that
+                // the predecessor's rows are complete).  A goal event that must run after the observation (site B) keeps
+                // the state open: such a block (rare) is released at the end.
+                __syncthreads_or((dev_scn && scn_ev && !kicked) ? 1 : 0);
+            }
         }
 
         // ================= observation (of the post-response, or freshly reset, state) =================
@@ -1164,10 +1209,13 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         if (valid && dsum_dirty) st.slots[SL_DIST_SUMS * st.a_pad + a] = dsum;
         if (env_ok && i == 0) st.env_ctr[env] = make_int4(ctr.tick, ctr.step_count, ctr.svd_count, ctr.episode_idx);
     }
-    if (!SPLIT && p.obs_bulk) bulk_drain();           // shared memory must outlive the bulk copy's reads
+    if (!SPLIT && p.obs_bulk) {
+        if (has_courier) bulk_drain_writes();         // ... and the `done` word promises that the rows are written
+        else bulk_drain();                            // shared memory must outlive the bulk copy's reads
+    }
     if (HO) {
         if (SPLIT) bar_sync(4); else __syncthreads();
-        if (threadIdx.x == 0) handover_release(st.ready + blockIdx.x);
+        if (threadIdx.x == 0 && !has_courier) handover_release(st.ready + blockIdx.x);
     }
     QS_TL(7);
 }

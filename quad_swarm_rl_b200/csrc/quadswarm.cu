@@ -357,14 +357,17 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // launch, 8 x 1024 envs: 8.05 -> 7.17 us) but adds work, so it only pays while the GPU has idle issue slots, i.e.
     // up to about one physics warp per SM sub-partition (4 x 148 on B200).
     if (h->pregen_every > 0) {
-        // next-episode records for the envs that consumed theirs (qs_pregen_kernel): every pregen_every steps — and at the
-        // head of every captured graph, because a graph that is replayed forever repeats exactly the launches of its
-        // capture (a 20-step graph captured between two generator launches would otherwise never refill a record, and every
-        // auto-reset would generate its episode inside the step: same results, ~12 us per reset on c3)
+        // next-episode records for the envs that consumed theirs (qs_pregen_kernel): every pregen_every step launches.  A
+        // captured graph repeats exactly the launches of its capture: a short graph captured between two generator launches
+        // and replayed forever never refills a record, and every auto-reset then generates its episode inside the step (same
+        // results; ~12 us per reset on c3, which the per-block hand-over mostly hides: 10.0 -> 10.4 us per step).  With
+        // QS_PREGEN_HEAD=1 every captured graph starts with a generator launch instead (costs ~10 us per replay).
         bool due = (h->since_pregen += p_in.T) >= h->pregen_every;
+        static int head = -1;
+        if (head < 0) { const char* e = getenv("QS_PREGEN_HEAD"); head = e ? atoi(e) : 0; }
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         unsigned long long cid = 0;
-        if (cudaStreamGetCaptureInfo(s, &cs, &cid) == cudaSuccess && cs == cudaStreamCaptureStatusActive && cid != h->capture_id) {
+        if (head && cudaStreamGetCaptureInfo(s, &cs, &cid) == cudaSuccess && cs == cudaStreamCaptureStatusActive && cid != h->capture_id) {
             h->capture_id = cid;
             due = true;
         }
@@ -393,26 +396,45 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
         // measured: c5 (8 x 4096, K = 6, staggered resets) 13.7 -> 10.0 us per step, c3 unchanged
         if (wpc >= 2 && wpc * 32 <= QS_LB && ((wpc * 32) % h->NP) == 0) { kBlock = wpc * 32; balanced = true; }
     }
-    const int envs_per_block = (split ? 32 : kBlock) / h->NP;
-    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
-    size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
-    smem = (smem + 127) / 128 * 128;              // TMA sources are 128-byte aligned
-    p.smem_tile_off = (int)(smem / sizeof(float));
-    if (p.obs_stage) smem += (size_t)(split ? 1 : kBlock / 32) * 32 * p.obs_dp * sizeof(float);
-    if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
-    if (balanced && smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;       // only one CTA fits an SM
-    // Programmatic dependent launch between consecutive step grids (QS_PDL overrides; default -1 = choose per handle):
-    //   0 off; 1 grid-wide wait, trigger at kernel start (measured 2 us slower); 2 grid-wide wait, trigger before the final
-    //   stores (0.2-0.4 us faster per step than 0); 3 per-block hand-over, no grid-wide wait (qs_step.cuh).
-    // Measured (profiles/r01_notes.md): 3 wins when a step grid needs more than one wave of CTAs (c4: 29.3 -> 20.1 us,
-    // 16384 x 8 drones: 22.4 -> 19.8 us) and for the split shape (c2: 7.18 -> 6.99 us); for a single-wave grid whose
-    // warps run in lock-step anyway (c3) its acquire / release costs what the hidden launch latency saves, so 2 stays.
     if (h->pdl_env == -2) {          // read once per handle
         const char* e = getenv("QS_PDL");
         const int m = e ? atoi(e) : -1;
         h->pdl_env = (m < -1 || m > 4) ? -1 : m;
     }
     const int pdl_env = h->pdl_env;
+    // Balanced single-wave grids use the per-block hand-over with a COURIER warp (qs_step.cuh): one more warp per CTA that
+    // carries no envs and does the hand-over's flag traffic — acquire of the predecessor's state word, early release of
+    // this block's state (before the observation is built), the `done` word that orders the observation rows of consecutive
+    // steps.  Measured (profiles/r02_notes.md): c3 10.0 -> 8.5 us per step, c5 9.3 -> 8.6.  QS_COURIER=0 switches it off.
+    static int courier_env = -1;
+    if (courier_env < 0) { const char* e = getenv("QS_COURIER"); courier_env = e ? atoi(e) : 1; }
+    if (h->handover < 0 && balanced)          // decided before the first launch so that every grid of a chain has the same shape
+        h->handover = pdl_env >= 0 ? (pdl_env == 3) : ((courier_env && kBlock + 32 <= QS_LB) || h->cfg.use_obstacles != 0);
+    const bool courier = balanced && courier_env && h->handover == 1 && h->chained && h->st.dyn == nullptr && kBlock + 32 <= QS_LB;
+    if (courier) kBlock += 32;
+    p.courier = courier ? 1 : 0;
+    const int work_warps = kBlock / 32 - (courier ? 1 : 0);
+    const int envs_per_block = (split ? 32 : work_warps * 32) / h->NP;
+    const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    size_t smem = h->cfg.use_obstacles ? (size_t)envs_per_block * h->M * sizeof(float2) : 0;
+    smem = (smem + 127) / 128 * 128;              // TMA sources are 128-byte aligned
+    p.smem_tile_off = (int)(smem / sizeof(float));
+    if (p.obs_stage) smem += (size_t)(split ? 1 : work_warps) * 32 * p.obs_dp * sizeof(float);
+    if (split) smem += (size_t)HAND_FLOATS * sizeof(float);
+    // shared-memory footprint of a balanced CTA.  Without a courier warp: 120 KB, i.e. one CTA per SM and never two CTAs of
+    // the same grid on one SM.  With it: 64 KB, so that the successor's CTA (whose block was released early) already runs on
+    // the SM while this one writes its observation rows; the register file limits an SM to two such CTAs anyway.
+    // Measured (c3 / c5, us per step): 120 KB 9.7 / 9.3, 100 KB 9.1 / 9.3, 70 KB 8.8 / 8.8, 48 KB 8.8 / 8.7.  QS_BALANCE_KB overrides.
+    static int balance_kb = -1;
+    if (balance_kb < 0) { const char* e = getenv("QS_BALANCE_KB"); balance_kb = e ? atoi(e) : 0; }
+    const int pad_kb = balance_kb > 0 ? balance_kb : (courier ? 64 : 120);
+    if (balanced && smem < (size_t)pad_kb * 1024) smem = (size_t)pad_kb * 1024;
+    // Programmatic dependent launch between consecutive step grids (QS_PDL overrides; default -1 = choose per handle):
+    //   0 off; 1 grid-wide wait, trigger at kernel start (measured 2 us slower); 2 grid-wide wait, trigger before the final
+    //   stores (0.2-0.4 us faster per step than 0); 3 per-block hand-over, no grid-wide wait (qs_step.cuh).
+    // Measured (profiles/r01_notes.md): 3 wins when a step grid needs more than one wave of CTAs (c4: 29.3 -> 20.1 us,
+    // 16384 x 8 drones: 22.4 -> 19.8 us) and for the split shape (c2: 7.18 -> 6.99 us); for a single-wave grid whose
+    // warps run in lock-step anyway (c3) its acquire / release costs what the hidden launch latency saves, so 2 stays.
     using KernelFn = void (*)(StepParams);
     const bool ticked_obst = p.scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL && p.scenario <= QS_SCENARIO_O_EP_RAND_BEZIER;
     const bool scn = p.use_obst ? ticked_obst
@@ -597,10 +619,11 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.next_scn_f, sizeof(float4) * 3 * E);
     QS_ALLOC0(st.epi, sizeof(int2) * E);
     {   // per-block hand-over words (at most one block per env), all "ready"
-        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * (E + 1)));
+        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * (2 * E + 2)));
         std::vector<int> ones((size_t)E + 1, 1);
         ones[(size_t)E] = 0;                                  // time-out counter
         QS_CUDA(cudaMemcpy(st.ready, ones.data(), sizeof(int) * (E + 1), cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMemset(st.ready + E + 1, 0, sizeof(int) * (E + 1)));      // `done` words (courier warps)
     }
     // rotation = identity so that a never-reset env still holds a valid state
     {

@@ -1,6 +1,6 @@
 """Small workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): both step-kernel shapes, both
 launch-chaining modes, resets, contacts, every device-side scenario id, rollout, state and statistics kernels, the
-pre-generated episode records, per-drone dynamics, obstacle randomisation and the training-wrapper kernel (replay on)."""
+pre-generated episode records, per-drone dynamics, obstacle randomisation and the training-wrapper kernel (replay on), and the courier-warp hand-over of balanced grids."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -63,4 +63,7 @@ def run_extras():
 
 
 run_extras()
+os.environ.pop('QS_PDL', None)                       # default launch rule: balanced CTAs with a courier warp (>= 2 warps per SM)
+run(OBST, 600, 'o_random', steps=8)
+run(dict(num_agents=8, neighbor_visible_num=6), 600, 'swap_goals', steps=8)
 print('sanitize workload done')

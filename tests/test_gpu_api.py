@@ -274,6 +274,44 @@ def test_batched_env_mix_on_device_reports_scenario_names():
     env.close()
 
 
+@pytest.mark.parametrize('E,dev_scn', [(4096, 'o_random'), (300, 'o_static_same_goal')])
+def test_chained_step_grids_into_one_output_array(E, dev_scn):
+    """Early hand-over of the courier warp: a block publishes its env state before its observation rows are written, and its
+    successor starts on that.  When the caller gives every step the SAME output arrays, the rows of step t+1 must still land
+    after those of step t (the `done` word, qs_step.cuh).  A graph of chained launches into one array must leave exactly what
+    stepping with a synchronisation after every launch leaves."""
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    T, N = 80, C3['num_agents']
+    mk = lambda: QuadSwarmEngine(num_envs=E, seed=4, ep_time=0.5, device_scenario=dev_scn, **C3)
+    e1, e2 = mk(), mk()
+    e1.set_chained(True); e2.set_chained(True)
+    a = _actions(T, E, N)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        e1.reset()
+        e1.step(a[0])
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for t in range(1, T):
+                e1.step(a[t])                       # engine-owned obs / rewards / dones arrays: the same every step
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+    e2.reset()
+    e2.step(a[0])
+    for _ in range(3):
+        for t in range(1, T):
+            e2.step(a[t])
+            torch.cuda.synchronize()
+    assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.rewards, e2.rewards) and torch.equal(e1.dones, e2.dones)
+    s1, s2 = e1.get_state(), e2.get_state()
+    for k in ('agent_f32', 'agent_u32', 'env_i32'):
+        assert torch.equal(s1[k], s2[k]), k
+    assert e1.handover_timeouts == 0 and e2.handover_timeouts == 0
+    e1.close(); e2.close()
+
+
 C4 = dict(num_agents=32, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega')
 
 

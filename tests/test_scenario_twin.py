@@ -291,3 +291,73 @@ def test_ticked_obstacle_twin_follows_the_reference_semantics(scenario):
             assert events == list(range(src.period, 1250, src.period))
         else:
             assert events == list(range(1, 1250))
+
+
+# ---- same DISTRIBUTIONS as the reference-pinned host generators (the kernels draw from keyed Philox streams, the reference
+#      from numpy's global stream: the samples differ, the laws must not) ----
+def _p_discrete(a, b, k):
+    from scipy.stats import chi2_contingency
+    t = np.array([np.bincount(a, minlength=k), np.bincount(b, minlength=k)])
+    t = t[:, t.sum(axis=0) > 0]
+    return chi2_contingency(t)[1]
+
+
+def _p_cont(a, b):
+    from scipy.stats import ks_2samp
+    return ks_2samp(a, b)[1]
+
+
+@pytest.mark.parametrize('mode', ['static_diff_goal', 'swap_goals', 'dynamic_formations', 'swarm_vs_swarm', 'o_swap_goals'])
+def test_formation_pick_law_equals_host_generator(mode):
+    """Formation type, size, layer distance and the 4-6 s period: two-sample tests (chi-square / Kolmogorov-Smirnov, n = 1500
+    each) between the twin's keyed draws and the host class driven by a RandomState — the class whose trajectories replay
+    the reference's (test_oracle_vs_reference.py)."""
+    n, N = 1500, 8
+    rs = np.random.RandomState(7)
+    host = hs.create_scenario(mode, N, rng=rs, use_obstacles=mode.startswith('o_'))
+    hf, hsz, hl, hp = [], [], [], []
+    for _ in range(n):
+        host.pick_formation()
+        hf.append(hs.FORMATIONS.index(host.formation)); hsz.append(host.formation_size); hl.append(host.layer_dist)
+        hp.append(int(rs.uniform(low=4.0, high=6.0) * 100.0))
+    mid = sg.O_SWAP_GOALS if mode == 'o_swap_goals' else sg.MODE_IDS[mode]
+    tf, tsz, tl, tp = [], [], [], []
+    for e in range(n):
+        d = px.KeyedDraws(31, e, px.EPISODE_KEY_BIT | 1)
+        fm = sg.pick_formation(d, sg.STREAM_RESET, mid, N // 2 if mode == 'swarm_vs_swarm' else N)
+        tf.append(fm['f']); tsz.append(fm['size']); tl.append(fm['layer'])
+        tp.append(400 + sg._pk(d, sg.STREAM_RESET, sg.SV_PERIOD, 200))
+    hf, tf = np.array(hf), np.array(tf)
+    assert set(tf) == set(hf) and _p_discrete(hf, tf, 8) > 1e-3
+    for f in set(hf):                                          # size law per formation type (the ranges differ by type)
+        a, b = np.array(hsz)[hf == f], np.array(tsz)[tf == f]
+        assert _p_cont(a, b) > 1e-3 and abs(a.min() - b.min()) < 0.05 * (a.max() - a.min() + 1e-9) + 1e-9
+        assert _p_cont(np.array(hl)[hf == f], np.array(tl)[tf == f]) > 1e-3
+    assert _p_cont(np.array(hp, float), np.array(tp, float)) > 1e-3 and min(tp) >= 400 and max(tp) <= 599
+
+
+def test_obstacle_episode_law_equals_host_generator():
+    """o_random: pillar cells, spawn cells and goal heights of the twin against obstacle_map_given_density + ORandom (host,
+    reference-pinned): per-cell pillar frequency (chi-square over the 64 cells), spawn-on-free-cell, z ~ U(1, 3)."""
+    n, N, L = 600, 8, 8
+    rs = np.random.RandomState(3)
+    host = hs.create_scenario('o_random', N, rng=rs, use_obstacles=True)
+    hc, hz, hspawn = [], [], []
+    for _ in range(n):
+        obst_map, pos, cells = hs.obstacle_map_given_density(rs, (8.0, 8.0), 0.2)
+        host.reset(obst_map=obst_map, cell_centers=cells)
+        for p in pos:
+            hc.append(int(np.floor(p[0] + 4)) * L + int(np.floor(p[1] + 4)))
+        hz += list(host.goals[:, 2])
+        hspawn += [int(np.floor(p[0] + 4)) * L + int(np.floor(p[1] + 4)) for p in host.spawn_points]
+    tc, tz, tspawn = [], [], []
+    for e in range(n):
+        d = px.KeyedDraws(5, e, px.EPISODE_KEY_BIT | 2)
+        goals, spawn, obst = sg.o_random_episode(d, N, 12, L, L)
+        tc += [int(np.floor(p[0] + 4)) * L + int(np.floor(p[1] + 4)) for p in obst]
+        tz += list(goals[:, 2])
+        tspawn += [int(np.floor(p[0] + 4)) * L + int(np.floor(p[1] + 4)) for p in spawn]
+        assert not ({tuple(p) for p in obst} & {tuple(p[:2]) for p in spawn})
+    assert _p_discrete(np.array(hc), np.array(tc), 64) > 1e-3
+    assert _p_discrete(np.array(hspawn), np.array(tspawn), 64) > 1e-3
+    assert _p_cont(np.array(hz), np.array(tz)) > 1e-3
