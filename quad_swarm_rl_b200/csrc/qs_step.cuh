@@ -543,22 +543,36 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     if (has_courier && (int)threadIdx.x >= work_threads) {
         int* const ready = st.ready + blockIdx.x;
         int* const done = st.ready + p.E + 1 + blockIdx.x;
+        int* const turn = st.ready + 2 * (p.E + 1) + blockIdx.x;      // wrapped control steps only, see below
+        // Inside qs_wrap_step (p.wrap_chain) the wrapper kernel's block b stands between this block and its successor: it
+        // takes `done` (everything of this step written), may rewrite the env state (replay) and releases `ready` itself.
+        // A third word, `turn`, is passed from step block b to step block b of the next control step (the wrapper kernel has
+        // its own): a block lets its dependents launch as soon as it holds its turn, i.e. when its predecessor of the SAME
+        // kind has finished — a whole control step before the dependent grid's block is needed, so that no launch waits for
+        // the slowest block of the grid in front of it.  Every word still has exactly one waiter at any time: a grid exists
+        // only after all blocks of the grid two launches before it have taken their turn.
         if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (lane == 0) handover_acquire(ready, st.ready + p.E, st.err_flag);
-        __syncthreads();                                              // the workers start loading the state
+        if (lane == 0) handover_acquire(p.wrap_chain ? turn : ready, st.ready + p.E, st.err_flag);
+        __syncthreads();                                              // wrapped chain: turn taken; else: the workers start loading the state
         asm volatile("griddepcontrol.launch_dependents;");
-        if (lane == 0) {
+        if (p.wrap_chain) {
+            if (lane == 0) handover_acquire(ready, st.ready + p.E, st.err_flag);
+            __syncthreads();                                          // the workers start loading the state
+        }
+        if (lane == 0 && !(p.wrap_chain && p.chained)) {
             // the predecessor block's observation rows are complete: its `done` word is taken; after the grid-wide wait of
-            // an unchained launch everything before this grid is complete and the word is simply cleared
+            // an unchained launch everything before this grid is complete and the word is simply cleared.  (In a chain of
+            // wrapped steps the wrapper kernel has taken it.)
             if (p.chained) handover_acquire(done, st.ready + p.E, st.err_flag);
             else asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(0) : "memory");
         }
         const int late = __syncthreads_or(0);                         // the workers have stored the block's state
-        if (!late && lane == 0) handover_release(ready);
+        if (!late && lane == 0 && !p.wrap_chain) handover_release(ready);
         __syncthreads();                                              // the workers' last stores (bulk copies drained) are issued
         if (lane == 0) {
             handover_publish_done(done);
-            if (late) handover_release(ready);
+            if (late && !p.wrap_chain) handover_release(ready);
+            if (p.wrap_chain) handover_release(turn);
         }
         return;
     }
@@ -587,6 +601,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         if (threadIdx.x == 0 && !has_courier) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
+        if (has_courier && p.wrap_chain) __syncthreads();            // wrapped chain: the courier takes `ready` after its turn
     } else {
         if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
         asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -44,6 +44,7 @@ constexpr int RP_STEPS_AGO = 3;  // the checkpoint from 1.5 s before the collisi
 constexpr int RP_COOLDOWN = 500; // one event per 5 s (:154)
 constexpr int RP_MAX_REPLAYS = 10;
 constexpr int RP_GRACE = 150;    // collisions_grace_period_seconds * control_freq
+constexpr int SNAP_BATCH = 32;   // observation words in flight per lane in a snapshot copy (a row of c3 is 40 words: 2 round trips)
 constexpr int SNAP_ENV_I32 = 40; // env_ctr 4, env_cnt 13, scn_i 4, scn_f 12 (bit patterns), spare
 constexpr uint32_t SITE_REPLAY_U = 17;     // (env) uniforms v0 replay?, v1 which event   quad_experience_replay.py:176-178
 
@@ -69,11 +70,18 @@ struct WrapState {
     int replay_on, always_active;
 };
 
+// kernel parameters of the stand-alone wrapper kernel (qs_wrap_apply, and qs_wrap_step behind the split step shape)
 struct WrapParams {
-    StepParams sp;
+    StepParams sp;               // sp.actions / sp.rew_terms / sp.dones / sp.obs: this control step's arrays
     WrapState w;
+    int chain;                   // 1: per-block hand-over with the step grids (see qs_wrap_kernel)
+};
+// what the body works on
+struct WrapView {
+    const StepParams* sp;
+    const WrapState* w;
     const float4* actions;
-    const float* terms;          // [A][QS_NUM_TERMS] written by the step kernel of this step
+    const float* terms;          // [A][QS_NUM_TERMS] written by the step of this control step
     const uint8_t* dones;        // [A]
     float* obs;                  // [A][D]  (rows of replayed envs are overwritten)
 };
@@ -82,10 +90,10 @@ __device__ __forceinline__ void agg_add(float* agg, int k, float v) { if (v != 0
 
 // copy the rows of env `env` between the live state and snapshot slot `slot` (all lanes of the env take part)
 template <bool TO_SNAP>
-__device__ __forceinline__ void snap_copy(const WrapParams& q, int env, int i, bool valid, int slot, bool keep_live_counters) {
-    const StepParams& p = q.sp;
+__device__ __forceinline__ void snap_copy(const WrapView& q, int env, int i, bool valid, int slot, bool keep_live_counters) {
+    const StepParams& p = *q.sp;
     const DevState& st = p.st;
-    const WrapState& w = q.w;
+    const WrapState& w = *q.w;
     const long long a = (long long)env * p.N + i;
     const long long sbase = ((long long)env * w.slots + slot);
     // All loads of a copy are issued before its first store (the compiler must assume the two sides alias, so a load -> store
@@ -101,19 +109,19 @@ __device__ __forceinline__ void snap_copy(const WrapParams& q, int env, int i, b
             else st.slots[(long long)k * st.a_pad + a] = v[k];
         }
     }
-    // observation rows and pillar table: the env's lanes stride over them, 8 words in flight per lane
+    // observation rows and pillar table: the env's lanes stride over them, SNAP_BATCH words in flight per lane
     float* so = w.snap_obs + sbase * p.N * p.D;
     float* lo = q.obs + (long long)env * p.N * p.D;
     const float* src = TO_SNAP ? lo : so;
     float* dst = TO_SNAP ? so : lo;
     if (valid) {
         const int total = p.N * p.D;
-        for (int k0 = i; k0 < total; k0 += 8 * p.N) {
-            float t[8];
+        for (int k0 = i; k0 < total; k0 += SNAP_BATCH * p.N) {
+            float t[SNAP_BATCH];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int k = k0 + u * p.N; t[u] = k < total ? __ldcg(src + k) : 0.f; }
+            for (int u = 0; u < SNAP_BATCH; ++u) { const int k = k0 + u * p.N; t[u] = k < total ? __ldcg(src + k) : 0.f; }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int k = k0 + u * p.N; if (k < total) dst[k] = t[u]; }
+            for (int u = 0; u < SNAP_BATCH; ++u) { const int k = k0 + u * p.N; if (k < total) dst[k] = t[u]; }
         }
     }
     if (p.M > 0 && valid) {
@@ -172,9 +180,9 @@ __device__ __forceinline__ void snap_copy(const WrapParams& q, int env, int i, b
 }
 
 // snapshot slot -> snapshot slot of the same env (checkpoint ring -> event buffer)
-__device__ __forceinline__ void snap_move(const WrapParams& q, int env, int i, bool valid, int src, int dst) {
-    const StepParams& p = q.sp;
-    const WrapState& w = q.w;
+__device__ __forceinline__ void snap_move(const WrapView& q, int env, int i, bool valid, int src, int dst) {
+    const StepParams& p = *q.sp;
+    const WrapState& w = *q.w;
     const long long sb = ((long long)env * w.slots + src), db = ((long long)env * w.slots + dst);
     if (valid) {
         float4 v[NUM_SLOTS];
@@ -183,12 +191,12 @@ __device__ __forceinline__ void snap_move(const WrapParams& q, int env, int i, b
 #pragma unroll
         for (int k = 0; k < NUM_SLOTS; ++k) w.snap_slots[(db * NUM_SLOTS + k) * p.N + i] = v[k];
         const int total = p.N * p.D;
-        for (int k0 = i; k0 < total; k0 += 8 * p.N) {
-            float t[8];
+        for (int k0 = i; k0 < total; k0 += SNAP_BATCH * p.N) {
+            float t[SNAP_BATCH];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int k = k0 + u * p.N; t[u] = k < total ? __ldcg(w.snap_obs + sb * total + k) : 0.f; }
+            for (int u = 0; u < SNAP_BATCH; ++u) { const int k = k0 + u * p.N; t[u] = k < total ? __ldcg(w.snap_obs + sb * total + k) : 0.f; }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int k = k0 + u * p.N; if (k < total) w.snap_obs[db * total + k] = t[u]; }
+            for (int u = 0; u < SNAP_BATCH; ++u) { const int k = k0 + u * p.N; if (k < total) w.snap_obs[db * total + k] = t[u]; }
         }
         for (int m = i; m < p.M; m += p.N) w.snap_obst[db * p.M + m] = __ldcg(w.snap_obst + sb * p.M + m);
         for (int k = i; k < SNAP_ENV_I32; k += p.N) w.snap_env[db * SNAP_ENV_I32 + k] = __ldcg(w.snap_env + sb * SNAP_ENV_I32 + k);
@@ -196,19 +204,26 @@ __device__ __forceinline__ void snap_move(const WrapParams& q, int env, int i, b
 }
 
 template <int NP>
-__global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ WrapParams q) {
-    const StepParams& p = q.sp;
+__device__ __forceinline__ void wrap_body(const WrapView& q, int env, int i) {
+    const StepParams& p = *q.sp;
     const DevState& st = p.st;
-    const WrapState& w = q.w;
+    const WrapState& w = *q.w;
     const int lane = threadIdx.x & 31;
-    const int i = lane & (NP - 1);
-    const int env = blockIdx.x * (blockDim.x / NP) + threadIdx.x / NP;
     const bool env_ok = env < p.E;
     const bool valid = env_ok && i < p.N;
     const long long a = (long long)env * p.N + i;
     const long long A = (long long)p.E * p.N;
-    asm volatile("griddepcontrol.launch_dependents;");       // the next step grid may start launching: it waits for this grid
-    asm volatile("griddepcontrol.wait;" ::: "memory");        // the step grid of this control step is complete
+
+    // (all loads of state that another block instance wrote go through L2 — __ldcg: with block-chained launches there is no
+    // kernel boundary, hence no L1 invalidation, between the writer and this reader)
+    // env-level words: issued here, together with the per-agent loads below (one memory round trip for everything; loaded
+    // where they are used, behind the shuffle, they added two serialised ones to every block's chain)
+    int steps_prev = 0;
+    int4 rp = make_int4(0, 0, 0, -(1 << 30)), rq = make_int4(0, 0, 0, 0), ctr_now = make_int4(0, 0, 0, 0);
+    if (env_ok) {
+        steps_prev = __ldcg(w.ep_steps + env);
+        if (w.replay_on) { rp = __ldcg(w.rp + env); rq = __ldcg(w.rq + env); ctr_now = __ldcg(st.env_ctr + env); }
+    }
 
     // ---- reward shaping: accumulate this step (reward_shaping.py:66-78) ----
     float raw[QS_NUM_TERMS], rwd[QS_NUM_TERMS];
@@ -219,13 +234,13 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
     for (int k = 0; k < QS_NUM_TERMS; ++k) { raw[k] = 0.f; rwd[k] = 0.f; }
     if (valid) {
         const float4* t4 = reinterpret_cast<const float4*>(q.terms + a * QS_NUM_TERMS);
-        const float4 ta = __ldcs(t4), tb = __ldcs(t4 + 1);
+        const float4 ta = __ldcg(t4), tb = __ldcg(t4 + 1);      // written by the step grid that may still be running: L2, not L1
         const float tt[QS_NUM_TERMS] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
         term_quadcol = tt[QS_TERM_RAW_QUADCOL]; term_obst = tt[QS_TERM_RAW_QUADCOL_OBST]; term_crash = tt[QS_TERM_RAW_CRASH];
         const float cf[QS_NUM_TERMS] = {p.rew[QS_REW_POS], p.rew[QS_REW_EFFORT], p.rew[QS_REW_CRASH], p.rew[QS_REW_ORIENT],
                                         p.rew[QS_REW_SPIN], p.rew[QS_REW_QUADCOL_BIN], 1.0f, p.rew[QS_REW_QUADCOL_BIN_OBST]};
-        float4 r0 = w.acc[0 * A + a], r1 = w.acc[1 * A + a], w0 = w.acc[2 * A + a], w1 = w.acc[3 * A + a];
-        asum = w.acc[4 * A + a]; asq = w.acc[5 * A + a];
+        float4 r0 = __ldcg(w.acc + 0 * A + a), r1 = __ldcg(w.acc + 1 * A + a), w0 = __ldcg(w.acc + 2 * A + a), w1 = __ldcg(w.acc + 3 * A + a);
+        asum = __ldcg(w.acc + 4 * A + a); asq = __ldcg(w.acc + 5 * A + a);
         act = __ldcs(q.actions + a);
         r0.x += tt[0]; r0.y += tt[1]; r0.z += tt[2]; r0.w += tt[3]; r1.x += tt[4]; r1.y += tt[5]; r1.z += tt[6]; r1.w += tt[7];
         w0.x += tt[0] * cf[0]; w0.y += tt[1] * cf[1]; w0.z += tt[2] * cf[2]; w0.w += tt[3] * cf[3];
@@ -234,19 +249,14 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
         asq.x += act.x * act.x; asq.y += act.y * act.y; asq.z += act.z * act.z; asq.w += act.w * act.w;
         raw[0] = r0.x; raw[1] = r0.y; raw[2] = r0.z; raw[3] = r0.w; raw[4] = r1.x; raw[5] = r1.y; raw[6] = r1.z; raw[7] = r1.w;
         rwd[0] = w0.x; rwd[1] = w0.y; rwd[2] = w0.z; rwd[3] = w0.w; rwd[4] = w1.x; rwd[5] = w1.y; rwd[6] = w1.z; rwd[7] = w1.w;
-        done = q.dones[a] != 0;
+        done = __ldcg(q.dones + a) != 0;
         if (!done) {
             w.acc[0 * A + a] = r0; w.acc[1 * A + a] = r1; w.acc[2 * A + a] = w0; w.acc[3 * A + a] = w1;
             w.acc[4 * A + a] = asum; w.acc[5 * A + a] = asq;
         }
     }
     const bool env_done = __shfl_sync(0xffffffffu, done, lane & ~(NP - 1)) && env_ok;      // all agents of an env end together
-    int steps = 0;
-    int4 rp = make_int4(0, 0, 0, -(1 << 30)), rq = make_int4(0, 0, 0, 0);
-    if (env_ok) {
-        steps = w.ep_steps[env] + 1;
-        if (w.replay_on) { rp = w.rp[env]; rq = w.rq[env]; }
-    }
+    int steps = env_ok ? steps_prev + 1 : 0;
     const bool saved = rq.x != 0;                              // the episode that ran this step is a replay
     int ev_dst = 0;
 
@@ -318,11 +328,7 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
     // ---- collision-event replay (quad_experience_replay.py:120-209), per env, masked.  Every phase is entered by the whole
     //      warp (warp-uniform `any`), the per-env predicate selects the lanes that act; no collective sits in divergent code.
     const int gbase = lane & ~(NP - 1);
-    int tick = 0, step_count = 0;
-    if (env_ok) {
-        const int4 c = __ldcg(st.env_ctr + env);
-        tick = c.x; step_count = c.y;
-    }
+    const int tick = ctr_now.x, step_count = ctr_now.y;
     // crashes_last_episode += infos[0]['rewards']['rew_crash'] (quadrotor_multi.py:611-612): agent 0's weighted term
     const float crash = __shfl_sync(0xffffffffu, term_crash, gbase) * p.rew[QS_REW_CRASH];
     const bool col_any = group_ballot<NP>(valid && (term_quadcol < 0.f || term_obst < 0.f)) != 0u;
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
         if (ev) {
             int dst = -1;
             for (int b = 0; b < w.buffer; ++b)                       // first free slot, else round-robin (:36-45)
-                if (dst < 0 && w.ev_state[(long long)env * w.buffer + b] < 0) dst = b;
+                if (dst < 0 && __ldcg(w.ev_state + (long long)env * w.buffer + b) < 0) dst = b;
             if (dst < 0) dst = rp.z;
             const int src = (rp.x - RP_STEPS_AGO + RP_KEEP) % RP_KEEP;
             snap_move(q, env, i, valid, src, RP_KEEP + dst);
@@ -364,19 +370,19 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
             agg_add(w.agg, WA_EVENTS_STORED, 1.0f);
         }
     }
-    if (running && i == 0 && crash != 0.f) w.crash_now[env] += crash;
+    if (running && i == 0 && crash != 0.f) w.crash_now[env] = __ldcg(w.crash_now + env) + crash;
 
     // 3. a finished env: can_drones_fly bookkeeping (quadrotor_multi.py:281-287,356-359), then a buffered event is replayed
     //    with probability p instead of the fresh episode the step kernel has already started (:167-209)
     if (__any_sync(0xffffffffu, env_done)) {
         float mean = 0.f;
         if (env_done && i == 0) {
-            const float cn = w.crash_now[env] + crash;
+            const float cn = __ldcg(w.crash_now + env) + crash;
             w.crash_hist[(long long)env * 100 + (rq.z % 100)] = cn;
             w.crash_now[env] = 0.f;
             const int cnt = min(rq.z + 1, 100);
             if (cnt >= 10 && !rq.y) {
-                for (int k = 0; k < cnt; ++k) mean += w.crash_hist[(long long)env * 100 + k];
+                for (int k = 0; k < cnt; ++k) mean += __ldcg(w.crash_hist + (long long)env * 100 + k);
                 mean /= (float)cnt;
             }
         }
@@ -388,14 +394,14 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
             rp.y = 0; rp.w = -(1 << 30);                         // fresh-episode defaults (new_episode, :167-174)
             rq.x = 0;
             int n_valid = 0;
-            for (int b = 0; b < w.buffer; ++b) n_valid += w.ev_state[(long long)env * w.buffer + b] >= 0 ? 1 : 0;
+            for (int b = 0; b < w.buffer; ++b) n_valid += __ldcg(w.ev_state + (long long)env * w.buffer + b) >= 0 ? 1 : 0;
             RngKey k2;
             k2.k0 = p.seed_lo; k2.k1 = p.seed_hi; k2.env = (uint32_t)(p.env_id_offset + env); k2.step = (uint32_t)step_count;
             const float4 u = rng_uniform4(k2, SITE_REPLAY_U, 0, 0, 0);
             if (n_valid > 0 && rq.y && u.x < w.replay_prob) {
                 int want = min((int)(u.y * (float)n_valid), n_valid - 1);
                 for (int b = 0; b < w.buffer; ++b) {
-                    if (w.ev_state[(long long)env * w.buffer + b] >= 0) {
+                    if (__ldcg(w.ev_state + (long long)env * w.buffer + b) >= 0) {
                         if (want == 0) { pick = b; break; }
                         --want;
                     }
@@ -407,12 +413,45 @@ __global__ void __launch_bounds__(128) qs_wrap_kernel(const __grid_constant__ Wr
         }
         __syncwarp();
         if (env_done && pick >= 0 && i == 0) {
-            const int r = w.ev_state[(long long)env * w.buffer + pick] + 1;
+            const int r = __ldcg(w.ev_state + (long long)env * w.buffer + pick) + 1;
             w.ev_state[(long long)env * w.buffer + pick] = r >= RP_MAX_REPLAYS ? -1 : r;          // cleanup (:56-57)
             agg_add(w.agg, WA_REPLAYED_EVENTS, 1.0f);
         }
     }
     if (env_ok && i == 0 && dirty) { w.rp[env] = rp; w.rq[env] = rq; }
+}
+
+// q.chain = 0: the kernel follows the step grid with a grid-wide wait (any launch shape; qs_wrap_apply).
+// q.chain = 1: launched with the step grid's env -> block mapping behind a courier step launch (qs_wrap_step on a chained
+// handle): block b takes the `done` word of step block b (all of its stores are out), does the wrappers' work for the
+// block's envs — which may rewrite their state (replay) — and then hands the block to the next step grid (`ready`).  No
+// grid-wide barrier is left in a wrapped control step; a block lets its dependents launch once it holds its `turn` (block b
+// of the previous wrapper grid is through), see the courier warp of the step kernel.
+template <int NP>
+__global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ WrapParams q) {
+    const DevState& st = q.sp.st;
+    int* const turn = st.ready + 3 * (q.sp.E + 1) + blockIdx.x;
+    if (q.chain) {
+        if (threadIdx.x == 0) handover_acquire(turn, st.ready + q.sp.E, st.err_flag);        // block b of the previous wrapper grid is through
+        __syncthreads();
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (threadIdx.x == 0) handover_acquire(st.ready + q.sp.E + 1 + blockIdx.x, st.ready + q.sp.E, st.err_flag);      // `done` of step block b
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");        // the step grid of this control step is complete
+    }
+    WrapView v;
+    v.sp = &q.sp; v.w = &q.w; v.actions = q.sp.actions; v.terms = q.sp.rew_terms; v.dones = q.sp.dones; v.obs = q.sp.obs;
+    const int lane = threadIdx.x & 31;
+    wrap_body<NP>(v, blockIdx.x * (blockDim.x / NP) + threadIdx.x / NP, lane & (NP - 1));
+    if (q.chain) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            handover_release(st.ready + blockIdx.x);
+            handover_release(turn);
+        }
+    }
 }
 
 }  // namespace qs

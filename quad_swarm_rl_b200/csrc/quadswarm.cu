@@ -40,6 +40,10 @@ struct QsHandle {
     unsigned long long capture_id;   // id of the stream capture that saw the last generator launch at its head
     int chained;          // qs_set_chained: consecutive qs_step / qs_rollout launches follow each other directly on the stream
     int last_was_step;    // the last launch this handle enqueued was a step / rollout grid
+    int last_was_wrap;    // ... was the wrapper kernel of a wrapped control step launched block-chained (qs_wrap_step)
+    int in_wrap_step;     // launch_step is called from qs_wrap_step
+    int step_wrap_chain;  // the step grid just launched leaves its blocks to the wrapper kernel (StepParams.wrap_chain)
+    int wrap_block;       // worker threads per block of that step grid (the wrapper kernel uses the same env -> block mapping)
     int bulk_mode;        // QS_OBS_BULK: -1 auto, 0 never use the bulk-copy engine for the observation write-out, 2 linear copies only
     int* err_host;        // mapped page-locked word the step kernels set when a hand-over wait timed out (sticky)
     cudaEvent_t ev_sync;  // the *_host entry points (own stream) order themselves after the caller-stream work below
@@ -172,6 +176,7 @@ static void choose_obs_writeout(const QsHandle* h, StepParams& p, bool dst_is_de
 // the caller's stream is complete before qs_step_host reads the state.  Nothing is recorded on the hot path.
 static void note_async(QsHandle* h, cudaStream_t s, bool is_step) {
     h->last_was_step = is_step ? 1 : 0;
+    h->last_was_wrap = 0;
     if (s != h->own_stream) { h->last_stream = s; h->async_pending = true; }
 }
 static void join_caller_stream(QsHandle* h) {
@@ -475,7 +480,11 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     }
     // The hand-over kernels pay off only between step grids that follow each other directly; an unchained handle uses
     // the grid-wide wait (formally safe after any predecessor) and never pre-fetches across the dependency wait.
-    p.chained = (h->chained && h->last_was_step) ? 1 : 0;
+    // inside qs_wrap_step the stream predecessor that counts is the block-chained wrapper kernel of the previous control step
+    p.chained = (h->chained && (h->in_wrap_step ? h->last_was_wrap : h->last_was_step)) ? 1 : 0;
+    p.wrap_chain = (h->in_wrap_step && courier) ? 1 : 0;
+    h->step_wrap_chain = p.wrap_chain;
+    h->wrap_block = work_warps * 32;
 #ifdef QS_TIMELINE
     if (!h->tl) { QS_CUDA(cudaMalloc((void**)&h->tl, sizeof(unsigned long long) * 64 * 4096 * 16)); QS_CUDA(cudaMemset(h->tl, 0, sizeof(unsigned long long) * 64 * 4096 * 16)); }
     p.tl = h->tl; p.tl_slot = h->tl_next; h->tl_next = (h->tl_next + 1) % 64;
@@ -619,11 +628,13 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.next_scn_f, sizeof(float4) * 3 * E);
     QS_ALLOC0(st.epi, sizeof(int2) * E);
     {   // per-block hand-over words (at most one block per env), all "ready"
-        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * (2 * E + 2)));
-        std::vector<int> ones((size_t)E + 1, 1);
-        ones[(size_t)E] = 0;                                  // time-out counter
-        QS_CUDA(cudaMemcpy(st.ready, ones.data(), sizeof(int) * (E + 1), cudaMemcpyHostToDevice));
-        QS_CUDA(cudaMemset(st.ready + E + 1, 0, sizeof(int) * (E + 1)));      // `done` words (courier warps)
+        // four words per block, [4][E + 1]: `ready` (1), `done` (0), and the `turn` words of the step and the wrapper kernel
+        // in block-chained wrapped control steps (1); [0][E] is the time-out counter
+        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * 4 * (E + 1)));
+        std::vector<int> init((size_t)4 * (E + 1), 1);
+        init[(size_t)E] = 0;
+        for (long long k = 0; k <= E; ++k) init[(size_t)(E + 1 + k)] = 0;
+        QS_CUDA(cudaMemcpy(st.ready, init.data(), sizeof(int) * 4 * (E + 1), cudaMemcpyHostToDevice));
     }
     // rotation = identity so that a never-reset env still holds a valid state
     {
@@ -762,13 +773,15 @@ extern "C" int qs_wrap_enable(QsHandle* h, const QsWrapConfig* cfg) {
     return QS_OK;
 }
 
-static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream);
+static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream, bool chain = false);
 
 extern "C" int qs_wrap_step(QsHandle* h, const float* actions_dev, float* obs_dev, float* rewards_dev, uint8_t* dones_dev, void* stream) {
     if (!h || !h->wrap_on) return fail(QS_ERR_INVALID_ARG, "qs_wrap_enable first");
+    h->in_wrap_step = 1;
     int rc = qs_step(h, actions_dev, obs_dev, rewards_dev, dones_dev, h->d_terms, stream);
+    h->in_wrap_step = 0;
     if (rc != QS_OK) return rc;
-    return launch_wrap(h, actions_dev, h->d_terms, obs_dev, dones_dev, stream);
+    return launch_wrap(h, actions_dev, h->d_terms, obs_dev, dones_dev, stream, h->step_wrap_chain != 0);
 }
 
 extern "C" int qs_wrap_apply(QsHandle* h, const float* actions_dev, const float* rew_terms_dev, float* obs_dev, const uint8_t* dones_dev,
@@ -778,7 +791,7 @@ extern "C" int qs_wrap_apply(QsHandle* h, const float* actions_dev, const float*
     return launch_wrap(h, actions_dev, rew_terms_dev, obs_dev, (uint8_t*)dones_dev, stream);
 }
 
-static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream) {
+static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms_dev, float* obs_dev, uint8_t* dones_dev, void* stream, bool chain) {
     int rc = QS_OK;
     static int probe = -1;                 // QS_WRAP_PROBE (tuning): 1 = skip the wrapper kernel, 2 = launch it without PDL
     if (probe < 0) { const char* e = getenv("QS_WRAP_PROBE"); probe = e ? atoi(e) : 0; }
@@ -786,11 +799,12 @@ static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms
     WrapParams q;
     fill_params(h, q.sp);
     q.w = h->wrap;
-    q.actions = (const float4*)actions_dev;
-    q.terms = terms_dev;
-    q.dones = dones_dev;
-    q.obs = obs_dev;
-    const int kBlock = 128;
+    q.sp.actions = (const float4*)actions_dev;
+    q.sp.rew_terms = const_cast<float*>(terms_dev);
+    q.sp.dones = dones_dev;
+    q.sp.obs = obs_dev;
+    q.chain = chain ? 1 : 0;
+    const int kBlock = chain ? h->wrap_block : 128;            // chained: block b covers the envs of step block b
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
     cudaLaunchConfig_t lc = {};
@@ -807,6 +821,7 @@ static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx(wrap): ") + cudaGetErrorString(lerr));
     h->launches += 1;
     note_async(h, (cudaStream_t)stream, false);
+    h->last_was_wrap = chain ? 1 : 0;
     return QS_OK;
 }
 
@@ -834,6 +849,7 @@ extern "C" int qs_set_chained(QsHandle* h, int on) {
     if (!h) return fail(QS_ERR_INVALID_ARG, "null argument");
     h->chained = on ? 1 : 0;
     h->last_was_step = 0;
+    h->last_was_wrap = 0;
     return QS_OK;
 }
 

@@ -166,6 +166,12 @@ class _EnvBase:
             # host-side `mix` over obstacle scenarios the value of o_random is used for every episode
             approch_goal_metric=1.0 if quads_mode in ('o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals',
                                                        'o_ep_rand_bezier') else 0.5)
+        if quads_mode == 'mix' and use_obstacles and device_scenario is None:
+            import warnings
+            warnings.warn("quads_mode='mix' with obstacles on host tables: the reached-goal radius (approch_goal_metric) of "
+                          "o_random, 0.5, is used for every episode, also for the o_static_same_goal ones (the reference: 1.0). "
+                          "The device-side generator (device_scenarios=True, the default of QuadrotorEnvMultiBatched) keeps it "
+                          "per episode.")
         if self._dyn_sources is not None:
             self.engine.set_dynamics(self._dyn_rows)
         self.device_scenario = device_scenario

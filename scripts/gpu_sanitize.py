@@ -44,18 +44,20 @@ for scn in ('static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynami
     run(dict(num_agents=8, neighbor_visible_num=3), 5, scn, steps=4, chained=False)
 
 
-def run_extras():
+def run_extras(E=9, steps=40, chained=False, dynamics=True):
     """Round-2 kernels: dynamics rows latched at reset, obstacle density / size per episode, wrapper epilogue with replay."""
     from quad_swarm_rl_b200 import quad_models as qm
     kw = dict(OBST, obst_density=0.8)
-    eng = QuadSwarmEngine(num_envs=9, seed=3, ep_time=0.1, device_scenario='o_random', **kw)
+    eng = QuadSwarmEngine(num_envs=E, seed=3, ep_time=0.1, device_scenario='o_random', **kw)
     eng.set_obstacle_randomization([0.2, 0.8], [0.6, 0.85])
-    rows = np.stack([np.stack([qm.constants_row(qm.crazyflie_params()) for _ in range(8)]) for _ in range(9)])
-    eng.set_dynamics(rows.astype(np.float32), at_next_reset=True)
-    eng.wrap_enable(use_replay=True, replay_buffer_size=4, replay_prob=0.75)
+    rows = np.stack([np.stack([qm.constants_row(qm.crazyflie_params()) for _ in range(8)]) for _ in range(E)])
+    if dynamics:
+        eng.set_dynamics(rows.astype(np.float32), at_next_reset=True)
+    eng.wrap_enable(use_replay=True, replay_buffer_size=4, replay_prob=0.75, replay_always_active=True)
+    eng.set_chained(chained)
     eng.reset()
-    a = torch.rand((40, 9, 8, 4), device='cuda') * 2 - 1
-    for k in range(40):
+    a = torch.rand((steps, E, 8, 4), device='cuda') * 2 - 1
+    for k in range(steps):
         eng.wrap_step(a[k].contiguous())
     eng.wrap_read()
     torch.cuda.synchronize()
@@ -66,4 +68,5 @@ run_extras()
 os.environ.pop('QS_PDL', None)                       # default launch rule: balanced CTAs with a courier warp (>= 2 warps per SM)
 run(OBST, 600, 'o_random', steps=8)
 run(dict(num_agents=8, neighbor_visible_num=6), 600, 'swap_goals', steps=8)
+run_extras(E=600, steps=30, chained=True, dynamics=False)      # wrapped control steps, block-chained with the wrapper kernel
 print('sanitize workload done')

@@ -273,3 +273,49 @@ def test_replay_kernel_follows_the_reference_wrapper_schedule(golden_dir):
                 break
     assert len(starts) == len(ref["episode_start_ticks"]) and set(starts) <= {100, 600}, starts
     env.close()
+
+
+def test_block_chained_wrapped_steps_equal_synchronised_ones():
+    """qs_wrap_step on a chained handle with balanced step grids: no grid-wide barrier is left — the wrapper kernel's block b
+    takes the `done` word of step block b and hands the block to the next step grid (csrc/qs_wrap.cuh, qs_wrap_kernel).  A
+    CUDA graph of such control steps (replay on, clustered spawns so that collision events are stored and replayed) must
+    leave what the same launches with a device synchronisation after every one leave: state, outputs, aggregate."""
+    from quad_swarm_rl_b200.engine import QuadSwarmEngine
+    kw = dict(num_agents=8, neighbor_visible_num=2, obs_repr='xyz_vxyz_R_omega_floor', use_obstacles=True, use_downwash=True,
+              collision_hitbox_radius=30.0, collision_falloff_radius=32.0)      # neighbouring spawn cells touch: events for sure
+    E, T = 600, 260
+    mk = lambda: QuadSwarmEngine(num_envs=E, seed=12, ep_time=2.0, device_scenario='o_static_same_goal', **kw)
+    e1, e2 = mk(), mk()
+    g = torch.Generator(device='cuda'); g.manual_seed(3)
+    a = (0.05 + 0.4 * (torch.rand((T, E, 8, 4), device='cuda', generator=g) * 2 - 1)).contiguous()
+    for e in (e1, e2):
+        e.wrap_enable(use_replay=True, replay_buffer_size=4, replay_prob=0.9, replay_always_active=True)
+        e.set_chained(True)
+        e.reset()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        e1.wrap_step(a[0])
+        st.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for t in range(1, T):
+                e1.wrap_step(a[t])
+        for _ in range(3):
+            gr.replay()
+        st.synchronize()
+    e2.wrap_step(a[0])
+    for _ in range(3):
+        for t in range(1, T):
+            e2.wrap_step(a[t])
+            torch.cuda.synchronize()
+    assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.rewards, e2.rewards) and torch.equal(e1.dones, e2.dones)
+    s1, s2 = e1.get_state(), e2.get_state()
+    for k in ('agent_f32', 'agent_u32', 'env_i32'):
+        assert torch.equal(s1[k], s2[k]), k
+    g1, g2 = e1.wrap_read(), e2.wrap_read()
+    from quad_swarm_rl_b200 import _lib as L
+    assert g1[L.WA['EPISODES_TOTAL']] == g2[L.WA['EPISODES_TOTAL']] > 0
+    assert g1[L.WA['EVENTS_STORED']] == g2[L.WA['EVENTS_STORED']] and g1[L.WA['REPLAYED_EVENTS']] == g2[L.WA['REPLAYED_EVENTS']] > 0
+    np.testing.assert_allclose(g1, g2, rtol=2e-4, atol=1e-3)             # float atomics: the order of the additions differs
+    assert e1.handover_timeouts == 0 and e2.handover_timeouts == 0
+    e1.close(); e2.close()
