@@ -427,9 +427,16 @@ __device__ __forceinline__ void wrap_body(const WrapView& q, int env, int i) {
 // block's envs — which may rewrite their state (replay) — and then hands the block to the next step grid (`ready`).  No
 // grid-wide barrier is left in a wrapped control step; a block lets its dependents launch once it holds its `turn` (block b
 // of the previous wrapper grid is through), see the courier warp of the step kernel.
+#ifdef QS_TIMELINE
+#define QS_WTL(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) q.sp.tl[((long long)q.sp.tl_slot * 4096 + blockIdx.x) * 16 + 12 + (k)] = gtime(); } while (0)
+#else
+#define QS_WTL(k) do { } while (0)
+#endif
+
 template <int NP>
 __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ WrapParams q) {
     const DevState& st = q.sp.st;
+    QS_WTL(0);
     int* const turn = st.ready + 3 * (q.sp.E + 1) + blockIdx.x;
     if (q.chain) {
         if (threadIdx.x == 0) handover_acquire(turn, st.ready + q.sp.E, st.err_flag);        // block b of the previous wrapper grid is through
@@ -444,7 +451,9 @@ __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ Wr
     WrapView v;
     v.sp = &q.sp; v.w = &q.w; v.actions = q.sp.actions; v.terms = q.sp.rew_terms; v.dones = q.sp.dones; v.obs = q.sp.obs;
     const int lane = threadIdx.x & 31;
+    QS_WTL(1);
     wrap_body<NP>(v, blockIdx.x * (blockDim.x / NP) + threadIdx.x / NP, lane & (NP - 1));
+    QS_WTL(2);
     if (q.chain) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -452,6 +461,7 @@ __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ Wr
             handover_release(turn);
         }
     }
+    QS_WTL(3);
 }
 
 }  // namespace qs

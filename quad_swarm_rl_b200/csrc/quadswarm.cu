@@ -804,6 +804,9 @@ static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms
     q.sp.dones = dones_dev;
     q.sp.obs = obs_dev;
     q.chain = chain ? 1 : 0;
+#ifdef QS_TIMELINE
+    q.sp.tl = h->tl; q.sp.tl_slot = (h->tl_next + 63) % 64;      // the slot of the step grid this kernel follows
+#endif
     const int kBlock = chain ? h->wrap_block : 128;            // chained: block b covers the envs of step block b
     const int envs_per_block = kBlock / h->NP;
     const int grid = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;

@@ -10,6 +10,5 @@ echo "== bare default"; run
 echo "== wrapped default"; run --wrapped-main
 echo "== wrapped no replay"; QS_WRAP_REPLAY=0 run --wrapped-main
 echo "== wrapped lockstep"; run "--wrapped-main --lockstep"
-echo "== wrapped KB=120"; QS_BALANCE_KB=120 run --wrapped-main
-echo "== wrapped KB=48"; QS_BALANCE_KB=48 run --wrapped-main
 } 2>&1 | tee gpurun_out/r2u_ab.txt
+for tool in memcheck racecheck; do echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/gpu_sanitize.py 2>&1 | tail -6; done 2>&1 | tee gpurun_out/r2u_sanitize.txt
