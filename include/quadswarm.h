@@ -274,8 +274,11 @@ int qs_read_episode_stats(QsHandle* h, int32_t* env_stats_dev, float* agent_stat
  * that wrote actions_dev.  On: the caller promises that between two consecutive qs_step / qs_rollout calls of this
  * handle nothing else is enqueued on `stream` (pre-generated action rollouts, benchmarks, CUDA graphs of steps); the
  * first step after any other call of the handle still does the full wait.  Chained grids prefetch their actions before
- * the dependency wait and, where a grid needs more than one wave of CTAs (or the split shape is used), hand their envs
- * over per CTA instead of waiting grid-wide.  Environment QS_CHAINED=1 sets the initial value.
+ * the dependency wait and hand their envs over per CTA instead of waiting grid-wide: block b of a step starts as soon as
+ * block b of the previous step has stored its env state — before that block has written its observation rows (DESIGN.md,
+ * "Launch chaining").  The output arrays of consecutive chained steps may be the same ones (the rows of a block are
+ * ordered by a second per-block word); with qs_wrap_step the wrapper kernel takes part in the same per-block protocol.
+ * Environment QS_CHAINED=1 sets the initial value.
  * There is no reference counterpart (Sample Factory steps its envs from Python, one at a time). */
 int qs_set_chained(QsHandle* h, int on);
 
