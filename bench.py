@@ -661,10 +661,10 @@ def run_cuda_arm(args):
             agg = m['runner'].eng.wrap_read(reset=False)
             from quad_swarm_rl_b200 import _lib as L_
             extra['wrapped'] = {'us_per_step': m['us_per_step'], 'agent_steps_per_s': m['value'], 'vs_bare_step': m['us_per_step'] / main['us_per_step'],
-                                'launches_per_step': 1, 'episodes_finished': float(agg[L_.WA['EPISODES_TOTAL']]),
+                                'launches_per_step': 2, 'episodes_finished': float(agg[L_.WA['EPISODES_TOTAL']]),
                                 'checkpoints': float(agg[L_.WA['CHECKPOINTS']]), 'events_stored': float(agg[L_.WA['EVENTS_STORED']]),
                                 'events_replayed': float(agg[L_.WA['REPLAYED_EVENTS']]),
-                                'note': 'qs_wrap_step: the wrappers as the tail of the step kernel (reward-shaping accumulators and episode statistics, '
+                                'note': 'qs_wrap_step: step kernel + the wrapper kernel, chained block by block (reward-shaping accumulators and episode statistics, '
                                         'checkpoint every 0.5 s, collision events, replay p = 0.75 with the can_drones_fly gate open); no host sync'}
             m['runner'].close()
             torch.cuda.empty_cache()

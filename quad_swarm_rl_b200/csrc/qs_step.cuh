@@ -450,6 +450,17 @@ __device__ __noinline__ void bar_sync(int id) {
     __syncwarp();          // bar.sync is warp-aligned: lanes that diverged in the preceding code must reconverge first
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
+// Barriers between the worker warps and the courier warp (single-warp shapes): producer / consumer pairs on named barriers —
+// the side that has something to wait for executes bar.sync, the side that only reports executes bar.arrive and goes on.
+// `n` = all threads of the CTA.  (Ids: 1 state may be loaded, 4 ... in a wrapped chain, 2 state stored, 3 all stores issued.)
+__device__ __forceinline__ void named_sync(int id, int n) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int n) {
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 
 // running episode counter += v.  A reduction (RED.ADD, no return value): a load + store pair per counter put one L2
 // round trip per counter on the critical path of every warp with a discrete event (the debug-build timeline showed +3 us).
@@ -526,6 +537,7 @@ __device__ __forceinline__ void hand_load(const float* hand, int lane, Agent& s,
 template <int NP, bool SPLIT, bool SCN, bool HO, bool DYN = false>
 __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) float2 s_obst[];
+    __shared__ int s_late;          // courier launches: a block with a goal event behind the observation is released at its end
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
     const int i = lane & (NP - 1);
@@ -551,13 +563,17 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         // kind has finished — a whole control step before the dependent grid's block is needed, so that no launch waits for
         // the slowest block of the grid in front of it.  Every word still has exactly one waiter at any time: a grid exists
         // only after all blocks of the grid two launches before it have taken their turn.
+        const int nthr = (int)blockDim.x;
         if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (lane == 0) handover_acquire(p.wrap_chain ? turn : ready, st.ready + p.E, st.err_flag);
-        __syncthreads();                                              // wrapped chain: turn taken; else: the workers start loading the state
+        if (lane == 0) {
+            s_late = 0;
+            handover_acquire(p.wrap_chain ? turn : ready, st.ready + p.E, st.err_flag);
+        }
+        named_arrive(1, nthr);                                        // wrapped chain: turn taken; else: the workers start loading the state
         asm volatile("griddepcontrol.launch_dependents;");
         if (p.wrap_chain) {
             if (lane == 0) handover_acquire(ready, st.ready + p.E, st.err_flag);
-            __syncthreads();                                          // the workers start loading the state
+            named_arrive(4, nthr);                                    // the workers start loading the state
         }
         if (lane == 0 && !(p.wrap_chain && p.chained)) {
             // the predecessor block's observation rows are complete: its `done` word is taken; after the grid-wide wait of
@@ -566,9 +582,10 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
             if (p.chained) handover_acquire(done, st.ready + p.E, st.err_flag);
             else asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(0) : "memory");
         }
-        const int late = __syncthreads_or(0);                         // the workers have stored the block's state
+        named_sync(2, nthr);                                          // the workers have stored the block's state (and do not wait here)
+        const int late = *reinterpret_cast<volatile int*>(&s_late);
         if (!late && lane == 0 && !p.wrap_chain) handover_release(ready);
-        __syncthreads();                                              // the workers' last stores (bulk copies drained) are issued
+        named_sync(3, nthr);                                          // the workers' last stores (bulk copies drained) are issued
         if (lane == 0) {
             handover_publish_done(done);
             if (late && !p.wrap_chain) handover_release(ready);
@@ -598,10 +615,15 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         // not chained: the stream predecessor may be a foreign kernel (it never triggers early, so this grid starts when
         // it has completed; the wait makes its writes formally visible).  Chained step grids (qs_set_chained) skip it.
         if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (threadIdx.x == 0 && !has_courier) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
-        __syncthreads();
-        asm volatile("griddepcontrol.launch_dependents;");
-        if (has_courier && p.wrap_chain) __syncthreads();            // wrapped chain: the courier takes `ready` after its turn
+        if (has_courier) {
+            named_sync(1, (int)blockDim.x);                          // the courier holds the block (wrapped chain: its turn)
+            asm volatile("griddepcontrol.launch_dependents;");
+            if (p.wrap_chain) named_sync(4, (int)blockDim.x);        // wrapped chain: the courier takes `ready` after its turn
+        } else {
+            if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
+            __syncthreads();
+            asm volatile("griddepcontrol.launch_dependents;");
+        }
     } else {
         if (p.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;");
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1177,7 +1199,8 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 // observation rows still to be written belong to this step's output arrays (the courier has made sure that
                 // the predecessor's rows are complete).  A goal event that must run after the observation (site B) keeps
                 // the state open: such a block (rare) is released at the end.
-                __syncthreads_or((dev_scn && scn_ev && !kicked) ? 1 : 0);
+                if (dev_scn && scn_ev && !kicked) *reinterpret_cast<volatile int*>(&s_late) = 1;
+                named_arrive(2, (int)blockDim.x);
             }
         }
 
@@ -1229,8 +1252,11 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         else bulk_drain();                            // shared memory must outlive the bulk copy's reads
     }
     if (HO) {
-        if (SPLIT) bar_sync(4); else __syncthreads();
-        if (threadIdx.x == 0 && !has_courier) handover_release(st.ready + blockIdx.x);
+        if (has_courier) named_arrive(3, (int)blockDim.x);
+        else {
+            if (SPLIT) bar_sync(4); else __syncthreads();
+            if (threadIdx.x == 0) handover_release(st.ready + blockIdx.x);
+        }
     }
     QS_TL(7);
 }

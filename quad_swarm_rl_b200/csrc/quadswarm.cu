@@ -501,6 +501,9 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
     KernelFn fn = fn_dyn ? fn_dyn : (use_ho ? fn_ho : fn_wait);
     if (smem > 48 * 1024) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int carve = -2;          // QS_CARVEOUT (experiment): preferred shared-memory carve-out in % for the step and wrapper kernels
+    if (carve == -2) { const char* e = getenv("QS_CARVEOUT"); carve = e ? atoi(e) : -1; }
+    if (carve >= 0) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn, p);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(lerr));
     QS_CUDA(cudaGetLastError());
@@ -820,6 +823,12 @@ static int launch_wrap(QsHandle* h, const float* actions_dev, const float* terms
     WrapFn fn = nullptr;
     rc = dispatch_np(h->NP, [&](auto np) { fn = (WrapFn)qs_wrap_kernel<decltype(np)::value>; return QS_OK; });
     if (rc != QS_OK) return rc;
+    {
+        const char* e = getenv("QS_CARVEOUT");
+        if (e && atoi(e) >= 0) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        const char* d = getenv("QS_WRAP_SMEM_KB");          // experiment: dummy dynamic shared memory of the wrapper kernel
+        if (e || d) { lc.dynamicSmemBytes = d ? (size_t)atoi(d) * 1024 : 0; if (lc.dynamicSmemBytes > 48 * 1024) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.dynamicSmemBytes)); }
+    }
     const cudaError_t lerr = cudaLaunchKernelEx(&lc, fn, q);
     if (lerr != cudaSuccess) return fail(QS_ERR_CUDA, std::string("cudaLaunchKernelEx(wrap): ") + cudaGetErrorString(lerr));
     h->launches += 1;

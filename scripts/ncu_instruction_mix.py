@@ -25,7 +25,8 @@ for s in sections:
             except ValueError:
                 n = 0
             per_line[(name, int(r[li]))] = per_line.get((name, int(r[li])), 0) + n
-# phases: (file, first line, last line, label) — line numbers of the sources this capture was taken from
+# phases: (file, first line, last line, label) — line numbers of the ROUND-1 sources (the capture behind
+# profiles/r01_v8_instruction_mix.txt); re-derive the table from the source page before using it on a newer capture
 PH = [
     ('qs_rng.cuh', 1, 10 ** 6, 'Philox blocks + Box-Muller (OU and sensor noise draws)'),
     ('qs_device.cuh', 141, 176, 'state load / store'),
