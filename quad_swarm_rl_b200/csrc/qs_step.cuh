@@ -471,7 +471,7 @@ __device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { if (v != 0) 
 // stream-serialization attribute; instead of griddepcontrol.wait (a grid-wide barrier: every step then costs the launch
 // latency plus the SLOWEST warp of the grid) a block waits for its own predecessor's `ready` word, takes it, and only
 // then lets the next grid start launching — so at most two step grids overlap and a block of step t+2 can never see the
-// word block b(t) left for b(t+1).  The writer publishes with barrier + __threadfence + st.release; the reader acquires
+// word block b(t) left for b(t+1).  The writer publishes with barrier + st.release; the reader acquires
 // and reads the state with ld.global.cg (L1 is not coherent across the grids).  Any other kernel / copy on the stream
 // never triggers early, so it still sees, and is seen by, whole step grids.
 __device__ __forceinline__ void handover_acquire(int* ready, int* timeouts, int* err_flag) {
@@ -487,8 +487,10 @@ __device__ __forceinline__ void handover_acquire(int* ready, int* timeouts, int*
     }
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(0) : "memory");
 }
+// st.release = fence + store (SASS: MEMBAR.ALL.GPU; STG.E.STRONG.GPU); an extra __threadfence() in front of it was a second,
+// sequentially consistent membar on the block's critical path.  The writes of the block's other threads are ordered before
+// it by the barrier they arrived at (cumulativity).
 __device__ __forceinline__ void handover_release(int* ready) {
-    __threadfence();
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(1) : "memory");
 }
 // Early hand-over (courier warp, see the kernel): a block publishes its env state BEFORE it writes the observation rows, so
@@ -497,7 +499,6 @@ __device__ __forceinline__ void handover_release(int* ready) {
 // successor's own observation rows may be written (same addresses when the caller reuses one array).  No launch numbers:
 // a replayed CUDA graph repeats its kernel parameters.
 __device__ __forceinline__ void handover_publish_done(int* done) {
-    __threadfence();
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(1) : "memory");
 }
 __device__ __forceinline__ void bulk_drain_writes() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
