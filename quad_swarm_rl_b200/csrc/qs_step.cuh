@@ -461,6 +461,20 @@ __device__ __forceinline__ void named_arrive(int id, int n) {
     __syncwarp();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+// one-shot shared-memory mbarrier (one arrival): the courier tells the workers something without making them wait for each other
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity) {
+    int ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 // running episode counter += v.  A reduction (RED.ADD, no return value): a load + store pair per counter put one L2
 // round trip per counter on the critical path of every warp with a discrete event (the debug-build timeline showed +3 us).
@@ -473,7 +487,8 @@ __device__ __forceinline__ void cnt_add(int32_t* c, int k, int v) { if (v != 0) 
 // then lets the next grid start launching — so at most two step grids overlap and a block of step t+2 can never see the
 // word block b(t) left for b(t+1).  The writer publishes with barrier + st.release; the reader acquires
 // and reads the state with ld.global.cg (L1 is not coherent across the grids).  Any other kernel / copy on the stream
-// never triggers early, so it still sees, and is seen by, whole step grids.
+// never triggers early, so it still sees, and is seen by, whole step grids.  (This flag protocol, run by thread 0, serves the
+// split and the multi-wave shapes; balanced single-wave grids use the counters of the courier warp below.)
 __device__ __forceinline__ void handover_acquire(int* ready, int* timeouts, int* err_flag) {
     int v = 0, spins = 0;
     do {
@@ -493,14 +508,35 @@ __device__ __forceinline__ void handover_acquire(int* ready, int* timeouts, int*
 __device__ __forceinline__ void handover_release(int* ready) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready), "r"(1) : "memory");
 }
-// Early hand-over (courier warp, see the kernel): a block publishes its env state BEFORE it writes the observation rows, so
-// its successor must not take "state ready" for "everything written".  A second word per block, `done`, is set when ALL
-// stores of the block are out; the successor's courier takes it (waits for 1, writes 0 — handover_acquire) before the
-// successor's own observation rows may be written (same addresses when the caller reuses one array).  No launch numbers:
-// a replayed CUDA graph repeats its kernel parameters.
-__device__ __forceinline__ void handover_publish_done(int* done) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(1) : "memory");
+// ---- courier warps: the same hand-over with COUNTERS instead of flags ----
+// A block publishes its env state BEFORE it writes the observation rows ("early hand-over", see the kernel), and a block lets
+// its dependents launch the moment it starts — so several generations of block b can be resident and waiting at once, which
+// a flag with one waiter cannot express.  Per block b, all monotonic (a replayed CUDA graph repeats its kernel parameters,
+// so nothing here comes from the host):
+//   T  tickets: instance k of block b takes k = T++ when it starts (before it lets the next grid launch, so tickets follow
+//      the launch order);
+//   S  states handed on: instance k waits for S >= k, and S becomes k + 1 when the state it left may be used — by the block
+//      itself as soon as the state is stored, or by the wrapper kernel's block in a wrapped control step;
+//   D  instances whose LAST store is out: instance k waits for D >= k before its own observation rows may be written
+//      (same addresses when the caller reuses one array);
+//   Tw / Dw  the wrapper kernel's tickets and the number of wrapped step instances that are through (qs_wrap_kernel).
+// At rest T = S = D and Tw = Dw; an unchained launch needs no special case.
+enum { HW_READY = 0, HW_T = 1, HW_S = 2, HW_D = 3, HW_TW = 4, HW_DW = 5, HW_ROWS = 6 };     // rows of DevState::ready, [E + 1] each
+__device__ __forceinline__ int* hw_word(const DevState& st, int E, int row) { return st.ready + (long long)row * (E + 1) + blockIdx.x; }
+__device__ __forceinline__ void counter_wait(const int* c, int want, int* timeouts, int* err_flag) {
+    int v = 0, spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        if (v - want < 0) __nanosleep(40);
+    } while (v - want < 0 && ++spins < (1 << 24));    // ~1 s: a lost hand-over must not hang the GPU
+    if (v - want < 0) {
+        atomicAdd(timeouts, 1);
+        if (err_flag != nullptr) *reinterpret_cast<volatile int*>(err_flag) = 1;
+        __threadfence_system();
+    }
 }
+__device__ __forceinline__ void counter_set(int* c, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c), "r"(v) : "memory"); }
+__device__ __forceinline__ void counter_inc(int* c) { asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(c), "r"(1) : "memory"); }
 __device__ __forceinline__ void bulk_drain_writes() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // physics warp -> shared hand-off arrays
@@ -539,6 +575,7 @@ template <int NP, bool SPLIT, bool SCN, bool HO, bool DYN = false>
 __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) float2 s_obst[];
     __shared__ int s_late;          // courier launches: a block with a goal event behind the observation is released at its end
+    __shared__ unsigned long long s_rows;      // courier launches: mbarrier, completes when the previous instance's observation rows are out
     const DevState& st = p.st;
     const int lane = threadIdx.x & 31;
     const int i = lane & (NP - 1);
@@ -554,43 +591,33 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
     const int env_local = tid / NP;
     const int env = blockIdx.x * envs_per_block + env_local;
     if (has_courier && (int)threadIdx.x >= work_threads) {
-        int* const ready = st.ready + blockIdx.x;
-        int* const done = st.ready + p.E + 1 + blockIdx.x;
-        int* const turn = st.ready + 2 * (p.E + 1) + blockIdx.x;      // wrapped control steps only, see below
-        // Inside qs_wrap_step (p.wrap_chain) the wrapper kernel's block b stands between this block and its successor: it
-        // takes `done` (everything of this step written), may rewrite the env state (replay) and releases `ready` itself.
-        // A third word, `turn`, is passed from step block b to step block b of the next control step (the wrapper kernel has
-        // its own): a block lets its dependents launch as soon as it holds its turn, i.e. when its predecessor of the SAME
-        // kind has finished — a whole control step before the dependent grid's block is needed, so that no launch waits for
-        // the slowest block of the grid in front of it.  Every word still has exactly one waiter at any time: a grid exists
-        // only after all blocks of the grid two launches before it have taken their turn.
+        int* const tmo = st.ready + p.E;
         const int nthr = (int)blockDim.x;
-        if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");      // after a foreign kernel: its writes formally visible
+        int k = 0;
         if (lane == 0) {
             s_late = 0;
-            handover_acquire(p.wrap_chain ? turn : ready, st.ready + p.E, st.err_flag);
+            mbar_init(&s_rows, 1);
+            k = atomicAdd(hw_word(st, p.E, HW_T), 1);                 // this instance's ticket ...
         }
-        named_arrive(1, nthr);                                        // wrapped chain: turn taken; else: the workers start loading the state
+        named_arrive(5, nthr);                                        // ... is taken before any thread of the block lets the next grid launch
         asm volatile("griddepcontrol.launch_dependents;");
-        if (p.wrap_chain) {
-            if (lane == 0) handover_acquire(ready, st.ready + p.E, st.err_flag);
-            named_arrive(4, nthr);                                    // the workers start loading the state
-        }
-        if (lane == 0 && !(p.wrap_chain && p.chained)) {
-            // the predecessor block's observation rows are complete: its `done` word is taken; after the grid-wide wait of
-            // an unchained launch everything before this grid is complete and the word is simply cleared.  (In a chain of
-            // wrapped steps the wrapper kernel has taken it.)
-            if (p.chained) handover_acquire(done, st.ready + p.E, st.err_flag);
-            else asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(done), "r"(0) : "memory");
+        if (lane == 0) counter_wait(hw_word(st, p.E, HW_S), k, tmo, st.err_flag);
+        named_arrive(1, nthr);                                        // the workers start loading the state
+        if (lane == 0) {
+            // the predecessor's observation rows are out (in a wrapped chain the wrapper kernel has waited for that)
+            if (!p.wrap_chain) counter_wait(hw_word(st, p.E, HW_D), k, tmo, st.err_flag);
+            mbar_arrive(&s_rows);
         }
         named_sync(2, nthr);                                          // the workers have stored the block's state (and do not wait here)
         const int late = *reinterpret_cast<volatile int*>(&s_late);
-        if (!late && lane == 0 && !p.wrap_chain) handover_release(ready);
+        // plain chain: the next instance may start.  Wrapped chain: the wrapper kernel's block hands the state on.
+        if (!late && lane == 0 && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k + 1);
         named_sync(3, nthr);                                          // the workers' last stores (bulk copies drained) are issued
         if (lane == 0) {
-            handover_publish_done(done);
-            if (late && !p.wrap_chain) handover_release(ready);
-            if (p.wrap_chain) handover_release(turn);
+            counter_set(hw_word(st, p.E, HW_D), k + 1);
+            if (late && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k + 1);
+            if (p.wrap_chain) counter_inc(hw_word(st, p.E, HW_DW));
         }
         return;
     }
@@ -617,9 +644,9 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         // it has completed; the wait makes its writes formally visible).  Chained step grids (qs_set_chained) skip it.
         if (!p.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (has_courier) {
-            named_sync(1, (int)blockDim.x);                          // the courier holds the block (wrapped chain: its turn)
+            named_sync(5, (int)blockDim.x);                          // the courier has taken the block's ticket
             asm volatile("griddepcontrol.launch_dependents;");
-            if (p.wrap_chain) named_sync(4, (int)blockDim.x);        // wrapped chain: the courier takes `ready` after its turn
+            named_sync(1, (int)blockDim.x);                          // the state of the previous instance has been handed on
         } else {
             if (threadIdx.x == 0) handover_acquire(st.ready + blockIdx.x, st.ready + p.E, st.err_flag);
             __syncthreads();
@@ -1202,6 +1229,8 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
                 // the state open: such a block (rare) is released at the end.
                 if (dev_scn && scn_ev && !kicked) *reinterpret_cast<volatile int*>(&s_late) = 1;
                 named_arrive(2, (int)blockDim.x);
+                // the rows of the previous instance are out (checked by the courier long ago: this does not spin in practice)
+                mbar_wait(&s_rows, 0);
             }
         }
 

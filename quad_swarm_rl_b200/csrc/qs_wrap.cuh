@@ -437,12 +437,14 @@ template <int NP>
 __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ WrapParams q) {
     const DevState& st = q.sp.st;
     QS_WTL(0);
-    int* const turn = st.ready + 3 * (q.sp.E + 1) + blockIdx.x;
     if (q.chain) {
-        if (threadIdx.x == 0) handover_acquire(turn, st.ready + q.sp.E, st.err_flag);        // block b of the previous wrapper grid is through
+        // instance j of wrapper block b (ticket from Tw) waits for the j-th wrapped step instance of block b to be through
+        // (Dw > j); its own predecessor finished before that step instance could start (counters: qs_step.cuh)
+        __shared__ int s_ticket;
+        if (threadIdx.x == 0) s_ticket = atomicAdd(hw_word(st, q.sp.E, HW_TW), 1);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
-        if (threadIdx.x == 0) handover_acquire(st.ready + q.sp.E + 1 + blockIdx.x, st.ready + q.sp.E, st.err_flag);      // `done` of step block b
+        if (threadIdx.x == 0) counter_wait(hw_word(st, q.sp.E, HW_DW), s_ticket + 1, st.ready + q.sp.E, st.err_flag);
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.launch_dependents;");
@@ -456,10 +458,7 @@ __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ Wr
     QS_WTL(2);
     if (q.chain) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            handover_release(st.ready + blockIdx.x);
-            handover_release(turn);
-        }
+        if (threadIdx.x == 0) counter_inc(hw_word(st, q.sp.E, HW_S));          // the block's state goes to the next step instance
     }
     QS_WTL(3);
 }
