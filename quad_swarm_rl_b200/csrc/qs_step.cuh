@@ -611,12 +611,13 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         }
         named_sync(2, nthr);                                          // the workers have stored the block's state (and do not wait here)
         const int late = *reinterpret_cast<volatile int*>(&s_late);
+        const int k1 = (int)((unsigned)k + 1u);                       // the counters wrap around after 2^32 steps; waits compare differences
         // plain chain: the next instance may start.  Wrapped chain: the wrapper kernel's block hands the state on.
-        if (!late && lane == 0 && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k + 1);
+        if (!late && lane == 0 && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k1);
         named_sync(3, nthr);                                          // the workers' last stores (bulk copies drained) are issued
         if (lane == 0) {
-            counter_set(hw_word(st, p.E, HW_D), k + 1);
-            if (late && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k + 1);
+            counter_set(hw_word(st, p.E, HW_D), k1);
+            if (late && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k1);
             if (p.wrap_chain) counter_inc(hw_word(st, p.E, HW_DW));
         }
         return;

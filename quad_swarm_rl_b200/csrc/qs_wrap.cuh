@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ Wr
         if (threadIdx.x == 0) s_ticket = atomicAdd(hw_word(st, q.sp.E, HW_TW), 1);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
-        if (threadIdx.x == 0) counter_wait(hw_word(st, q.sp.E, HW_DW), s_ticket + 1, st.ready + q.sp.E, st.err_flag);
+        if (threadIdx.x == 0) counter_wait(hw_word(st, q.sp.E, HW_DW), (int)((unsigned)s_ticket + 1u), st.ready + q.sp.E, st.err_flag);
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.launch_dependents;");
