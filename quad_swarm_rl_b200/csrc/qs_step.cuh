@@ -519,9 +519,10 @@ __device__ __forceinline__ void handover_release(int* ready) {
 //      itself as soon as the state is stored, or by the wrapper kernel's block in a wrapped control step;
 //   D  instances whose LAST store is out: instance k waits for D >= k before its own observation rows may be written
 //      (same addresses when the caller reuses one array);
-//   Tw / Dw  the wrapper kernel's tickets and the number of wrapped step instances that are through (qs_wrap_kernel).
-// At rest T = S = D and Tw = Dw; an unchained launch needs no special case.
-enum { HW_READY = 0, HW_T = 1, HW_S = 2, HW_D = 3, HW_TW = 4, HW_DW = 5, HW_ROWS = 6 };     // rows of DevState::ready, [E + 1] each
+//   Tw / Dw / Rw  the wrapper kernel's tickets, the number of wrapped step instances whose state (and rewards, dones, reward
+//      terms) is stored, and the number of those whose last store is out (qs_wrap_kernel).
+// At rest T = S = D and Tw = Dw = Rw; an unchained launch needs no special case.
+enum { HW_READY = 0, HW_T = 1, HW_S = 2, HW_D = 3, HW_TW = 4, HW_DW = 5, HW_RW = 6, HW_ROWS = 7 };     // rows of DevState::ready, [E + 1] each
 __device__ __forceinline__ int* hw_word(const DevState& st, int E, int row) { return st.ready + (long long)row * (E + 1) + blockIdx.x; }
 __device__ __forceinline__ void counter_wait(const int* c, int want, int* timeouts, int* err_flag) {
     int v = 0, spins = 0;
@@ -612,13 +613,18 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         named_sync(2, nthr);                                          // the workers have stored the block's state (and do not wait here)
         const int late = *reinterpret_cast<volatile int*>(&s_late);
         const int k1 = (int)((unsigned)k + 1u);                       // the counters wrap around after 2^32 steps; waits compare differences
-        // plain chain: the next instance may start.  Wrapped chain: the wrapper kernel's block hands the state on.
-        if (!late && lane == 0 && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k1);
+        // plain chain: the next instance may start.  Wrapped chain: the wrapper kernel's block may start on the stored state
+        // (it waits for Rw where it needs this step's observation rows, and before it hands the state on).
+        if (!late && lane == 0) {
+            if (p.wrap_chain) counter_inc(hw_word(st, p.E, HW_DW)); else counter_set(hw_word(st, p.E, HW_S), k1);
+        }
         named_sync(3, nthr);                                          // the workers' last stores (bulk copies drained) are issued
         if (lane == 0) {
+            if (p.wrap_chain) {
+                if (late) counter_inc(hw_word(st, p.E, HW_DW));
+                counter_inc(hw_word(st, p.E, HW_RW));
+            } else if (late) counter_set(hw_word(st, p.E, HW_S), k1);
             counter_set(hw_word(st, p.E, HW_D), k1);
-            if (late && !p.wrap_chain) counter_set(hw_word(st, p.E, HW_S), k1);
-            if (p.wrap_chain) counter_inc(hw_word(st, p.E, HW_DW));
         }
         return;
     }

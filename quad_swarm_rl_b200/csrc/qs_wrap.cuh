@@ -84,9 +84,25 @@ struct WrapView {
     const float* terms;          // [A][QS_NUM_TERMS] written by the step of this control step
     const uint8_t* dones;        // [A]
     float* obs;                  // [A][D]  (rows of replayed envs are overwritten)
+    const int* rows;             // block-chained launch: counter Rw of the block (else null) and the value it must reach before rows
+    int rows_want;               // of q.obs are read or overwritten
 };
 
 __device__ __forceinline__ void agg_add(float* agg, int k, float v) { if (v != 0.f) atomicAdd(agg + k, v); }
+
+// Block-chained launch: the body starts when the step block has stored state, rewards, dones and reward terms; its
+// observation rows may still be on their way.  Called by whole warps right before they read or overwrite rows of q.obs.
+__device__ __forceinline__ void wait_rows(const WrapView& q) {
+    if (q.rows == nullptr) return;
+    if ((threadIdx.x & 31) == 0) {
+        int v = 0, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(q.rows) : "memory");
+            if (v - q.rows_want < 0) __nanosleep(40);
+        } while (v - q.rows_want < 0 && ++spins < (1 << 24));      // a lost count is caught (and reported) at the end of the kernel
+    }
+    __syncwarp();
+}
 
 // copy the rows of env `env` between the live state and snapshot slot `slot` (all lanes of the env take part)
 template <bool TO_SNAP>
@@ -339,6 +355,7 @@ __device__ __forceinline__ void wrap_body(const WrapView& q, int env, int i) {
     // 1. checkpoint every 0.5 s (not while replaying an event), :140-142
     const bool cp = running && active && !saved && tick > 0 && (tick % RP_CP_EVERY) == 0;
     if (__any_sync(0xffffffffu, cp)) {
+        wait_rows(q);
         if (cp) {
             snap_copy<true>(q, env, i, valid, rp.x, false);
             if (i == 0) agg_add(w.agg, WA_CHECKPOINTS, 1.0f);
@@ -375,6 +392,7 @@ __device__ __forceinline__ void wrap_body(const WrapView& q, int env, int i) {
     // 3. a finished env: can_drones_fly bookkeeping (quadrotor_multi.py:281-287,356-359), then a buffered event is replayed
     //    with probability p instead of the fresh episode the step kernel has already started (:167-209)
     if (__any_sync(0xffffffffu, env_done)) {
+        wait_rows(q);                                            // a replayed event overwrites rows of this step's observation
         float mean = 0.f;
         if (env_done && i == 0) {
             const float cn = __ldcg(w.crash_now + env) + crash;
@@ -436,11 +454,12 @@ __device__ __forceinline__ void wrap_body(const WrapView& q, int env, int i) {
 template <int NP>
 __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ WrapParams q) {
     const DevState& st = q.sp.st;
+    __shared__ int s_ticket;
     QS_WTL(0);
     if (q.chain) {
-        // instance j of wrapper block b (ticket from Tw) waits for the j-th wrapped step instance of block b to be through
-        // (Dw > j); its own predecessor finished before that step instance could start (counters: qs_step.cuh)
-        __shared__ int s_ticket;
+        // instance j of wrapper block b (ticket from Tw) waits for the j-th wrapped step instance of block b to have stored its
+        // state, rewards, dones and reward terms (Dw > j); its own predecessor finished before that step instance could start
+        // (counters: qs_step.cuh).  The step block may still be writing its observation rows: see wait_rows.
         if (threadIdx.x == 0) s_ticket = atomicAdd(hw_word(st, q.sp.E, HW_TW), 1);
         __syncthreads();
         asm volatile("griddepcontrol.launch_dependents;");
@@ -452,13 +471,18 @@ __global__ void __launch_bounds__(256) qs_wrap_kernel(const __grid_constant__ Wr
     }
     WrapView v;
     v.sp = &q.sp; v.w = &q.w; v.actions = q.sp.actions; v.terms = q.sp.rew_terms; v.dones = q.sp.dones; v.obs = q.sp.obs;
+    v.rows = q.chain ? hw_word(st, q.sp.E, HW_RW) : nullptr;
+    v.rows_want = q.chain ? (int)((unsigned)s_ticket + 1u) : 0;
     const int lane = threadIdx.x & 31;
     QS_WTL(1);
     wrap_body<NP>(v, blockIdx.x * (blockDim.x / NP) + threadIdx.x / NP, lane & (NP - 1));
     QS_WTL(2);
     if (q.chain) {
         __syncthreads();
-        if (threadIdx.x == 0) counter_inc(hw_word(st, q.sp.E, HW_S));          // the block's state goes to the next step instance
+        if (threadIdx.x == 0) {
+            counter_wait(hw_word(st, q.sp.E, HW_RW), v.rows_want, st.ready + q.sp.E, st.err_flag);      // the step block is through: its rows are out
+            counter_inc(hw_word(st, q.sp.E, HW_S));                  // the block's state goes to the next step instance
+        }
     }
     QS_WTL(3);
 }

@@ -631,12 +631,12 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     QS_ALLOC0(st.next_scn_f, sizeof(float4) * 3 * E);
     QS_ALLOC0(st.epi, sizeof(int2) * E);
     {   // per-block hand-over words (at most one block per env), all "ready"
-        // hand-over words per block, [6][E + 1] (rows HW_*, qs_step.cuh): the `ready` flag of the thread-0 hand-over (1) and the
-        // courier warps' counters T, S, D, Tw, Dw (0); [0][E] is the time-out counter
-        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * 6 * (E + 1)));
-        std::vector<int> init((size_t)6 * (E + 1), 0);
+        // hand-over words per block, [HW_ROWS][E + 1] (rows HW_*, qs_step.cuh): the `ready` flag of the thread-0 hand-over (1) and
+        // the courier warps' counters T, S, D, Tw, Dw, Rw (0); [0][E] is the time-out counter
+        QS_CUDA(cudaMalloc((void**)&st.ready, sizeof(int) * HW_ROWS * (E + 1)));
+        std::vector<int> init((size_t)HW_ROWS * (E + 1), 0);
         for (long long k = 0; k < E; ++k) init[(size_t)k] = 1;
-        QS_CUDA(cudaMemcpy(st.ready, init.data(), sizeof(int) * 6 * (E + 1), cudaMemcpyHostToDevice));
+        QS_CUDA(cudaMemcpy(st.ready, init.data(), sizeof(int) * HW_ROWS * (E + 1), cudaMemcpyHostToDevice));
     }
     // rotation = identity so that a never-reset env still holds a valid state
     {
