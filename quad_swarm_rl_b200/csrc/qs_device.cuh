@@ -128,6 +128,7 @@ struct StepParams {
     int chained;                        // 1: the stream predecessor of this launch is a step grid of the same handle (qs_set_chained):
     int courier;            // per-block hand-over with a courier warp (last warp of the block, no envs): early release of the state
     int wrap_chain;         // courier launch inside qs_wrap_step: block-chained with the wrapper kernel (see qs_wrap_kernel)
+    int poll_mode;          // how the courier polls for its turn (counter_wait, QS_POLL)
                                         //    actions are prefetched before the dependency wait; hand-over kernels skip the grid-wide wait
     int scenario, grid_l, grid_w;       // QS_SCENARIO_*, pillar grid cells along x / y
     int pdl_mode;                       // 0 off, 1 trigger dependents at kernel start, 2 trigger before the final stores,

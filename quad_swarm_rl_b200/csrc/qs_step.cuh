@@ -524,12 +524,23 @@ __device__ __forceinline__ void handover_release(int* ready) {
 // At rest T = S = D and Tw = Dw = Rw; an unchained launch needs no special case.
 enum { HW_READY = 0, HW_T = 1, HW_S = 2, HW_D = 3, HW_TW = 4, HW_DW = 5, HW_RW = 6, HW_ROWS = 7 };     // rows of DevState::ready, [E + 1] each
 __device__ __forceinline__ int* hw_word(const DevState& st, int E, int row) { return st.ready + (long long)row * (E + 1) + blockIdx.x; }
-__device__ __forceinline__ void counter_wait(const int* c, int want, int* timeouts, int* err_flag) {
+// mode (tuning, QS_POLL): bits 0-7 = nanoseconds to sleep between two polls, bit 8 = poll with relaxed loads and fence once at
+// the end (an ld.acquire is LDG.STRONG + CCTL.IVALL: every poll then invalidates the SM's L1, also for the co-resident CTA)
+__device__ __forceinline__ void counter_wait(const int* c, int want, int* timeouts, int* err_flag, int mode = 40) {
     int v = 0, spins = 0;
-    do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
-        if (v - want < 0) __nanosleep(40);
-    } while (v - want < 0 && ++spins < (1 << 24));    // ~1 s: a lost hand-over must not hang the GPU
+    const unsigned ns = (unsigned)(mode & 0xff);
+    if (mode & 0x100) {
+        do {
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            if (v - want < 0 && ns) __nanosleep(ns);
+        } while (v - want < 0 && ++spins < (1 << 24));
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    } else {
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            if (v - want < 0 && ns) __nanosleep(ns);
+        } while (v - want < 0 && ++spins < (1 << 24));    // ~1 s: a lost hand-over must not hang the GPU
+    }
     if (v - want < 0) {
         atomicAdd(timeouts, 1);
         if (err_flag != nullptr) *reinterpret_cast<volatile int*>(err_flag) = 1;
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(NP >= 16 ? 128 : QS_LB) qs_step_kernel(const _
         }
         named_arrive(5, nthr);                                        // ... is taken before any thread of the block lets the next grid launch
         asm volatile("griddepcontrol.launch_dependents;");
-        if (lane == 0) counter_wait(hw_word(st, p.E, HW_S), k, tmo, st.err_flag);
+        if (lane == 0) counter_wait(hw_word(st, p.E, HW_S), k, tmo, st.err_flag, p.poll_mode);
         named_arrive(1, nthr);                                        // the workers start loading the state
         if (lane == 0) {
             // the predecessor's observation rows are out (in a wrapped chain the wrapper kernel has waited for that)

@@ -483,6 +483,9 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // inside qs_wrap_step the stream predecessor that counts is the block-chained wrapper kernel of the previous control step
     p.chained = (h->chained && (h->in_wrap_step ? h->last_was_wrap : h->last_was_step)) ? 1 : 0;
     p.wrap_chain = (h->in_wrap_step && courier) ? 1 : 0;
+    static int poll_mode = -1;
+    if (poll_mode < 0) { const char* e = getenv("QS_POLL"); poll_mode = e ? atoi(e) : 40; }
+    p.poll_mode = poll_mode;
     h->step_wrap_chain = p.wrap_chain;
     h->wrap_block = work_warps * 32;
 #ifdef QS_TIMELINE
