@@ -384,7 +384,16 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     StepParams p = p_in;
     choose_obs_writeout(h, p, obs_in_device_memory);
     const long long phys_warps = ((long long)h->cfg.num_envs * h->NP + 31) / 32;
-    const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148);
+    // A chained handle whose batch gives every SM at least two warps steps faster in the balanced shape with a courier warp
+    // (below) than in the split shape: c2 (1024 envs x 8 drones) 7.03 -> 6.42 us per step.
+    static int courier_env = -1;
+    if (courier_env < 0) { const char* e = getenv("QS_COURIER"); courier_env = e ? atoi(e) : 1; }
+    int sms = 0;
+    QS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int wpc_all = (int)((phys_warps + sms - 1) / sms);
+    const bool courier_shape = h->chained && courier_env && h->NP < 16 && h->st.dyn == nullptr && wpc_all >= 2 &&
+                               (wpc_all + 1) * 32 <= QS_LB && ((wpc_all * 32) % h->NP) == 0;
+    const bool want_split = h->split_mode == 1 || (h->split_mode == -1 && phys_warps <= 4 * 148 && !courier_shape);
     const bool split = want_split && p.obs_stage && h->NP > 1 && h->st.dyn == nullptr && !h->obst_random;
     // QS_BALANCE=1 (experiment): one CTA per SM, ceil(warps / SMs) warps each — every SM then holds the same number of warps
     // whatever the CTA scheduler does while two step grids overlap (the timeline of the debug build showed SMs with 6 CTAs
@@ -395,9 +404,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     if (h->NP >= 16 && kBlock > 128) kBlock = 128;          // launch bounds of the NP >= 16 instantiations
     bool balanced = false;
     if (balance && !split && h->NP < 16) {
-        int sms = 0;
-        QS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        const int wpc = (int)((phys_warps + sms - 1) / sms);
+        const int wpc = wpc_all;
         // measured: c5 (8 x 4096, K = 6, staggered resets) 13.7 -> 10.0 us per step, c3 unchanged
         if (wpc >= 2 && wpc * 32 <= QS_LB && ((wpc * 32) % h->NP) == 0) { kBlock = wpc * 32; balanced = true; }
     }
@@ -411,8 +418,6 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     // carries no envs and does the hand-over's flag traffic — acquire of the predecessor's state word, early release of
     // this block's state (before the observation is built), the `done` word that orders the observation rows of consecutive
     // steps.  Measured (profiles/r02_notes.md): c3 10.0 -> 8.5 us per step, c5 9.3 -> 8.6.  QS_COURIER=0 switches it off.
-    static int courier_env = -1;
-    if (courier_env < 0) { const char* e = getenv("QS_COURIER"); courier_env = e ? atoi(e) : 1; }
     if (h->handover < 0 && balanced)          // decided before the first launch so that every grid of a chain has the same shape
         h->handover = pdl_env >= 0 ? (pdl_env == 3) : ((courier_env && kBlock + 32 <= QS_LB) || h->cfg.use_obstacles != 0);
     const bool courier = balanced && courier_env && h->handover == 1 && h->chained && h->st.dyn == nullptr && kBlock + 32 <= QS_LB;
@@ -503,7 +508,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
     KernelFn fn = fn_dyn ? fn_dyn : (use_ho ? fn_ho : fn_wait);
-    if (smem > 48 * 1024) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem + 1024 > 48 * 1024) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // + the kernel's static words
     static int carve = -2;          // QS_CARVEOUT (experiment): preferred shared-memory carve-out in % for the step and wrapper kernels
     if (carve == -2) { const char* e = getenv("QS_CARVEOUT"); carve = e ? atoi(e) : -1; }
     if (carve >= 0) QS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));

@@ -317,7 +317,8 @@ C4 = dict(num_agents=32, neighbor_visible_num=6, obs_repr='xyz_vxyz_R_omega')
 
 @pytest.mark.parametrize('name,kw,E,dev_scn,pdl,chained', [
     ('c3_handover', C3, 4096, 'o_random', '3', True), ('c3_auto', C3, 4096, 'o_random', None, True),
-    ('c2_split_handover', C2, 1024, 'swap_goals', None, True), ('c4_multiwave_handover', C4, 2048, 'swarm_vs_swarm', None, True),
+    ('c2_split_handover', C2, 1024, 'swap_goals', None, True), ('c2_courier', C2, 1024, 'swap_goals', None, True),
+    ('c4_multiwave_handover', C4, 2048, 'swarm_vs_swarm', None, True),
     ('c3_small', C3, 37, None, '3', True), ('c3_wait', C3, 300, None, '2', True),
     ('c3_unchained', C3, 4096, 'o_random', None, False), ('c4_unchained', C4, 2048, 'swarm_vs_swarm', None, False),
     ('c2_vector_stores', C2, 1024, 'swap_goals', None, True)])
@@ -328,6 +329,8 @@ def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, ch
     from quad_swarm_rl_b200.engine import QuadSwarmEngine
     if pdl is not None:
         monkeypatch.setenv('QS_PDL', pdl)           # read by each engine at its first step launch
+    if 'split' in name:
+        monkeypatch.setenv('QS_SPLIT', '1')         # a chained handle of this size would use the balanced shape with a courier warp
     if name.endswith('vector_stores'):
         monkeypatch.setenv('QS_OBS_BULK', '0')      # observation tiles leave with vector stores instead of the copy engine
     T, R = 96, 3
