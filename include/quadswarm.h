@@ -79,7 +79,11 @@ extern "C" {
 #define QS_SCENARIO_O_DYNAMIC_SAME_GOAL 13
 #define QS_SCENARIO_O_SWAP_GOALS 14
 #define QS_SCENARIO_O_EP_RAND_BEZIER 15
-#define QS_SCENARIO_LAST QS_SCENARIO_O_EP_RAND_BEZIER
+/* scenarios/run_away.py: a shuffled goal formation around (0, 0, 2); every second (tick % 100 == 0, tick > 0) the goals of
+ * drones 0 and 1 jump onto the goals of two random drones drawn from 1..N-1 (run_away.py:14-25).  Obstacle-free family,
+ * not part of `mix` (scenarios/utils.py:7-10); needs num_agents >= 2, as the reference's randint(1, N). */
+#define QS_SCENARIO_RUN_AWAY 16
+#define QS_SCENARIO_LAST QS_SCENARIO_RUN_AWAY
 #define QS_SCENARIO_DEVICE_FAMILY_FIRST QS_SCENARIO_STATIC_SAME_GOAL
 
 /* reward coefficient slots: the subset of QuadrotorEnvMulti.rew_coeff (quadrotor_multi.py:91-94) with a

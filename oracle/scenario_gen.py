@@ -203,16 +203,18 @@ class DeviceORandomSource:
 STATIC_SAME_GOAL, STATIC_DIFF_GOAL, DYNAMIC_SAME_GOAL, DYNAMIC_DIFF_GOAL, SWAP_GOALS, DYNAMIC_FORMATIONS, \
     EP_LISSAJOUS3D, SWARM_VS_SWARM, MIX = range(2, 11)
 EP_RAND_BEZIER = 12
+RUN_AWAY = 16
 SV_BEZIER, BEZIER_STEPS, BEZIER_MAX_TRIES = 64, 500, 512
 MODE_NAMES = {STATIC_SAME_GOAL: 'static_same_goal', STATIC_DIFF_GOAL: 'static_diff_goal',
               DYNAMIC_SAME_GOAL: 'dynamic_same_goal', DYNAMIC_DIFF_GOAL: 'dynamic_diff_goal', SWAP_GOALS: 'swap_goals',
               DYNAMIC_FORMATIONS: 'dynamic_formations', EP_LISSAJOUS3D: 'ep_lissajous3D',
-              SWARM_VS_SWARM: 'swarm_vs_swarm', MIX: 'mix', EP_RAND_BEZIER: 'ep_rand_bezier'}
+              SWARM_VS_SWARM: 'swarm_vs_swarm', MIX: 'mix', EP_RAND_BEZIER: 'ep_rand_bezier', RUN_AWAY: 'run_away'}
 MODE_IDS = {v: k for k, v in MODE_NAMES.items()}
 FORMATION_NAMES = ('circle_horizontal', 'circle_vertical_xz', 'circle_vertical_yz', 'sphere',
                    'grid_horizontal', 'grid_vertical_xz', 'grid_vertical_yz', 'cube')          # utils.py:24-25
 
 SV_MIX, SV_PERIOD, SV_FORMATION, SV_SIZE, SV_LAYER, SV_CX, SV_CY, SV_CZ, SV_DIST, SV_PHI, SV_THETA, SV_GROW, SV_SPEED = range(13)
+SV_RUN0, SV_RUN1 = 13, 14
 SV_SHUFFLE = 16
 STREAM_RESET, STREAM_TICK = 1, 2
 NEVER = 0x7fffffff
@@ -362,6 +364,8 @@ class DeviceScenarioSource:
         if mode in (DYNAMIC_SAME_GOAL, DYNAMIC_DIFF_GOAL, SWAP_GOALS, SWARM_VS_SWARM):
             s['period'] = 400 + _pk(d, STREAM_RESET, SV_PERIOD, 200)
             s['next'] = s['period']
+        elif mode == RUN_AWAY:
+            s['period'], s['next'] = 100, 100           # run_away.py:15-18: every second, never at tick 0
         if svs:
             c1 = np.array([-BOX + 2.0 * BOX * _u(d, STREAM_RESET, SV_CX), -BOX + 2.0 * BOX * _u(d, STREAM_RESET, SV_CY),
                            z_above_ground(_u(d, STREAM_RESET, SV_CZ), N, fm['per_layer'], fm['f'], fm['size'])])
@@ -404,6 +408,12 @@ class DeviceScenarioSource:
         g = self.goals
         if mode == SWAP_GOALS:
             g = np.array([g[shuffle_rank(d, STREAM_TICK, i, 0, N)] for i in range(N)])
+        elif mode == RUN_AWAY:
+            # run_away.py:19-24: goals[0] = goals[g0]; goals[1] = goals[g1] with g0, g1 ~ randint(1, N)
+            g = np.array(g, dtype=np.float64)
+            g0, g1 = 1 + _pk(d, STREAM_TICK, SV_RUN0, N - 1), 1 + _pk(d, STREAM_TICK, SV_RUN1, N - 1)
+            g[0] = g[g0]
+            g[1] = g[g1]
         elif mode == DYNAMIC_SAME_GOAL:
             s['c1'] = np.array([-BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CX), -BOX + 2.0 * BOX * _u(d, STREAM_TICK, SV_CY),
                                 max(0.25, (-0.5 * BOX + BOX * _u(d, STREAM_TICK, SV_CZ)) + 2.0)])

@@ -24,7 +24,7 @@ SCENARIO_HOST_TABLES, SCENARIO_O_RANDOM = 0, 1
 DEVICE_SCENARIOS = {'o_random': 1, 'static_same_goal': 2, 'static_diff_goal': 3, 'dynamic_same_goal': 4,
                     'dynamic_diff_goal': 5, 'swap_goals': 6, 'dynamic_formations': 7, 'ep_lissajous3D': 8,
                     'swarm_vs_swarm': 9, 'mix': 10, 'o_static_same_goal': 11, 'ep_rand_bezier': 12,
-                    'o_dynamic_same_goal': 13, 'o_swap_goals': 14, 'o_ep_rand_bezier': 15}
+                    'o_dynamic_same_goal': 13, 'o_swap_goals': 14, 'o_ep_rand_bezier': 15, 'run_away': 16}
 OBSTACLE_SCENARIOS = ('o_random', 'o_static_same_goal', 'o_dynamic_same_goal', 'o_swap_goals', 'o_ep_rand_bezier')
 SCENARIO_NAMES = {v: k for k, v in DEVICE_SCENARIOS.items()}
 

@@ -23,7 +23,8 @@ namespace qs {
 // draw slots (v) inside a stream
 enum ScnSlot {
     SV_MIX = 0, SV_PERIOD = 1, SV_FORMATION = 2, SV_SIZE = 3, SV_LAYER = 4, SV_CX = 5, SV_CY = 6, SV_CZ = 7,
-    SV_DIST = 8, SV_PHI = 9, SV_THETA = 10, SV_GROW = 11, SV_SPEED = 12, SV_SHUFFLE = 16,     // SV_SHUFFLE + drone index
+    SV_DIST = 8, SV_PHI = 9, SV_THETA = 10, SV_GROW = 11, SV_SPEED = 12, SV_RUN0 = 13, SV_RUN1 = 14,
+    SV_SHUFFLE = 16,        // SV_SHUFFLE + drone index
     SV_BEZIER = 64          // + 8 * try + j: six direction uniforms (j = 0..5) and the distance draw (j = 6) of a rejection try
 };
 constexpr int BEZIER_STEPS = 500;      // int(num_secs * control_freq), ep_rand_bezier.py:13-14
@@ -260,6 +261,8 @@ __device__ __noinline__ ScnOut scenario_reset(RngKey key, int cfg_mode, int N, i
     if (s.mode == QS_SCENARIO_DYNAMIC_SAME_GOAL || s.mode == QS_SCENARIO_DYNAMIC_DIFF_GOAL || s.mode == QS_SCENARIO_SWAP_GOALS || svs) {
         s.period = 400 + scn_pick(key, SCN_STREAM_RESET, SV_PERIOD, 200);       // int(U(4, 6) s * 100 Hz)
         s.next = s.period;
+    } else if (s.mode == QS_SCENARIO_RUN_AWAY) {
+        s.period = 100; s.next = 100;                                           // run_away.py:15-18: every second, never at tick 0
     }
     ScnOut o;
     if (svs) {
@@ -299,10 +302,13 @@ __device__ __noinline__ ScnOut scenario_tick(RngKey key, int N, int i, int tick,
     s.mode = -1;
     if (active) s = scn_load(st, env);
     // swap_goals.py: goals are permuted among the drones
-    const int src = (active && s.mode == QS_SCENARIO_SWAP_GOALS) ? shuffle_rank(key, SCN_STREAM_TICK, i, 0, N) : i;
+    int src = (active && s.mode == QS_SCENARIO_SWAP_GOALS) ? shuffle_rank(key, SCN_STREAM_TICK, i, 0, N) : i;
+    // run_away.py:19-24: goals[0] = goals[g0], goals[1] = goals[g1] with g0, g1 ~ randint(1, N): neither reads goals[0], so
+    // the two sequential assignments equal one gather of the old goals
+    if (active && s.mode == QS_SCENARIO_RUN_AWAY && i < 2 && N >= 2) src = 1 + scn_pick(key, SCN_STREAM_TICK, i == 0 ? SV_RUN0 : SV_RUN1, N - 1);
     const float gx = shfl<NP>(goal.x, src), gy = shfl<NP>(goal.y, src), gz = shfl<NP>(goal.z, src);
     if (active) {
-        if (s.mode == QS_SCENARIO_SWAP_GOALS) {
+        if (s.mode == QS_SCENARIO_SWAP_GOALS || s.mode == QS_SCENARIO_RUN_AWAY) {
             o.goal.x = gx; o.goal.y = gy; o.goal.z = gz;
         } else if (s.mode == QS_SCENARIO_DYNAMIC_SAME_GOAL) {
             s.c1.x = -SCN_BOX + 2.0f * SCN_BOX * scn_u(key, SCN_STREAM_TICK, SV_CX);

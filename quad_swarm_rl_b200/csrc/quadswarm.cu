@@ -449,7 +449,7 @@ static int launch_step(QsHandle* h, const StepParams& p_in, cudaStream_t s, bool
     const bool ticked_obst = p.scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL && p.scenario <= QS_SCENARIO_O_EP_RAND_BEZIER;
     const bool scn = p.use_obst ? ticked_obst
                                 : ((p.scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && p.scenario <= QS_SCENARIO_MIX) ||
-                                   p.scenario == QS_SCENARIO_EP_RAND_BEZIER);
+                                   p.scenario == QS_SCENARIO_EP_RAND_BEZIER || p.scenario == QS_SCENARIO_RUN_AWAY);
     KernelFn fn_wait = nullptr, fn_ho = nullptr;
     int rc = dispatch_np(h->NP, [&](auto np) {
         constexpr int NPv = decltype(np)::value;
@@ -570,12 +570,14 @@ extern "C" int qs_create(const QsConfig* cfg, int device, QsHandle** out) {
     if (cfg->ep_time <= 0.f) return fail(QS_ERR_INVALID_ARG, "ep_time must be positive");
     if (cfg->scenario < QS_SCENARIO_HOST_TABLES || cfg->scenario > QS_SCENARIO_LAST)
         return fail(QS_ERR_INVALID_ARG, "unknown scenario");
-    if (((cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->scenario < QS_SCENARIO_MIX) || cfg->scenario == QS_SCENARIO_EP_RAND_BEZIER) &&
-        cfg->use_obstacles)
+    if (((cfg->scenario >= QS_SCENARIO_DEVICE_FAMILY_FIRST && cfg->scenario < QS_SCENARIO_MIX) || cfg->scenario == QS_SCENARIO_EP_RAND_BEZIER ||
+         cfg->scenario == QS_SCENARIO_RUN_AWAY) && cfg->use_obstacles)
         return fail(QS_ERR_INVALID_ARG, "the device-side goal-formation scenarios are obstacle-free (use_obstacles must be 0)");
     if ((cfg->scenario == QS_SCENARIO_O_STATIC_SAME_GOAL || cfg->scenario == QS_SCENARIO_O_RANDOM ||
-         cfg->scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL) && !cfg->use_obstacles)
+         (cfg->scenario >= QS_SCENARIO_O_DYNAMIC_SAME_GOAL && cfg->scenario <= QS_SCENARIO_O_EP_RAND_BEZIER)) && !cfg->use_obstacles)
         return fail(QS_ERR_INVALID_ARG, "the o_* scenarios need use_obstacles");
+    if (cfg->scenario == QS_SCENARIO_RUN_AWAY && cfg->num_agents < 2)
+        return fail(QS_ERR_INVALID_ARG, "run_away needs at least two drones (run_away.py:20 draws randint(1, num_agents))");
     if (cfg->use_obstacles && cfg->scenario != QS_SCENARIO_HOST_TABLES) {
         const int cells = cfg->obst_grid[0] * cfg->obst_grid[1];
         if (cfg->obst_grid[0] < 1 || cfg->obst_grid[1] < 1 || cells > 64)

@@ -484,7 +484,8 @@ class QuadrotorEnvMultiBatched(_EnvBase):
         # family and mix without; every other mode uses host tables
         dev_scn = None
         if device_scenarios and quads_mode in L.DEVICE_SCENARIOS and \
-                (quads_mode == 'mix' or (quads_mode in L.OBSTACLE_SCENARIOS) == bool(use_obstacles)):
+                (quads_mode == 'mix' or (quads_mode in L.OBSTACLE_SCENARIOS) == bool(use_obstacles)) and \
+                not (quads_mode == 'run_away' and num_agents < 2):      # host class: fails at the first event, as the reference
             dev_scn = quads_mode
         super().__init__(num_envs, num_agents, ep_time, rew_coeff, obs_repr, neighbor_visible_num, neighbor_obs_type,
                          collision_hitbox_radius, collision_falloff_radius, use_obstacles, obst_density, obst_size,

@@ -258,12 +258,12 @@ def test_device_side_ticked_obstacle_scenarios_match_twin(scenario, n):
 
 
 DEVICE_FAMILY = ['static_same_goal', 'static_diff_goal', 'dynamic_same_goal', 'dynamic_diff_goal', 'swap_goals',
-                 'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix', 'ep_rand_bezier']
+                 'dynamic_formations', 'ep_lissajous3D', 'swarm_vs_swarm', 'mix', 'ep_rand_bezier', 'run_away']
 
 
 @pytest.mark.parametrize('mode', DEVICE_FAMILY)
 def test_device_side_scenario_family_matches_twin(mode):
-    """QS_SCENARIO_STATIC_SAME_GOAL .. QS_SCENARIO_MIX: formation picks, goal formations and the timed / per-tick goal
+    """QS_SCENARIO_STATIC_SAME_GOAL .. QS_SCENARIO_MIX, EP_RAND_BEZIER, RUN_AWAY (an event every second): formation picks, goal formations and the timed / per-tick goal
     changes happen inside the kernels and equal oracle/scenario_gen.py (same keyed draws); the trajectory — goals
     included, compared every step — stays in parity across goal events and auto-resets."""
     from oracle.scenario_gen import DeviceScenarioSource
@@ -279,7 +279,8 @@ def test_device_side_scenario_family_matches_twin(mode):
         assert all(o.source.events >= 1 for o in pair.oracles)
     es, _ = pair.engine.episode_stats()
     names = {int(x) for x in es[:, 12].cpu().numpy()}
-    assert names <= (set(range(2, 10)) | {12}) and (mode == 'mix' or names == {pu.L.DEVICE_SCENARIOS[mode]})
+    assert names <= (set(range(2, 10)) | {12, 16}) and (mode == 'mix' or names == {pu.L.DEVICE_SCENARIOS[mode]})
+    assert mode != 'mix' or 16 not in names                                  # run_away is not one of mix's modes (utils.py:7-10)
     pair.engine.close()
 
 

@@ -361,3 +361,55 @@ def test_obstacle_episode_law_equals_host_generator():
     assert _p_discrete(np.array(hc), np.array(tc), 64) > 1e-3
     assert _p_discrete(np.array(hspawn), np.array(tspawn), 64) > 1e-3
     assert _p_cont(np.array(hz), np.array(tz)) > 1e-3
+
+
+def test_run_away_twin_follows_the_reference_schedule_and_draw_range():
+    """oracle/scenario_gen.py's run_away (twin of the kernels') against scenarios/run_away.py:14-25 as restated by the
+    reference-pinned host class (scenarios.RunAway, replayed against the reference in
+    test_oracle_vs_reference.py[run_away_5]): an event at every tick that is a positive multiple of 100 and at no other
+    tick; drones 0 and 1 take goals that drones 1..N-1 held before the event, the rest keep theirs; the two draws are
+    uniform over 1..N-1 and never 0 (counted at the first event of an episode, where all goals are still distinct)."""
+    N = 5
+    cfg = pc.cfg_to_oracle(dict(num_agents=N, obs_repr='xyz_vxyz_R_omega', neighbor_visible_num=2, ep_time=4.2))
+    counts = np.zeros((2, N), dtype=int)
+    for env_id in range(150):
+        src = sg.DeviceScenarioSource('run_away')
+        env = qo.OracleEnv(cfg, qo.PhiloxRng(23), src, env_id=env_id)
+        env.reset()
+        assert src.name() == 'Scenario_run_away' and src.s['mode'] == sg.RUN_AWAY
+        g_prev = np.array([d.goal for d in env.drones])
+        assert len({tuple(np.round(g, 9)) for g in g_prev}) == N          # a formation of N distinct points (size >= 5 arms)
+        assert np.abs(g_prev[:, :2].mean(axis=0)).max() < 1.0             # around the centre (0, 0, 2), run_away.py:31
+        T = 400 if env_id < 10 else 100
+        for t in range(1, T + 1):
+            env.step(np.zeros((N, 4)))
+            g = np.array([d.goal for d in env.drones])
+            if t % 100 == 0:
+                assert np.array_equal(g[2:], g_prev[2:])
+                for k in (0, 1):
+                    hit = [j for j in range(1, N) if np.array_equal(g[k], g_prev[j])]
+                    assert hit, (env_id, t, k)
+                    if t == 100:
+                        assert len(hit) == 1
+                        counts[k, hit[0]] += 1
+            else:
+                assert np.array_equal(g, g_prev), (env_id, t)
+            g_prev = g
+        assert src.events == T // 100
+    assert counts[:, 0].sum() == 0 and (counts.sum(axis=1) == 150).all()
+    # 150 first events per drone over 4 sources: 37.5 expected each, sigma 5.3
+    assert counts[:, 1:].min() > 12 and counts[:, 1:].max() < 65, counts
+
+
+def test_run_away_host_class_draws_the_same_range():
+    rs = np.random.RandomState(4)
+    sc = hs.RunAway(5, rng=rs)
+    sc.reset()
+    seen = set()
+    for k in range(1, 60):
+        before = sc.goals.copy()
+        sc.step(100 * k)
+        for d in (0, 1):
+            seen |= {j for j in range(5) if np.array_equal(sc.goals[d], before[j])}
+        assert np.array_equal(sc.goals[2:], before[2:])
+    assert 0 not in seen or len({tuple(g) for g in sc.goals}) < 5      # index 0 is never a source (equal goals aside)
