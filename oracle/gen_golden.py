@@ -109,6 +109,11 @@ CASES = [
     dict(name='o_ep_rand_bezier_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=6.4, use_obstacles=True,
                                             quads_mode='o_ep_rand_bezier', obs_repr='xyz_vxyz_R_omega_floor'),
          T=700, seed=104, obs_stride=20),
+    # more drones than one warp: pins the oracle for the N > 32 work (48 drones converging on one goal and a planted
+    # cluster: collision rows wider than 32 bits, K-nearest among 47 candidates, the flattened-id novelty quirk)
+    dict(name='swarm_48_downwash', kw=dict(num_agents=48, neighbor_visible_num=6, ep_time=0.7, use_downwash=True,
+                                           quads_mode='static_same_goal'), T=100, seed=111, obs_stride=5,
+         plant='cluster', plant_at=[30]),
     # other physical models: per-drone constants derived by the reference are stored in the fixture
     dict(name='defaultquad_4', kw=dict(num_agents=4, neighbor_visible_num=2, ep_time=1.0, quads_mode='static_diff_goal',
                                        dynamics_params='DefaultQuad'), T=130, seed=101, obs_stride=1, plant='room4', plant_at=[30]),
