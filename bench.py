@@ -365,6 +365,7 @@ class StepRunner:
         self.done = torch.empty((P, E, self.N), dtype=torch.uint8, device=dev)
         self.counter = 0
         self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))       # set_state / the action ring were enqueued on the default stream
         self.graphs = []
         with torch.cuda.stream(self.stream):
             for _ in range(3):

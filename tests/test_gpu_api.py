@@ -287,6 +287,7 @@ def test_chained_step_grids_into_one_output_array(E, dev_scn):
     e1.set_chained(True); e2.set_chained(True)
     a = _actions(T, E, N)
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())     # the tables / actions above were enqueued on the default stream
     with torch.cuda.stream(st):
         e1.reset()
         e1.step(a[0])
@@ -342,6 +343,7 @@ def test_back_to_back_step_grids_equal_one_rollout(name, kw, E, dev_scn, pdl, ch
                                                     # separate template instances: identical source, but only equal builds are bit-equal)
     a = _actions(T, E, N)
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())     # the tables / actions above were enqueued on the default stream
     obs = torch.empty((T, E, N, e1.D), device='cuda'); rew = torch.empty((T, E, N), device='cuda')
     dn = torch.empty((T, E, N), dtype=torch.uint8, device='cuda')
     with torch.cuda.stream(st):

@@ -293,6 +293,7 @@ def test_block_chained_wrapped_steps_equal_synchronised_ones():
         e.set_chained(True)
         e.reset()
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())     # resets / actions above were enqueued on the default stream
     with torch.cuda.stream(st):
         e1.wrap_step(a[0])
         st.synchronize()
